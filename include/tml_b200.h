@@ -1,0 +1,117 @@
+/* tml_b200 — C ABI of the B200-native PGD-immunization hot path.
+ *
+ * Plain C, opaque handle, caller-owned device buffers, explicit cudaStream_t (passed as void*),
+ * fully asynchronous (no internal synchronisation), int status (0 = ok, <0 = error, message from
+ * tml_last_error()).  No C++ exceptions and no torch types cross this boundary.
+ * One handle per device; a handle is not thread-safe, distinct handles are.
+ *
+ * The reference (OrLichter/tml_image_editing_defense) is pure Python with no FFI of its own; each
+ * entry point below names the reference call site it replaces (file:line in /root/reference).
+ * The ctypes binding a maintainer of the reference would add is in INTEGRATION.md and implemented
+ * in tml_image_editing_defense_b200/_lib.py.
+ */
+#ifndef TML_B200_H
+#define TML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct TmlEncoder TmlEncoder;
+
+/* AutoencoderKL encoder configuration (diffusers config.json fields). */
+typedef struct TmlEncoderCfg {
+    int in_channels;            /* 3 */
+    int latent_channels;        /* 4 */
+    int num_blocks;             /* 4 */
+    int block_out_channels[8];  /* 128,256,512,512 */
+    int layers_per_block;       /* 2 */
+    int norm_num_groups;        /* 32 */
+    float norm_eps;             /* 1e-6 */
+    int mid_block_add_attention;/* 1 */
+} TmlEncoderCfg;
+
+enum { TML_DTYPE_F32 = 0, TML_DTYPE_BF16 = 1, TML_DTYPE_F16 = 2 };
+enum { TML_LOSS_L2NORM = 0, TML_LOSS_MSE = 1 };
+
+const char* tml_last_error(void);
+int tml_version(void);
+
+/* ---- encoder: replaces pipeline.vae.encode(...) (main.py:75,191; old/train_noise.py:133;
+ *      pipelines/pipeline_stable_diffusion_img2img.py:751,756) and its autograd backward
+ *      (torch.autograd.grad(loss,[cur_image]), main.py:176). ---- */
+int tml_encoder_create(const TmlEncoderCfg* cfg, int device, TmlEncoder** out);
+void tml_encoder_destroy(TmlEncoder* enc);
+/* Register one tensor of the diffusers state dict ("encoder.conv_in.weight", "quant_conv.bias", ...;
+ * legacy attention names query/key/value/proj_attn are accepted).  ptr may be host or device memory. */
+int tml_encoder_set_weight(TmlEncoder* enc, const char* diffusers_key, const void* ptr, int dtype,
+                           const int64_t* shape, int ndim);
+/* Repack to bf16 K-major GEMM operands (forward and input-gradient forms), fold quant_conv into
+ * conv_out, upload.  Must be called once after all weights are set. */
+int tml_encoder_finalize(TmlEncoder* enc, void* stream);
+/* Bytes of scratch (`ws`) and of forward->backward state (`saved`) for a [B,3,H,W] batch. */
+int tml_encoder_query(TmlEncoder* enc, int B, int H, int W, size_t* workspace_bytes, size_t* saved_bytes);
+/* x: fp32 NCHW [B,3,H,W] -> moments: fp32 NCHW [B, 2*latent, H/8, W/8] (quant_conv output). */
+int tml_encoder_forward(TmlEncoder* enc, const float* x_nchw, int B, int H, int W, float* moments_nchw, void* saved,
+                        void* ws, void* stream);
+/* dmoments: fp32 NCHW [B,2*latent,H/8,W/8] -> dx = beta*dx + dLoss/dx, fp32 NCHW [B,3,H,W].
+ * beta = 1 accumulates the grad_reps of main.py:88-102 in place. */
+int tml_encoder_backward(TmlEncoder* enc, const float* dmoments_nchw, int B, int H, int W, const void* saved,
+                         float* dx_nchw, float beta, void* ws, void* stream);
+
+/* ---- posterior sample + latent loss + gradient: replaces latent_dist.sample() (main.py:191),
+ *      (output_latent - target_latent).norm(p=2) (main.py:162, kind 0) and F.mse_loss
+ *      (losses/losses.py:39-41, kind 1).  noise may be NULL (-> latent_dist.mode()).
+ *      z_out, loss_per_image, dmoments may be NULL.  dmoments = grad_scale * dloss_b/dmoments. ---- */
+int tml_latent_loss(int kind, const float* moments, const float* noise, const float* target, int B, int h, int w,
+                    float grad_scale, float* z_out, float* loss_per_image, float* dmoments, void* stream);
+
+/* ---- PGD updates: replace Trainer.perturbation_step (main.py:248-276). ---- */
+/* linf branch, main.py:272-274; in place on x_adv; bit-exact with the ATen sequence. */
+int tml_pgd_step_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
+                      int64_t n, void* stream);
+/* l2 branch, main.py:254-268; mask [B,1,H,W] or NULL; ws of tml_pgd_l2_workspace(B) bytes. */
+size_t tml_pgd_l2_workspace(int B);
+int tml_pgd_step_l2(float* x_adv, const float* grad, const float* x, const float* mask, float eps, float step,
+                    float lo, float hi, int B, int C, int64_t hw, void* ws, void* stream);
+
+/* ---- universal perturbation (old/train_noise.py:127-185) ---- */
+/* out[b] = x[b] + delta                                   (:132) */
+int tml_add_delta(const float* x, const float* delta, float* out, int B, int64_t per_image, void* stream);
+/* out = scale * sum_b g[b]   (fixed summation order)      (gradient of the shared delta) */
+int tml_batch_sum(const float* g, float* out, int B, int64_t per_image, float scale, void* stream);
+/* L2-normalised step, clamp to +-eps, optional image-range projection (:173-185); ws >= 1 KiB. */
+int tml_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
+                       float hi, int64_t n, void* ws, void* stream);
+
+/* ---- introspection / test hooks ---- */
+/* number of kernels launched by this library since load: [0] tcgen05 GEMMs, [1] all other kernels */
+void tml_launch_counts(int64_t out[2]);
+/* 0 = tcgen05 kernel (default, the product path), 1 = SIMT debug kernel (tests only) */
+void tml_debug_set_gemm_impl(int impl);
+/* Generic implicit-GEMM entry used by the kernel unit tests (same operation the encoder issues). */
+typedef struct TmlGemmDesc {
+    const void* A; int A_C, A_W, A_H, A_B; int64_t A_sW, A_sH, A_sB;
+    int stride, ntaps; int dh[9], dw[9]; int OW, OH;
+    const void* Bm; int N; int64_t B_sN, B_sBatch;
+    float alpha; const float* bias; const void* resid; int64_t R_sB, R_sH, R_sW;
+    void* D; int out_fp32; int64_t D_sB, D_sH, D_sW, D_sN; int n_store;
+} TmlGemmDesc;
+int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
+/* Offsets (bytes into `saved`) and [B,H,W,C] dims of the bf16 NHWC activations the forward keeps:
+ * "conv_in", "resnet_h1"/"resnet_out" (index = resnet in forward order), "down_out", "attn_qkv",
+ * "attn_P" ([B,tok,tok,1]), "attn_out". */
+int tml_debug_saved_tensor(TmlEncoder* enc, const char* name, int index, size_t* offset, int dims[4]);
+/* Every backward stage copies its output gradient (bf16 NHWC) into slot k of dev_buffer (NULL = off). */
+void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots);
+/* Host-only helpers (no CUDA calls) used by the CPU tests of the weight packing. */
+int tml_debug_pack_conv3x3(const float* w /*[Co][Ci][3][3]*/, int Co, int Ci, int mode /*0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity (ph,pw)=(0,0),(0,1),(1,0),(1,1)*/,
+                           uint16_t* out_bf16, int* ntaps, int* dh, int* dw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TML_B200_H */

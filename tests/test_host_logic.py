@@ -1,0 +1,131 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the
+weight packing + tap tables reproduce conv forward / input-gradient semantics, configs, sharding."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import emulate_gemm, pack_conv3x3, rel_err
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def test_library_exports_every_declared_symbol():
+    from tml_image_editing_defense_b200 import _lib
+    lib = _lib.load()
+    header = (ROOT / "include" / "tml_b200.h").read_text()
+    declared = set(re.findall(r"\b(tml_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tml_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.tml_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tml_image_editing_defense_b200 import _lib
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    with pytest.raises(_lib.TmlError):
+        AutoencoderKL()
+    from tml_image_editing_defense_b200 import ops
+    with pytest.raises(_lib.TmlError):
+        ops.pgd_step_linf_(torch.zeros(4), torch.zeros(4), torch.zeros(4), 0.1, 0.01, -1, 1)
+
+
+@pytest.mark.parametrize("ci,co", [(8, 16), (16, 8)])
+def test_pack_forward_s1_matches_conv2d(ci, co):
+    g = torch.Generator().manual_seed(0)
+    w = bf16_round(torch.randn(co, ci, 3, 3, generator=g))
+    x = bf16_round(torch.randn(2, ci, 8, 16, generator=g))
+    mat, dh, dw = pack_conv3x3(w, 0)
+    y = emulate_gemm(x.permute(0, 2, 3, 1), mat, dh, dw, 1, 8, 16).permute(0, 3, 1, 2)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    assert rel_err(y, ref) < 1e-12
+
+
+def test_pack_forward_s2_matches_padded_conv2d():
+    g = torch.Generator().manual_seed(1)
+    w = bf16_round(torch.randn(8, 8, 3, 3, generator=g))
+    x = bf16_round(torch.randn(2, 8, 16, 16, generator=g))
+    mat, dh, dw = pack_conv3x3(w, 2)
+    y = emulate_gemm(x.permute(0, 2, 3, 1), mat, dh, dw, 2, 8, 8).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), w.double(), stride=2)
+    assert rel_err(y, ref) < 1e-12
+
+
+def test_pack_dgrad_s1_matches_autograd():
+    g = torch.Generator().manual_seed(2)
+    ci, co = 8, 16
+    w = bf16_round(torch.randn(co, ci, 3, 3, generator=g))
+    x = torch.randn(2, ci, 8, 8, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = bf16_round(torch.randn(2, co, 8, 8, generator=g))
+    (ref,) = torch.autograd.grad(F.conv2d(x, w.double(), padding=1), x, dy.double())
+    mat, dh, dw = pack_conv3x3(w, 1)
+    dx = emulate_gemm(dy.permute(0, 2, 3, 1), mat, dh, dw, 1, 8, 8).permute(0, 3, 1, 2)
+    assert rel_err(dx, ref) < 1e-12
+
+
+def test_pack_dgrad_s2_parity_matches_autograd():
+    g = torch.Generator().manual_seed(3)
+    c = 8
+    w = bf16_round(torch.randn(c, c, 3, 3, generator=g))
+    x = torch.randn(2, c, 16, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = bf16_round(torch.randn(2, c, 8, 8, generator=g))
+    (ref,) = torch.autograd.grad(F.conv2d(F.pad(x, (0, 1, 0, 1)), w.double(), stride=2), x, dy.double())
+    dx = torch.zeros(2, 16, 16, c, dtype=torch.float64)
+    for q in range(4):
+        ph, pw = q >> 1, q & 1
+        mat, dh, dw = pack_conv3x3(w, 3 + q)
+        assert len(dh) == (2 - ph) * (2 - pw)
+        dx[:, ph::2, pw::2] = emulate_gemm(dy.permute(0, 2, 3, 1), mat, dh, dw, 1, 8, 8)
+    assert rel_err(dx.permute(0, 3, 1, 2), ref) < 1e-12
+
+
+def test_trainconfig_mirrors_reference_override():
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    c = TrainConfig(norm_type="l2", eps=1.0, step_size=1.0, grad_reps=1)
+    assert (c.eps, c.step_size, c.grad_reps) == (32, 7.5, 10)          # configs.py:152-155
+    c = TrainConfig(norm_type="linf")
+    assert (c.eps, c.step_size, c.grad_reps) == (0.1, 0.006, 5)        # configs.py:156-159
+    c = TrainConfig(norm_type="linf", eps=32 / 255, step_size=4 / 255, grad_reps=1, override_from_norm_type=False)
+    assert c.eps == 32 / 255 and c.grad_reps == 1
+    with pytest.raises(ValueError):
+        TrainConfig(apply_loss_on_images=False, apply_loss_on_latents=False)
+
+
+def test_shard_indices_partition():
+    from tml_image_editing_defense_b200.dataset import shard_indices, shard_counts, SyntheticImageDataset
+    for n in (0, 1, 7, 64):
+        for w in (1, 2, 4, 8):
+            parts = [shard_indices(n, r, w) for r in range(w)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert [len(p) for p in parts] == shard_counts(n, w)
+    ds = SyntheticImageDataset(5, resolution=8, seed=3)
+    a = ds.batch([1, 3])
+    assert torch.equal(a[1], ds.image(3)) and a.min() >= -1 and a.max() < 1
+
+
+def test_losses_mirror_reference(golden_dir):
+    from tml_image_editing_defense_b200 import losses
+    d = np.load(golden_dir / "losses.npz")
+    a, b = torch.from_numpy(d["a"]), torch.from_numpy(d["b"])
+    assert torch.equal(losses.perturbation_loss(a, b), torch.from_numpy(d["perturbation_loss"]))
+    assert torch.equal(losses.LpDistance(2)(a, b), torch.from_numpy(d["l2_distance"]))
+    assert torch.equal(losses.LpDistance(float("inf"))(a, b), torch.from_numpy(d["linf_distance"]))
+    assert torch.equal(losses.LpRegularization(2)([a, b]), torch.from_numpy(d["l2_regularization"]))
+    assert torch.equal(losses.CosineSimilarity()(a, b), torch.from_numpy(d["cosine"]))
+
+
+def test_parser_flag_names():
+    from tml_image_editing_defense_b200.parser import parse_args
+    a = parse_args(["--resolution", "1024", "--train_batch_size", "4", "--seed", "7", "--mixed_precision", "bf16"])
+    assert a.resolution == 1024 and a.train_batch_size == 4 and a.seed == 7

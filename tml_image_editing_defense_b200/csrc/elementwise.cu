@@ -1,0 +1,845 @@
+// Bandwidth-bound kernels of the PGD hot path: conv_in (K=27) forward / input gradient, GroupNorm
+// (+SiLU) forward / backward, softmax forward / backward, transposes, posterior sample + latent loss
+// gradient, and the fused PGD updates.  All reductions are two-stage with a fixed order, so results
+// are bitwise reproducible run to run and independent of how images are sharded over GPUs.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <atomic>
+
+#include "kernels.h"
+
+namespace tml {
+
+static std::atomic<long> g_launches{0};
+long kernel_launch_count() { return g_launches.load(); }
+#define COUNT_LAUNCH() g_launches.fetch_add(1)
+
+constexpr int kNumSMs = 148;
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf_lo(u.x); f[1] = bf_hi(u.x); f[2] = bf_lo(u.y); f[3] = bf_hi(u.y);
+    f[4] = bf_lo(u.z); f[5] = bf_hi(u.z); f[6] = bf_lo(u.w); f[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Block-wide sum broadcast to every thread (blockDim.x multiple of 32, <= 1024); fixed order.
+__device__ __forceinline__ float block_sum(float v, float* red /*[33]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        float t = lane < nw ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+__device__ __forceinline__ double block_sum_d(double v, double* red /*[33]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum_d(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red /*[33]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        float t = lane < nw ? red[lane] : -INFINITY;
+        t = warp_max(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ================================================================================================
+// conv_in forward: fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,C0]      (diffusers
+// encoder.conv_in, reached from main.py:191).  K = 27 is far too thin for tensor cores: this is a
+// direct convolution whose cost is writing the bf16 output once.
+// Block: 256 threads = 16 channel octets x 16 pixel groups of 4 -> 64 pixels of one image row.
+// ================================================================================================
+template <int C0>
+__global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_kc,
+                                                          const float* __restrict__ bias, bf16* __restrict__ y, int H,
+                                                          int W) {
+    static_assert(C0 == 128, "conv_in kernel is specialised for 128 output channels");
+    __shared__ __align__(16) float sw[27 * C0];
+    __shared__ float sb[C0];
+    __shared__ float sx[3][3][66];
+    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 27 * C0; i += 256) sw[i] = w_kc[i];
+    for (int i = threadIdx.x; i < C0; i += 256) sb[i] = bias[i];
+    for (int i = threadIdx.x; i < 3 * 3 * 66; i += 256) {
+        const int col = i % 66, r = (i / 66) % 3, ci = i / (66 * 3);
+        const int ih = h + r - 1, iw = w0 + col - 1;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((size_t)(b * 3 + ci) * H + ih) * W + iw];
+        sx[ci][r][col] = v;
+    }
+    __syncthreads();
+    const int oct = threadIdx.x & 15, pg = threadIdx.x >> 4;
+    const int co0 = oct * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = sb[co0 + j];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int k = ci * 9 + r * 3 + s;
+                const float4 wa = *reinterpret_cast<const float4*>(&sw[k * C0 + co0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&sw[k * C0 + co0 + 4]);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float xv = sx[ci][r][pg * 4 + p + s];
+                    acc[p][0] = fmaf(xv, wa.x, acc[p][0]); acc[p][1] = fmaf(xv, wa.y, acc[p][1]);
+                    acc[p][2] = fmaf(xv, wa.z, acc[p][2]); acc[p][3] = fmaf(xv, wa.w, acc[p][3]);
+                    acc[p][4] = fmaf(xv, wb.x, acc[p][4]); acc[p][5] = fmaf(xv, wb.y, acc[p][5]);
+                    acc[p][6] = fmaf(xv, wb.z, acc[p][6]); acc[p][7] = fmaf(xv, wb.w, acc[p][7]);
+                }
+            }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int w = w0 + pg * 4 + p;
+        if (w < W) *reinterpret_cast<uint4*>(y + (((size_t)b * H + h) * W + w) * C0 + co0) = pack8(acc[p]);
+    }
+}
+
+void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf16* y, int B, int H, int W, int C0,
+                        cudaStream_t s) {
+    dim3 grid((W + 63) / 64, H, B);
+    conv_in_fwd_kernel<128><<<grid, 256, 0, s>>>(x, w_kc, bias, y, H, W);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// conv_in input gradient: bf16 NHWC dY [B,H,W,C0] -> fp32 NCHW dX [B,3,H,W]   (the tensor PGD
+// consumes; main.py:176).  One warp per 32 consecutive pixels of a row; lane = 4 channels; the 3
+// outputs per pixel are warp-reduced and parked in lane (pixel%32) so the final store is coalesced.
+// dX = beta*dX + result implements the grad_reps accumulation of main.py:88-102 in place.
+// ================================================================================================
+template <int C0>
+__global__ void __launch_bounds__(256) conv_in_dgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ w_kc,
+                                                            float* __restrict__ dx, float beta, int H, int W) {
+    static_assert(C0 == 128, "conv_in kernel is specialised for 128 output channels");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int w0 = (blockIdx.x * 8 + warp) * 32;
+    if (w0 >= W) return;
+    // weights for this lane's 4 channels: wr[ci][tap][j] = W[co=4*lane+j][ci][r][s]
+    float wr[3][9][4];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(&w_kc[(ci * 9 + t) * C0 + lane * 4]);
+            wr[ci][t][0] = v.x; wr[ci][t][1] = v.y; wr[ci][t][2] = v.z; wr[ci][t][3] = v.w;
+        }
+    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f;
+    for (int p = 0; p < 32; ++p) {
+        const int w = w0 + p;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (w < W) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int oh = h + 1 - r;
+                if (oh < 0 || oh >= H) continue;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int ow = w + 1 - s;
+                    if (ow < 0 || ow >= W) continue;
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(dy + (((size_t)b * H + oh) * W + ow) * C0 + lane * 4));
+                    const float g0 = bf_lo(u.x), g1 = bf_hi(u.x), g2 = bf_lo(u.y), g3 = bf_hi(u.y);
+                    const int t = r * 3 + s;
+                    a0 = fmaf(g0, wr[0][t][0], a0); a0 = fmaf(g1, wr[0][t][1], a0);
+                    a0 = fmaf(g2, wr[0][t][2], a0); a0 = fmaf(g3, wr[0][t][3], a0);
+                    a1 = fmaf(g0, wr[1][t][0], a1); a1 = fmaf(g1, wr[1][t][1], a1);
+                    a1 = fmaf(g2, wr[1][t][2], a1); a1 = fmaf(g3, wr[1][t][3], a1);
+                    a2 = fmaf(g0, wr[2][t][0], a2); a2 = fmaf(g1, wr[2][t][1], a2);
+                    a2 = fmaf(g2, wr[2][t][2], a2); a2 = fmaf(g3, wr[2][t][3], a2);
+                }
+            }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == p) { keep0 = a0; keep1 = a1; keep2 = a2; }
+    }
+    const int w = w0 + lane;
+    if (w < W) {
+        const size_t plane = (size_t)H * W;
+        float* o = dx + (size_t)b * 3 * plane + (size_t)h * W + w;
+        if (beta != 0.f) {
+            o[0] = fmaf(beta, o[0], keep0); o[plane] = fmaf(beta, o[plane], keep1); o[2 * plane] = fmaf(beta, o[2 * plane], keep2);
+        } else {
+            o[0] = keep0; o[plane] = keep1; o[2 * plane] = keep2;
+        }
+    }
+}
+
+void launch_conv_in_dgrad(const bf16* dy, const float* w_kc, float* dx, float beta, int B, int H, int W, int C0,
+                          cudaStream_t s) {
+    dim3 grid((W + 255) / 256, H, B);
+    conv_in_dgrad_kernel<128><<<grid, 256, 0, s>>>(dy, w_kc, dx, beta, H, W);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// GroupNorm (32 groups, affine) [+ SiLU] over bf16 NHWC.   diffusers ResnetBlock2D.norm1/norm2,
+// Attention.group_norm, Encoder.conv_norm_out.
+// Thread layout shared by the stats / apply / backward kernels: a block owns a contiguous chunk of
+// pixels of one image; thread = (channel octet, pixel lane); consecutive threads read consecutive
+// 16-byte vectors, so every access is a full 128-byte line.
+// ================================================================================================
+constexpr int kGnPixPerChunk = 512;
+int gn_num_chunks(int HW) { return (HW + kGnPixPerChunk - 1) / kGnPixPerChunk; }
+
+// partial[b][chunk][g] = (sum, sumsq) over the chunk's pixels of group g
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW,
+                                                       int C) {
+    __shared__ float red[256][4];
+    const int C8 = C >> 3, PL = 256 / C8;
+    const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
+    const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int p0 = chunk * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+    const bf16* base = x + (size_t)b * HW * C + (size_t)oct * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_lo += f[j]; q_lo = fmaf(f[j], f[j], q_lo); }
+#pragma unroll
+        for (int j = 4; j < 8; ++j) { s_hi += f[j]; q_hi = fmaf(f[j], f[j], q_hi); }
+    }
+    red[threadIdx.x][0] = s_lo; red[threadIdx.x][1] = q_lo; red[threadIdx.x][2] = s_hi; red[threadIdx.x][3] = q_hi;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int g = threadIdx.x, cpg = C / 32;
+        float s = 0.f, q = 0.f;
+        // half-octets (4 channels each) belonging to group g: [g*cpg/4, (g+1)*cpg/4)
+        for (int hq = g * cpg / 4; hq < (g + 1) * cpg / 4; ++hq) {
+            const int o = hq >> 1, half = hq & 1;
+            for (int l = 0; l < PL; ++l) {
+                s += red[l * C8 + o][half * 2];
+                q += red[l * C8 + o][half * 2 + 1];
+            }
+        }
+        float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+        out[0] = s;
+        out[1] = q;
+    }
+}
+
+void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s) {
+    dim3 grid(gn_num_chunks(HW), B);
+    gn_stats_kernel<<<grid, 256, 0, s>>>(x, partial, HW, C);
+    COUNT_LAUNCH();
+}
+
+// per image: group mean / rstd, then per channel scale = rstd*gamma, shift = beta - mean*scale
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float2* __restrict__ ss,
+                                                          float2* __restrict__ mr, int nchunks, int HW, int C,
+                                                          float eps) {
+    __shared__ float2 smr[32];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 32) {
+        const int g = threadIdx.x;
+        double s = 0.0, q = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+            const float* in = partial + (((size_t)b * nchunks + c) * 32 + g) * 2;
+            s += (double)in[0];
+            q += (double)in[1];
+        }
+        const double n = (double)HW * (C / 32);
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        smr[g] = make_float2((float)mean, rstd);
+        mr[(size_t)b * 32 + g] = smr[g];
+    }
+    __syncthreads();
+    const int cpg = C / 32;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float2 m = smr[c / cpg];
+        const float sc = m.y * gamma[c];
+        ss[(size_t)b * C + c] = make_float2(sc, beta[c] - m.x * sc);
+    }
+}
+
+void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
+                        int HW, int C, float eps, cudaStream_t s) {
+    gn_finalize_kernel<<<B, 256, 0, s>>>(partial, gamma, beta, ss, mr, gn_num_chunks(HW), HW, C, eps);
+    COUNT_LAUNCH();
+}
+
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ss,
+                                                       bf16* __restrict__ y, int HW, int C, int silu) {
+    const int C8 = C >> 3, PL = 256 / C8;
+    const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 v = __ldg(&ss[(size_t)b * C + oct * 8 + j]);
+        sc[j] = v.x; sh[j] = v.y;
+    }
+    const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = fmaf(f[j], sc[j], sh[j]);
+            f[j] = silu ? silu_f(v) : v;
+        }
+        *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = pack8(f);
+    }
+}
+
+void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s) {
+    dim3 grid(gn_num_chunks(HW), B);
+    gn_apply_kernel<<<grid, 256, 0, s>>>(x, ss, y, HW, C, silu);
+    COUNT_LAUNCH();
+}
+
+// d(act(u))/du for act = SiLU (u*sigmoid(u)) or identity
+__device__ __forceinline__ float dact(float u, int silu) {
+    if (!silu) return 1.f;
+    const float sg = 1.f / (1.f + __expf(-u));
+    return sg * fmaf(u, 1.f - sg, 1.f);
+}
+
+// partial[b][chunk][g] = (sum dxh, sum dxh*xh), dxh = dy*act'(u)*gamma, xh = (x-mean)*rstd
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                             const float2* __restrict__ ss,
+                                                             const float2* __restrict__ mr,
+                                                             const float* __restrict__ gamma,
+                                                             float* __restrict__ partial, int HW, int C, int silu) {
+    __shared__ float red[256][4];
+    const int C8 = C >> 3, PL = 256 / C8, cpg = C / 32;
+    const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
+    const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int p0 = chunk * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    float sc[8], sh[8], gm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 v = __ldg(&ss[(size_t)b * C + oct * 8 + j]);
+        sc[j] = v.x; sh[j] = v.y;
+        gm[j] = __ldg(&gamma[oct * 8 + j]);
+    }
+    const float2 m_lo = __ldg(&mr[(size_t)b * 32 + (oct * 8) / cpg]);
+    const float2 m_hi = __ldg(&mr[(size_t)b * 32 + (oct * 8 + 4) / cpg]);
+    float a_lo = 0.f, b_lo = 0.f, a_hi = 0.f, b_hi = 0.f;
+    const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        float fx[8], fd[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), fx);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C)), fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = fmaf(fx[j], sc[j], sh[j]);
+            const float dxh = fd[j] * dact(u, silu) * gm[j];
+            const float2 m = j < 4 ? m_lo : m_hi;
+            const float xh = (fx[j] - m.x) * m.y;
+            if (j < 4) { a_lo += dxh; b_lo = fmaf(dxh, xh, b_lo); }
+            else { a_hi += dxh; b_hi = fmaf(dxh, xh, b_hi); }
+        }
+    }
+    red[threadIdx.x][0] = a_lo; red[threadIdx.x][1] = b_lo; red[threadIdx.x][2] = a_hi; red[threadIdx.x][3] = b_hi;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int g = threadIdx.x;
+        float s = 0.f, q = 0.f;
+        for (int hq = g * cpg / 4; hq < (g + 1) * cpg / 4; ++hq) {
+            const int o = hq >> 1, half = hq & 1;
+            for (int l = 0; l < PL; ++l) {
+                s += red[l * C8 + o][half * 2];
+                q += red[l * C8 + o][half * 2 + 1];
+            }
+        }
+        float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+        out[0] = s;
+        out[1] = q;
+    }
+}
+
+void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
+                           float* partial, int B, int HW, int C, int silu, cudaStream_t s) {
+    dim3 grid(gn_num_chunks(HW), B);
+    gn_bwd_partial_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, gamma, partial, HW, C, silu);
+    COUNT_LAUNCH();
+}
+
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float2* __restrict__ mm, int nchunks,
+                                       int HW, int C, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = b*32 + g
+    if (i >= total) return;
+    const int b = i / 32, g = i % 32;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const float* in = partial + (((size_t)b * nchunks + c) * 32 + g) * 2;
+        s += (double)in[0];
+        q += (double)in[1];
+    }
+    const double n = (double)HW * (C / 32);
+    mm[i] = make_float2((float)(s / n), (float)(q / n));
+}
+
+void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, cudaStream_t s) {
+    const int total = B * 32;
+    gn_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partial, mm, gn_num_chunks(HW), HW, C, total);
+    COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                           const float2* __restrict__ ss,
+                                                           const float2* __restrict__ mr,
+                                                           const float2* __restrict__ mm,
+                                                           const float* __restrict__ gamma,
+                                                           const bf16* __restrict__ resid, bf16* __restrict__ dx,
+                                                           int HW, int C, int silu) {
+    const int C8 = C >> 3, PL = 256 / C8, cpg = C / 32;
+    const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    float sc[8], sh[8], gm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 v = __ldg(&ss[(size_t)b * C + oct * 8 + j]);
+        sc[j] = v.x; sh[j] = v.y;
+        gm[j] = __ldg(&gamma[oct * 8 + j]);
+    }
+    const int g_lo = (oct * 8) / cpg, g_hi = (oct * 8 + 4) / cpg;
+    const float2 m_lo = __ldg(&mr[(size_t)b * 32 + g_lo]), m_hi = __ldg(&mr[(size_t)b * 32 + g_hi]);
+    const float2 k_lo = __ldg(&mm[(size_t)b * 32 + g_lo]), k_hi = __ldg(&mm[(size_t)b * 32 + g_hi]);
+    const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        float fx[8], fd[8], fr[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), fx);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C)), fd);
+        if (resid != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(resid + base + (size_t)p * C)), fr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = fmaf(fx[j], sc[j], sh[j]);
+            const float dxh = fd[j] * dact(u, silu) * gm[j];
+            const float2 m = j < 4 ? m_lo : m_hi;
+            const float2 k = j < 4 ? k_lo : k_hi;
+            const float xh = (fx[j] - m.x) * m.y;
+            float v = m.y * (dxh - k.x - xh * k.y);
+            if (resid != nullptr) v += fr[j];
+            o[j] = v;
+        }
+        *reinterpret_cast<uint4*>(dx + base + (size_t)p * C) = pack8(o);
+    }
+}
+
+void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
+                         const float* gamma, const bf16* resid, bf16* dx, int B, int HW, int C, int silu,
+                         cudaStream_t s) {
+    dim3 grid(gn_num_chunks(HW), B);
+    gn_bwd_apply_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, mm, gamma, resid, dx, HW, C, silu);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// softmax over rows of fp32 logits -> bf16 probabilities; and its backward
+//   dS = P * (dP - sum_j P*dP) * scale         (diffusers Attention)
+// ================================================================================================
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+                                                           int cols) {
+    __shared__ float red[33];
+    const float* row = S + (size_t)blockIdx.x * cols;
+    bf16* out = P + (size_t)blockIdx.x * cols;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.f / sum;
+    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        uint2 o;
+        o.x = pack2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+        o.y = pack2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+        *reinterpret_cast<uint2*>(out + c) = o;
+    }
+}
+
+void launch_softmax_rows(const float* S, bf16* P, long long rows, int cols, cudaStream_t s) {
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(S, P, cols);
+    COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __restrict__ P, const float* __restrict__ dP,
+                                                               bf16* __restrict__ dS, float scale, int cols) {
+    __shared__ float red[33];
+    const bf16* prow = P + (size_t)blockIdx.x * cols;
+    const float* drow = dP + (size_t)blockIdx.x * cols;
+    bf16* out = dS + (size_t)blockIdx.x * cols;
+    float dot = 0.f;
+    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+        const uint2 u = *reinterpret_cast<const uint2*>(prow + c);
+        const float4 d = *reinterpret_cast<const float4*>(drow + c);
+        dot += bf_lo(u.x) * d.x + bf_hi(u.x) * d.y + bf_lo(u.y) * d.z + bf_hi(u.y) * d.w;
+    }
+    dot = block_sum(dot, red);
+    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+        const uint2 u = *reinterpret_cast<const uint2*>(prow + c);
+        const float4 d = *reinterpret_cast<const float4*>(drow + c);
+        uint2 o;
+        o.x = pack2(bf_lo(u.x) * (d.x - dot) * scale, bf_hi(u.x) * (d.y - dot) * scale);
+        o.y = pack2(bf_lo(u.y) * (d.z - dot) * scale, bf_hi(u.y) * (d.w - dot) * scale);
+        *reinterpret_cast<uint2*>(out + c) = o;
+    }
+}
+
+void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float scale, long long rows, int cols,
+                             cudaStream_t s) {
+    softmax_bwd_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, dS, scale, cols);
+    COUNT_LAUNCH();
+}
+
+// out[b][c][r] = in[b][r][c]
+__global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R,
+                                                        int C, long long ld_in, long long bs_in, long long ld_out,
+                                                        long long bs_out) {
+    __shared__ bf16 tile[32][34];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < R && c < C) tile[i][tx] = in[(size_t)b * bs_in + (size_t)r * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) out[(size_t)b * bs_out + (size_t)c * ld_out + r] = tile[tx][i];
+    }
+}
+
+void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
+                      long long ld_out, long long bs_out, cudaStream_t s) {
+    dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
+    transpose_kernel<<<grid, 256, 0, s>>>(in, out, R, C, ld_in, bs_in, ld_out, bs_out);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// Posterior sample + latent loss + gradient w.r.t. the moments  
+//   mean, logvar = chunk(moments); logvar = clamp(logvar,-30,20); z = mean + exp(.5 logvar)*eps
+//   kind 0: loss_b = ||z_b - t_b||_2          (main.py:162, per image)
+//   kind 1: loss_b = mean((z_b - t_b)^2)      (losses/losses.py:39-41)
+// One block per image; the per-image sum uses a fixed-order block reduction in double.
+// ================================================================================================
+__global__ void __launch_bounds__(256) latent_loss_kernel(int kind, const float* __restrict__ moments,
+                                                          const float* __restrict__ noise,
+                                                          const float* __restrict__ target, int hw, float grad_scale,
+                                                          float* __restrict__ z_out, float* __restrict__ loss,
+                                                          float* __restrict__ dmoments) {
+    __shared__ double red[33];
+    const int b = blockIdx.x;
+    const int n = 4 * hw;
+    const float* mom = moments + (size_t)b * 8 * hw;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float mu = mom[i];
+        const float lv = fminf(fmaxf(mom[n + i], -30.f), 20.f);
+        const float e = noise ? noise[(size_t)b * n + i] : 0.f;
+        const float z = fmaf(expf(0.5f * lv), e, mu);
+        if (z_out) z_out[(size_t)b * n + i] = z;
+        const float d = z - target[(size_t)b * n + i];
+        acc += (double)d * (double)d;
+    }
+    const double tot = block_sum_d(acc, red);
+    float coef, l;
+    if (kind == 0) {
+        l = (float)sqrt(tot);
+        coef = l > 0.f ? grad_scale / l : 0.f;
+    } else {
+        l = (float)(tot / (double)n);
+        coef = grad_scale * 2.f / (float)n;
+    }
+    if (threadIdx.x == 0 && loss) loss[b] = l;
+    if (dmoments == nullptr) return;
+    float* dm = dmoments + (size_t)b * 8 * hw;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float mu = mom[i];
+        const float lv_raw = mom[n + i];
+        const float lv = fminf(fmaxf(lv_raw, -30.f), 20.f);
+        const float e = noise ? noise[(size_t)b * n + i] : 0.f;
+        const float sd = expf(0.5f * lv);
+        const float z = fmaf(sd, e, mu);
+        const float dz = coef * (z - target[(size_t)b * n + i]);
+        dm[i] = dz;
+        dm[n + i] = (lv_raw >= -30.f && lv_raw <= 20.f) ? dz * e * sd * 0.5f : 0.f;
+    }
+}
+
+void launch_latent_loss(int kind, const float* moments, const float* noise, const float* target, int B, int h, int w,
+                        float grad_scale, float* z, float* loss, float* dmoments, cudaStream_t s) {
+    latent_loss_kernel<<<B, 256, 0, s>>>(kind, moments, noise, target, h * w, grad_scale, z, loss, dmoments);
+    COUNT_LAUNCH();
+}
+
+__global__ void dmoments_pack_kernel(const float* __restrict__ dm, bf16* __restrict__ out, int hw, long long total) {
+    // one thread per (pixel, octet) of the 64-channel padded NHWC tensor
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int oct = int(i & 7);
+    const long long pix = i >> 3;  // b*hw + p
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (oct == 0) {
+        const long long b = pix / hw, p = pix % hw;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = dm[(b * 8 + c) * hw + p];
+    }
+    *reinterpret_cast<uint4*>(out + pix * 64 + oct * 8) = pack8(f);
+}
+
+void launch_dmoments_pack(const float* dm, bf16* out, int B, int h, int w, cudaStream_t s) {
+    const long long total = (long long)B * h * w * 8;
+    dmoments_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dm, out, h * w, total);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// PGD updates (main.py:248-276).  L-inf: one fused, 16-byte vectorised, grid-stride
+// kernel — 16 B/element of HBM traffic (read X_adv, grad, X; write X_adv) instead of the 8 ATen
+// launches of the reference.  Bit-exact with the ATen sequence including its special values:
+// sign(+-0) = sign(NaN) = 0, minimum / maximum / clamp propagate NaN.
+// ================================================================================================
+__device__ __forceinline__ float sgn(float g) { return float(g > 0.f) - float(g < 0.f); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) { return (v != v) ? v : fminf(fmaxf(v, lo), hi); }
+
+__device__ __forceinline__ float linf_one(float xa, float g, float x, float eps, float step, float lo, float hi) {
+    float v = __fsub_rn(xa, __fmul_rn(sgn(g), step));       // X_adv - sign(grad)*step  (no fma contraction)
+    v = min_nan(max_nan(v, __fsub_rn(x, eps)), __fadd_rn(x, eps));
+    return clamp_nan(v, lo, hi);
+}
+
+__global__ void __launch_bounds__(256) pgd_linf_kernel(float* __restrict__ x_adv, const float* __restrict__ grad,
+                                                       const float* __restrict__ x, float eps, float step, float lo,
+                                                       float hi, long long n) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 a = reinterpret_cast<const float4*>(x_adv)[i];
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(grad) + i);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(x) + i);
+        a.x = linf_one(a.x, g.x, s.x, eps, step, lo, hi);
+        a.y = linf_one(a.y, g.y, s.y, eps, step, lo, hi);
+        a.z = linf_one(a.z, g.z, s.z, eps, step, lo, hi);
+        a.w = linf_one(a.w, g.w, s.w, eps, step, lo, hi);
+        reinterpret_cast<float4*>(x_adv)[i] = a;
+    }
+    // tail (n not a multiple of 4)
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+        x_adv[i] = linf_one(x_adv[i], grad[i], x[i], eps, step, lo, hi);
+}
+
+void launch_pgd_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
+                     long long n, cudaStream_t s) {
+    long long blocks = ((n >> 2) + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;  // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pgd_linf_kernel<<<(unsigned)blocks, 256, 0, s>>>(x_adv, grad, x, eps, step, lo, hi, n);
+    COUNT_LAUNCH();
+}
+
+// ---- L2: per-image gradient normalisation, optional mask, step, renorm projection, clamp ----
+constexpr int kL2Chunks = 64;
+size_t pgd_l2_workspace_bytes(int B, long long) { return (size_t)B * kL2Chunks * sizeof(double) * 2; }
+
+__global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* __restrict__ g, double* __restrict__ part,
+                                                       long long per_image) {
+    __shared__ double red[33];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const long long c0 = per_image * chunk / kL2Chunks, c1 = per_image * (chunk + 1) / kL2Chunks;
+    const float* p = g + (size_t)b * per_image;
+    double acc = 0.0;
+    for (long long i = c0 + threadIdx.x; i < c1; i += 256) acc += (double)p[i] * (double)p[i];
+    acc = block_sum_d(acc, red);
+    if (threadIdx.x == 0) part[(size_t)b * kL2Chunks + chunk] = acc;
+}
+
+__device__ __forceinline__ float l2_norm_from_parts(const double* part, int b) {
+    double s = 0.0;
+    for (int c = 0; c < kL2Chunks; ++c) s += part[(size_t)b * kL2Chunks + c];
+    return (float)sqrt(s);
+}
+
+// x_adv <- x_adv - g/(||g||+1e-10) [*mask] * step ; part2 <- partial ||x_adv - x||^2
+__global__ void __launch_bounds__(256) l2_step_kernel(float* __restrict__ x_adv, const float* __restrict__ g,
+                                                      const float* __restrict__ x, const float* __restrict__ mask,
+                                                      const double* __restrict__ part, double* __restrict__ part2,
+                                                      float step, long long per_image, long long hw) {
+    __shared__ double red[33];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const float denom = l2_norm_from_parts(part, b) + 1e-10f;
+    const long long c0 = per_image * chunk / kL2Chunks, c1 = per_image * (chunk + 1) / kL2Chunks;
+    const size_t off = (size_t)b * per_image;
+    double acc = 0.0;
+    for (long long i = c0 + threadIdx.x; i < c1; i += 256) {
+        float gn = __fdiv_rn(g[off + i], denom);
+        if (mask) gn = __fmul_rn(gn, mask[(size_t)b * hw + (i % hw)]);
+        const float v = __fsub_rn(x_adv[off + i], __fmul_rn(gn, step));
+        x_adv[off + i] = v;
+        const float d = __fsub_rn(v, x[off + i]);
+        acc += (double)d * (double)d;
+    }
+    acc = block_sum_d(acc, red);
+    if (threadIdx.x == 0) part2[(size_t)b * kL2Chunks + chunk] = acc;
+}
+
+// torch.renorm(d, 2, 0, eps): rows with norm > eps are scaled by eps/(norm+1e-7); then clamp(X + d)
+__global__ void __launch_bounds__(256) l2_project_kernel(float* __restrict__ x_adv, const float* __restrict__ x,
+                                                         const double* __restrict__ part2, float eps, float lo,
+                                                         float hi, long long per_image) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const float nrm = l2_norm_from_parts(part2, b);
+    const bool scale = nrm > eps;
+    const float factor = scale ? __fdiv_rn(eps, __fadd_rn(nrm, 1e-7f)) : 1.f;
+    const long long c0 = per_image * chunk / kL2Chunks, c1 = per_image * (chunk + 1) / kL2Chunks;
+    const size_t off = (size_t)b * per_image;
+    for (long long i = c0 + threadIdx.x; i < c1; i += 256) {
+        float d = __fsub_rn(x_adv[off + i], x[off + i]);
+        if (scale) d = __fmul_rn(d, factor);
+        x_adv[off + i] = clamp_nan(__fadd_rn(x[off + i], d), lo, hi);
+    }
+}
+
+void launch_pgd_l2(float* x_adv, const float* grad, const float* x, const float* mask, float eps, float step, float lo,
+                   float hi, int B, int C, long long hw, void* ws, cudaStream_t s) {
+    const long long per_image = (long long)C * hw;
+    double* part = reinterpret_cast<double*>(ws);
+    double* part2 = part + (size_t)B * kL2Chunks;
+    dim3 grid(kL2Chunks, B);
+    l2_sumsq_kernel<<<grid, 256, 0, s>>>(grad, part, per_image);
+    l2_step_kernel<<<grid, 256, 0, s>>>(x_adv, grad, x, mask, part, part2, step, per_image, hw);
+    l2_project_kernel<<<grid, 256, 0, s>>>(x_adv, x, part2, eps, lo, hi, per_image);
+    COUNT_LAUNCH(); COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// Universal perturbation helpers (old/train_noise.py:127-185)
+// ================================================================================================
+__global__ void add_delta_kernel(const float* __restrict__ x, const float* __restrict__ delta, float* __restrict__ out,
+                                 long long per_image, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride)
+        out[i] = __fadd_rn(x[i], delta[i % per_image]);   // :132  source_image + perturbation
+}
+void launch_add_delta(const float* x, const float* delta, float* out, int B, long long per_image, cudaStream_t s) {
+    const long long total = (long long)B * per_image;
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    add_delta_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, delta, out, per_image, total);
+    COUNT_LAUNCH();
+}
+
+// out[i] = scale * sum_b g[b][i], summed in image order (fixed order -> identical on every rank)
+__global__ void batch_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int B, long long per_image,
+                                 float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_image; i += stride) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += g[(size_t)b * per_image + i];
+        out[i] = acc * scale;
+    }
+}
+void launch_batch_sum(const float* g, float* out, int B, long long per_image, float scale, cudaStream_t s) {
+    long long blocks = (per_image + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    batch_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, out, B, per_image, scale);
+    COUNT_LAUNCH();
+}
+
+// delta <- clamp(delta - g/(||g||+1e-10)*step, -eps, eps); optional image-range re-projection
+__global__ void __launch_bounds__(256) universal_step_kernel(float* __restrict__ delta, const float* __restrict__ g,
+                                                             const float* __restrict__ source,
+                                                             const double* __restrict__ part, float eps, float step,
+                                                             float lo, float hi, long long n) {
+    const float denom = l2_norm_from_parts(part, 0) + 1e-10f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float d = __fsub_rn(delta[i], __fmul_rn(__fdiv_rn(g[i], denom), step));   // :173-177
+        d = clamp_nan(d, -eps, eps);                                              // :180
+        if (source) d = __fsub_rn(clamp_nan(__fadd_rn(source[i], d), lo, hi), source[i]);  // :183-185
+        delta[i] = d;
+    }
+}
+void launch_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
+                           float hi, long long n, void* ws, cudaStream_t s) {
+    double* part = reinterpret_cast<double*>(ws);
+    dim3 grid(kL2Chunks, 1);
+    l2_sumsq_kernel<<<grid, 256, 0, s>>>(grad, part, n);
+    long long blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    universal_step_kernel<<<(unsigned)blocks, 256, 0, s>>>(delta, grad, source, part, eps, step, lo, hi, n);
+    COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
+}  // namespace tml

@@ -1,0 +1,63 @@
+// Host-side description of one implicit-GEMM launch (convolution taps over an NHWC bf16 tensor,
+// plain GEMM, or batched GEMM) and the launchers for the tcgen05 kernel and the SIMT debug kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tml {
+
+constexpr int kMaxTaps = 9;
+
+// D[b, oh, ow, n] = alpha * sum_t sum_c A[b, oh*stride + dh[t], ow*stride + dw[t], c] * Bm[batch][n][t*A_C + c]
+//                   + bias[n] + resid[b, oh, ow, n]
+// Out-of-range A coordinates read as zero (that is the convolution padding).
+struct GemmOp {
+    // A operand: bf16, channel-contiguous (NHWC-like); strides in elements.
+    const void* A = nullptr;
+    int A_C = 0, A_W = 0, A_H = 0, A_B = 0;
+    int64_t A_sW = 0, A_sH = 0, A_sB = 0;
+    int stride = 1;  // 1 or 2
+    int ntaps = 1;
+    int dh[kMaxTaps] = {0}, dw[kMaxTaps] = {0};
+    int OW = 0, OH = 0;  // output pixels per image (M = A_B * OH * OW)
+    // B operand: bf16 [batch][N][Ktot], Ktot = ntaps * A_C, K contiguous.
+    const void* Bm = nullptr;
+    int N = 0;
+    int64_t B_sN = 0;      // row stride (elements)
+    int64_t B_sBatch = 0;  // 0: shared by all images (weights); else per-image operand
+    // Epilogue.
+    float alpha = 1.0f;
+    const float* bias = nullptr;   // [N] or null
+    const void* resid = nullptr;   // bf16, n contiguous; strides below
+    int64_t R_sB = 0, R_sH = 0, R_sW = 0;
+    void* D = nullptr;
+    int out_fp32 = 0;  // 0: bf16, 1: fp32
+    int64_t D_sB = 0, D_sH = 0, D_sW = 0, D_sN = 1;
+    int n_store = 0;  // store only columns n < n_store (0 = N)
+    const char* name = "";
+};
+
+// Derived tiling, shared by both kernels (the debug kernel ignores the tile fields).
+struct GemmTiling {
+    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages;
+    size_t smem_bytes;
+};
+
+// Returns 0 and fills `t`, or a negative value and sets the thread-local error message.
+int gemm_plan(const GemmOp& op, GemmTiling* t);
+
+// tcgen05/TMEM/TMA implicit-GEMM kernel (the product path).
+int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream);
+// Straightforward SIMT kernel with identical semantics: test/debug aid only (selected through
+// tml_debug_set_gemm_impl(1)); never used by default.
+int gemm_launch_simt(const GemmOp& op, cudaStream_t stream);
+
+int gemm_launch(const GemmOp& op, int num_sms, cudaStream_t stream);  // dispatches on the debug switch
+void gemm_set_impl(int impl);
+int gemm_get_impl();
+long gemm_launch_count();  // number of tcgen05 GEMM launches since process start
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+}  // namespace tml

@@ -1,0 +1,435 @@
+// Implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared
+//     memory ring; convolution taps are expressed as shifted TMA box origins on the NHWC tensor,
+//     the hardware zero-fills out-of-range pixels (= the conv padding), so no im2col buffer exists;
+//   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16 per instruction, bf16 x bf16 ->
+//     fp32) with the accumulator in TMEM, double buffered (2 x BN columns) so that the epilogue of
+//     tile i overlaps the main loop of tile i+1;
+//   * four epilogue warps read the accumulator with tcgen05.ld (thread = output pixel), apply
+//     alpha / bias / residual and store bf16 NHWC (16-byte vectors) or a strided fp32 layout;
+//   * persistent grid (one CTA per SM), static round-robin tile schedule, warp-specialised roles
+//     synchronised only through mbarriers.
+//
+// Replaces the cuDNN conv fwd/dgrad + cuBLAS linear calls PyTorch makes for the reference's
+// vae.encode (main.py:75,191) and its autograd backward (main.py:176).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace tml {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, C ABI returns negative codes)
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::atomic<int> g_impl{0};
+static std::atomic<long> g_tc_launches{0};
+void gemm_set_impl(int impl) { g_impl.store(impl); }
+int gemm_get_impl() { return g_impl.load(); }
+long gemm_launch_count() { return g_tc_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// tiling
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaM = 128;
+constexpr int kATileBytes = kUmmaM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kBarrierBytes = 256;
+constexpr int kThreads = 256;
+
+static int largest_divisor_le(int n, int cap, int multiple_of) {
+    for (int d = (cap < n ? cap : n); d >= 1; --d)
+        if (n % d == 0 && d % multiple_of == 0) return d;
+    return 0;
+}
+
+int gemm_plan(const GemmOp& op, GemmTiling* t) {
+    if (op.A_C % kBlockK != 0) { set_error("%s: A_C=%d is not a multiple of 64", op.name, op.A_C); return -1; }
+    if (op.N % 16 != 0) { set_error("%s: N=%d is not a multiple of 16", op.name, op.N); return -1; }
+    if (op.stride != 1 && op.stride != 2) { set_error("%s: stride %d unsupported", op.name, op.stride); return -1; }
+    if (op.ntaps < 1 || op.ntaps > kMaxTaps) { set_error("%s: ntaps=%d", op.name, op.ntaps); return -1; }
+    int TW = largest_divisor_le(op.OW, 128, 8);
+    if (TW == 0) { set_error("%s: output width %d has no tile width (multiple of 8, <=128)", op.name, op.OW); return -1; }
+    int TH = largest_divisor_le(op.OH, 128 / TW, 1);
+    if (op.stride == 2 && (op.A_W % 2 != 0)) { set_error("%s: stride-2 input width must be even", op.name); return -1; }
+    int BN = 0;
+    if (op.N % 256 == 0) BN = 256;
+    else if (op.N % 128 == 0) BN = 128;
+    else if (op.N <= 256) BN = op.N;
+    else { set_error("%s: N=%d unsupported (need N%%128==0 or N<=256)", op.name, op.N); return -1; }
+    t->TW = TW;
+    t->TH = TH;
+    t->rows_valid = TW * TH;
+    t->tiles_w = op.OW / TW;
+    t->tiles_h = op.OH / TH;
+    t->BN = BN;
+    t->n_tiles = op.N / BN;
+    t->kchunks = op.A_C / kBlockK;
+    int stage_bytes = kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
+    int stages = (kMaxSmem - 1024 - kBarrierBytes) / stage_bytes;
+    if (stages > 8) stages = 8;
+    int kblocks = op.ntaps * t->kchunks;
+    if (stages > kblocks && kblocks >= 2) stages = kblocks;
+    if (stages < 2) stages = 2;
+    t->stages = stages;
+    t->smem_bytes = size_t(stages) * stage_bytes + kBarrierBytes + 1024;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+    int mode;  // 0: stride 1 (4-D map c,w,h,b)   1: stride 2 (5-D map c,wpar,w/2,h,b)
+    int TW, TH, rows_valid;
+    int tiles_w, tiles_h, nimg;
+    int n_tiles, BN;
+    int kchunks, ntaps;
+    int dh[kMaxTaps], dw[kMaxTaps];
+    int b_batched;
+    int stages, stage_bytes;
+    float alpha;
+    const float* bias;
+    const __nv_bfloat16* resid;
+    long long R_sB, R_sH, R_sW;
+    void* D;
+    int out_fp32;
+    long long D_sB, D_sH, D_sW, D_sN;
+    int n_store;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel).
+template <int NC>
+__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, bool valid, long long d_off,
+                                               long long r_off, int n0) {
+    if (!valid) return;
+    float f[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) f[j] += __ldg(p.bias + n0 + j);
+    }
+    if (p.resid != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + r_off + n0);
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            uint4 r = __ldg(rp + j);
+            f[8 * j + 0] += bf16_lo(r.x); f[8 * j + 1] += bf16_hi(r.x);
+            f[8 * j + 2] += bf16_lo(r.y); f[8 * j + 3] += bf16_hi(r.y);
+            f[8 * j + 4] += bf16_lo(r.z); f[8 * j + 5] += bf16_hi(r.z);
+            f[8 * j + 6] += bf16_lo(r.w); f[8 * j + 7] += bf16_hi(r.w);
+        }
+    }
+    if (p.D_sN == 1 && n0 + NC <= p.n_store) {
+        if (p.out_fp32) {
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n0);
+#pragma unroll
+            for (int j = 0; j < NC / 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n0);
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j)
+                dp[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+    } else {
+        // strided / partially stored columns (e.g. fp32 NCHW moments, transposed operands)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            if (n0 + j < p.n_store) {
+                long long o = d_off + (long long)(n0 + j) * p.D_sN;
+                if (p.out_fp32) reinterpret_cast<float*>(p.D)[o] = f[j];
+                else reinterpret_cast<__nv_bfloat16*>(p.D)[o] = __float2bfloat16_rn(f[j]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                         const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* bar_base = smem + size_t(p.stages) * p.stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);        // [stages]
+    uint64_t* empty_bar = full_bar + 8;                                // [stages]
+    uint64_t* tfull_bar = empty_bar + 8;                               // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = p.nimg * p.tiles_h * p.tiles_w;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int kblocks = p.ntaps * p.kchunks;
+    const uint32_t tx_bytes = uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                int mt = tile / p.n_tiles;
+                const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th_i = mt % p.tiles_h;
+                const int img = mt / p.tiles_h;
+                const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    const int tap = kb / p.kchunks;
+                    const int c0 = (kb - tap * p.kchunks) * kBlockK;
+                    uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
+                    uint8_t* sB = sA + kATileBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    if (p.mode == 0) {
+                        tma_load_4d(sA, &mapA, &full_bar[stage], c0, ow0 + p.dw[tap], oh0 + p.dh[tap], img);
+                    } else {
+                        const int dw = p.dw[tap], dh = p.dh[tap];
+                        for (int i = 0; i < p.TH; ++i)
+                            tma_load_5d(sA + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
+                                        ow0 + (dw >> 1), 2 * (oh0 + i) + dh, img);
+                    }
+                    tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? img : 0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kUmmaM, p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + size_t(stage) * p.stage_bytes);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
+                        umma_bf16(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
+        const int row = q * 32 + lane;
+        const bool valid = row < p.rows_valid;
+        const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            int mt = tile / p.n_tiles;
+            const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th_i = mt % p.tiles_h;
+            const int img = mt / p.tiles_h;
+            const int oh = th_i * p.TH + r_th, ow = tw_i * p.TW + r_tw;
+            const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
+            const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
+            int c = 0;
+            for (; c + 32 <= p.BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_addr + uint32_t(c), v);
+                tmem_ld_wait();
+                epilogue_store<32>(p, v, valid, d_off, r_off, nt * p.BN + c);
+            }
+            if (c < p.BN) {  // BN % 32 == 16
+                uint32_t v[16];
+                tmem_ld16(t_addr + uint32_t(c), v);
+                tmem_ld_wait();
+                epilogue_store<16>(p, v, valid, d_off, r_off, nt * p.BN + c);
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || p == nullptr)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, const char* what) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(%s) failed: %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", what, (int)r,
+                  rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+                  box[1], box[2]);
+        return -3;
+    }
+    return 0;
+}
+
+int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
+    GemmTiling t;
+    int rc = gemm_plan(op, &t);
+    if (rc) return rc;
+
+    CUtensorMap mapA, mapB;
+    if (op.stride == 1) {
+        cuuint64_t dims[4] = {(cuuint64_t)op.A_C, (cuuint64_t)op.A_W, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
+        cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)t.TW, (cuuint32_t)t.TH, 1};
+        if ((rc = encode_map(&mapA, op.A, 4, dims, str, box, op.name))) return rc;
+    } else {
+        cuuint64_t dims[5] = {(cuuint64_t)op.A_C, 2, (cuuint64_t)op.A_W / 2, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
+        cuuint64_t str[4] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sW * 4, (cuuint64_t)op.A_sH * 2,
+                             (cuuint64_t)op.A_sB * 2};
+        cuuint32_t box[5] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)t.TW, 1, 1};
+        if ((rc = encode_map(&mapA, op.A, 5, dims, str, box, op.name))) return rc;
+    }
+    {
+        const int ktot = op.ntaps * op.A_C;
+        const int nb = op.B_sBatch ? op.A_B : 1;
+        cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)op.N, (cuuint64_t)nb};
+        cuuint64_t sb = op.B_sBatch ? (cuuint64_t)op.B_sBatch * 2 : (cuuint64_t)op.B_sN * 2 * (cuuint64_t)op.N;
+        cuuint64_t str[2] = {(cuuint64_t)op.B_sN * 2, sb};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)t.BN, 1};
+        if ((rc = encode_map(&mapB, op.Bm, 3, dims, str, box, op.name))) return rc;
+    }
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = op.stride == 2 ? 1 : 0;
+    p.TW = t.TW; p.TH = t.TH; p.rows_valid = t.rows_valid;
+    p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.nimg = op.A_B;
+    p.n_tiles = t.n_tiles; p.BN = t.BN;
+    p.kchunks = t.kchunks; p.ntaps = op.ntaps;
+    for (int i = 0; i < op.ntaps; ++i) { p.dh[i] = op.dh[i]; p.dw[i] = op.dw[i]; }
+    p.b_batched = op.B_sBatch != 0;
+    p.stages = t.stages;
+    p.stage_bytes = kATileBytes + ((t.BN * 128 + 1023) / 1024) * 1024;
+    p.alpha = op.alpha;
+    p.bias = op.bias;
+    p.resid = reinterpret_cast<const __nv_bfloat16*>(op.resid);
+    p.R_sB = op.R_sB; p.R_sH = op.R_sH; p.R_sW = op.R_sW;
+    p.D = op.D; p.out_fp32 = op.out_fp32;
+    p.D_sB = op.D_sB; p.D_sH = op.D_sH; p.D_sW = op.D_sW; p.D_sN = op.D_sN;
+    p.n_store = op.n_store > 0 ? op.n_store : op.N;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxSmem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+        attr_set = true;
+    }
+    const int total_tiles = op.A_B * t.tiles_h * t.tiles_w * t.n_tiles;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    conv_gemm_tcgen05_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s: launch failed: %s", op.name, cudaGetErrorString(e)); return -5; }
+    g_tc_launches.fetch_add(1);
+    return 0;
+}
+
+int gemm_launch(const GemmOp& op, int num_sms, cudaStream_t stream) {
+    if (g_impl.load() == 1) return gemm_launch_simt(op, stream);
+    return gemm_launch_tc(op, num_sms, stream);
+}
+
+}  // namespace tml

@@ -1,0 +1,61 @@
+// Launchers for the bandwidth-bound kernels of the PGD hot path (everything that is not a GEMM).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tml {
+
+typedef __nv_bfloat16 bf16;
+
+// conv_in (3 -> C0, 3x3 s1 p1): fp32 NCHW image -> bf16 NHWC.  w_kc: [27][C0] fp32 (k = ci*9+r*3+s).
+void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf16* y, int B, int H, int W, int C0,
+                        cudaStream_t s);
+// its input gradient: bf16 NHWC dY -> fp32 NCHW dX (dX = beta*dX + result).  w_kc as above.
+void launch_conv_in_dgrad(const bf16* dy, const float* w_kc, float* dx, float beta, int B, int H, int W, int C0,
+                          cudaStream_t s);
+
+// GroupNorm(32 groups) over bf16 [B, HW, C].
+//   partial: [B][chunks][32][2] fp32 scratch;  ss: [B][C] float2 (scale, shift);  mr: [B][32] float2 (mean, rstd)
+int gn_num_chunks(int HW);
+void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s);
+void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
+                        int HW, int C, float eps, cudaStream_t s);
+void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s);
+// backward of y = act(GN(x)):  dx = rstd*(dxh - mean(dxh) - xh*mean(dxh*xh)) (+ resid)
+void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
+                           float* partial, int B, int HW, int C, int silu, cudaStream_t s);
+void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, cudaStream_t s);
+void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
+                         const float* gamma, const bf16* resid, bf16* dx, int B, int HW, int C, int silu,
+                         cudaStream_t s);
+
+// attention helpers
+void launch_softmax_rows(const float* S, bf16* P, long long rows, int cols, cudaStream_t s);
+void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float scale, long long rows, int cols,
+                             cudaStream_t s);
+// out[b][c][r] = in[b][r][c]; in row stride ld_in, batch strides in elements
+void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
+                      long long ld_out, long long bs_out, cudaStream_t s);
+
+// posterior sample + latent loss + d(loss)/d(moments)          (main.py:162,191; losses.py:39-41)
+void launch_latent_loss(int kind, const float* moments, const float* noise, const float* target, int B, int h, int w,
+                        float grad_scale, float* z, float* loss, float* dmoments, cudaStream_t s);
+// fp32 NCHW [B,8,h,w] -> bf16 NHWC [B,h,w,64] (channels 8..63 zero): the A operand of conv_out's dgrad
+void launch_dmoments_pack(const float* dm, bf16* out, int B, int h, int w, cudaStream_t s);
+
+// PGD updates                                                   (main.py:248-276)
+void launch_pgd_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
+                     long long n, cudaStream_t s);
+size_t pgd_l2_workspace_bytes(int B, long long per_image);
+void launch_pgd_l2(float* x_adv, const float* grad, const float* x, const float* mask, float eps, float step, float lo,
+                   float hi, int B, int C, long long hw, void* ws, cudaStream_t s);
+// universal perturbation                                        (old/train_noise.py:127-185)
+void launch_add_delta(const float* x, const float* delta, float* out, int B, long long per_image, cudaStream_t s);
+void launch_batch_sum(const float* g, float* out, int B, long long per_image, float scale, cudaStream_t s);
+void launch_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
+                           float hi, long long n, void* ws, cudaStream_t s);
+
+long kernel_launch_count();
+
+}  // namespace tml

@@ -1,0 +1,38 @@
+"""Command-line flags for the launcher, named after the (unused) argparse list the reference
+carries in utils/parser.py (``--resolution`` :116, ``--train_batch_size`` :139, ``--seed`` :114,
+``--mixed_precision`` :322, ``--local_rank`` :332, ``--pretrained_vae_model_name_or_path``,
+``--max_train_steps``, ``--output_dir``) plus the PGD options of configs.py:121-141."""
+from __future__ import annotations
+
+import argparse
+import os
+
+
+def parse_args(input_args=None):
+    p = argparse.ArgumentParser(description="B200-native PGD image immunization (VAE-encoder attack)")
+    p.add_argument("--pretrained_vae_model_name_or_path", type=str, default=None,
+                   help="Path to a torch state dict (diffusers AutoencoderKL keys); random init if omitted.")
+    p.add_argument("--train_data_dir", type=str, default=None, help="Folder of *.jpg images; synthetic if omitted.")
+    p.add_argument("--num_images", type=int, default=64)
+    p.add_argument("--output_dir", type=str, default="./output")
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--resolution", type=int, default=512)
+    p.add_argument("--train_batch_size", type=int, default=16, help="Images per encoder pass on each GPU.")
+    p.add_argument("--max_train_steps", type=int, default=200, help="PGD steps (n_optimization_steps).")
+    p.add_argument("--mixed_precision", type=str, default="bf16", choices=["bf16"],
+                   help="Activations/weights inside the encoder kernels; the iterate stays fp32.")
+    p.add_argument("--local_rank", type=int, default=-1)
+    p.add_argument("--norm_type", type=str, default="linf", choices=["linf", "l2"])
+    p.add_argument("--eps", type=float, default=32 / 255)
+    p.add_argument("--step_size", type=float, default=4 / 255)
+    p.add_argument("--min_value", type=float, default=-1.0)
+    p.add_argument("--max_value", type=float, default=1.0)
+    p.add_argument("--grad_reps", type=int, default=1)
+    p.add_argument("--latent_loss", type=str, default="l2norm", choices=["l2norm", "mse"])
+    p.add_argument("--universal", action="store_true", help="Shared-perturbation mode (old/train_noise.py).")
+    p.add_argument("--sdxl", action="store_true", help="SDXL VAE scaling factor (architecture is identical).")
+    args = p.parse_args(input_args)
+    env_local_rank = int(os.environ.get("LOCAL_RANK", -1))
+    if env_local_rank != -1 and env_local_rank != args.local_rank:
+        args.local_rank = env_local_rank
+    return args
