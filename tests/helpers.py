@@ -56,3 +56,68 @@ def cosine(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle tracing: intermediate activations and their gradients, by the names the CUDA path saves
+# ------------------------------------------------------------------------------------------------
+BACKWARD_STAGE_NAMES = ["res9_out", "attn_out", "res8_out", "res7_out", "res6_out", "down2_out", "res5_out",
+                        "res4_out", "down1_out", "res3_out", "res2_out", "down0_out", "res1_out", "res0_out",
+                        "conv_in"]
+
+
+def oracle_resnets(model):
+    enc = model.encoder
+    out = []
+    for blk in enc.down_blocks:
+        out.extend(list(blk.resnets))
+    out.extend(list(enc.mid_block.resnets))
+    return out
+
+
+def oracle_trace(model, x, target, noise, kind=0):
+    """Run the oracle with hooks.  Returns (acts, grads, moments, grad_x, losses): dicts of NCHW tensors."""
+    from oracle.encoder_oracle import latent_loss, DiagonalGaussianDistribution
+    acts = {}
+    handles = []
+
+    def keep(name):
+        def hook(mod, inp, out):
+            out.retain_grad()
+            acts[name] = out
+        return hook
+
+    enc = model.encoder
+    handles.append(enc.conv_in.register_forward_hook(keep("conv_in")))
+    for i, r in enumerate(oracle_resnets(model)):
+        handles.append(r.conv1.register_forward_hook(keep(f"res{i}_h1")))
+        handles.append(r.register_forward_hook(keep(f"res{i}_out")))
+    for i, blk in enumerate(enc.down_blocks):
+        if blk.downsamplers is not None:
+            handles.append(blk.downsamplers[0].register_forward_hook(keep(f"down{i}_out")))
+    if enc.mid_block.attentions is not None:
+        handles.append(enc.mid_block.attentions[0].register_forward_hook(keep("attn_out")))
+    with torch.enable_grad():
+        xx = x.clone().requires_grad_(True)
+        moments = model.moments(xx)
+        dist = DiagonalGaussianDistribution(moments)
+        z = dist.mean if noise is None else dist.mean + dist.std * noise
+        losses = latent_loss(z, target, kind)
+        losses.sum().backward()
+    for h in handles:
+        h.remove()
+    grads = {k: v.grad.detach() for k, v in acts.items() if v.grad is not None}
+    acts = {k: v.detach() for k, v in acts.items()}
+    return acts, grads, moments.detach(), xx.grad.detach(), losses.detach()
+
+
+def fetch_saved(vae, saved, name, index=0):
+    """bf16 NHWC activation kept by the CUDA forward -> fp32 NCHW torch tensor."""
+    from tml_image_editing_defense_b200 import _lib
+    off = C.c_size_t()
+    dims = (C.c_int * 4)()
+    _lib.check(vae._lib.tml_debug_saved_tensor(vae._h, name.encode(), index, C.byref(off), dims))
+    B, H, W, Cc = list(dims)
+    n = B * H * W * Cc
+    t = saved[off.value: off.value + 2 * n].view(torch.bfloat16).view(B, H, W, Cc)
+    return t.float().permute(0, 3, 1, 2).contiguous()

@@ -1,0 +1,140 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (run with -m gpu on a B200)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.test_oracle import assert_bit_equal, LINF, L2  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tml_image_editing_defense_b200 import _lib
+    return _lib.load()
+
+
+# ------------------------------------------------------------------ K9: fused PGD update
+@pytest.mark.parametrize("name", LINF)
+def test_pgd_linf_bit_exact_vs_reference_golden(golden_dir, dev, name):
+    from tml_image_editing_defense_b200 import ops
+    d = np.load(golden_dir / f"pgd_linf_{name}.npz")
+    eps, step, lo, hi = [float(v) for v in d["params"]]
+    xa = torch.from_numpy(d["x_adv"]).to(dev)
+    out = ops.pgd_step_linf_(xa, torch.from_numpy(d["grad"]).to(dev), torch.from_numpy(d["x"]).to(dev), eps, step,
+                             lo, hi)
+    assert_bit_equal(out.cpu().numpy(), d["out"])
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4 * 1000 * 1000 + 1])
+def test_pgd_linf_bit_exact_vs_oracle_odd_sizes(dev, n):
+    from oracle.pgd_oracle import pgd_step_linf
+    from tml_image_editing_defense_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(n, generator=g) * 2 - 1
+    xa = (x + (torch.rand(n, generator=g) - 0.5) * 0.2).clamp(-1, 1)
+    gr = torch.randn(n, generator=g)
+    gr[::7] = 0.0
+    ref = pgd_step_linf(xa, gr, x, 32 / 255, 4 / 255, -1, 1)
+    out = ops.pgd_step_linf_(xa.to(dev), gr.to(dev), x.to(dev), 32 / 255, 4 / 255, -1.0, 1.0)
+    assert_bit_equal(out.cpu().numpy(), ref.numpy())
+
+
+def test_pgd_linf_full_size_properties(dev):
+    """BASELINE cfg-2 size (64x3x512x512): result stays in the eps-ball and the clamp range, moves
+    by exactly +-step or 0 before projection, and is idempotent under a zero gradient."""
+    from tml_image_editing_defense_b200 import ops
+    n = 64 * 3 * 512 * 512
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand(n, generator=g, device=dev) * 2 - 1
+    xa = x.clone()
+    gr = torch.randn(n, generator=g, device=dev)
+    eps, step = 32 / 255, 4 / 255
+    for _ in range(3):
+        ops.pgd_step_linf_(xa, gr, x, eps, step, -1.0, 1.0)
+    assert float((xa - x).abs().max()) <= eps + 1e-7
+    assert float(xa.min()) >= -1 and float(xa.max()) <= 1
+    ref = torch.clamp(torch.minimum(torch.maximum(x - 3 * step * gr.sign(), x - eps), x + eps), -1, 1)
+    assert float((xa - ref).abs().max()) < 1e-6
+    before = xa.clone()
+    ops.pgd_step_linf_(xa, torch.zeros_like(gr), x, eps, step, -1.0, 1.0)
+    assert torch.equal(xa, before)
+
+
+@pytest.mark.parametrize("name", L2)
+def test_pgd_l2_vs_reference_golden(golden_dir, dev, name):
+    from tml_image_editing_defense_b200 import ops
+    d = np.load(golden_dir / f"pgd_l2_{name}.npz")
+    eps, step, lo, hi = [float(v) for v in d["params"]]
+    mask = torch.from_numpy(d["mask"]).to(dev) if d["mask"].size else None
+    out = ops.pgd_step_l2_(torch.from_numpy(d["x_adv"]).to(dev), torch.from_numpy(d["grad"]).to(dev),
+                           torch.from_numpy(d["x"]).to(dev), mask, eps, step, lo, hi)
+    # fp32 norms are reduced in a different order than ATen's: tolerance 2e-6 absolute on values in [-1,1]
+    np.testing.assert_allclose(out.cpu().numpy(), d["out"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["ref", "tight"])
+def test_universal_step_vs_reference_golden(golden_dir, dev, name):
+    from tml_image_editing_defense_b200 import ops
+    d = np.load(golden_dir / f"universal_update_{name}.npz")
+    eps, step = [float(v) for v in d["params"]]
+    out = ops.universal_step_(torch.from_numpy(d["delta"]).to(dev), torch.from_numpy(d["grad"]).to(dev),
+                              torch.from_numpy(d["source"]).to(dev), eps, step)
+    np.testing.assert_allclose(out.cpu().numpy(), d["out"], rtol=0, atol=2e-6)
+
+
+def test_add_delta_and_batch_sum(dev):
+    from tml_image_editing_defense_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 3, 16, 16, generator=g)
+    dl = torch.randn(1, 3, 16, 16, generator=g)
+    assert torch.equal(ops.add_delta(x.to(dev), dl.to(dev)).cpu(), x + dl)
+    s = ops.batch_sum(x.to(dev), 0.5).cpu()
+    ref = torch.zeros(1, 3, 16, 16)
+    for b in range(5):
+        ref += x[b]
+    assert torch.equal(s, ref * 0.5)
+
+
+# ------------------------------------------------------------------ K8: sample + loss + dmoments
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("use_noise", [True, False])
+def test_latent_loss_vs_autograd(dev, kind, use_noise):
+    from oracle.encoder_oracle import DiagonalGaussianDistribution, latent_loss
+    from tml_image_editing_defense_b200 import ops
+    g = torch.Generator().manual_seed(kind)
+    m = torch.randn(3, 8, 8, 8, generator=g)
+    m[:, 4:] *= 12            # exercise the logvar clamp on both sides
+    m[0, 4, 0, 0], m[0, 4, 0, 1] = 25.0, -35.0
+    t = torch.randn(3, 4, 8, 8, generator=g)
+    noise = torch.randn(3, 4, 8, 8, generator=g) if use_noise else None
+    mm = m.clone().requires_grad_(True)
+    dist = DiagonalGaussianDistribution(mm)
+    z_ref = dist.mean + dist.std * noise if use_noise else dist.mean
+    l_ref = latent_loss(z_ref, t, kind)
+    (dm_ref,) = torch.autograd.grad(l_ref.sum(), mm)
+    z, l, dm = ops.latent_loss(m.to(dev), noise.to(dev) if use_noise else None, t.to(dev), kind)
+    torch.testing.assert_close(z.cpu(), z_ref.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(l.cpu(), l_ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dm.cpu(), dm_ref, rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------ K1-K5: tcgen05 implicit GEMM
+def test_tcgen05_gemm_suite(dev, lib):
+    from tools.gpu_check import run_gemm_suite
+    lib.tml_debug_set_gemm_impl(0)
+    before = np.zeros(2, np.int64)
+    lib.tml_launch_counts(before.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert run_gemm_suite(lib, dev)
+    after = np.zeros(2, np.int64)
+    lib.tml_launch_counts(after.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert after[0] - before[0] >= 18, "the tcgen05 kernel did not run"

@@ -51,11 +51,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (the launch fails with an error the host
-// reports), never as a hung GPU.  ~2^28 probes is minutes of wall time only if every probe sleeps.
+// reports), never as a hung GPU.  No legitimate wait in these kernels lasts anywhere near 2 s.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
     }
 }
 
