@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: image-PGD-iterations / second of the SD-1.5 VAE-encoder attack
+(BASELINE.json metric; config[1]: batch 64 x 512^2, bf16 activations, fp32 iterate).
+
+    python bench.py --gpus N --steps K --warmup W              # this framework (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+
+One "step" = one PGD iteration for every image of the per-GPU batch: encoder forward, latent loss
+and its gradient, encoder input-gradient backward, fused sign-step / eps-projection / clamp.
+Images are independent, so N GPUs each run their own batch with no data-path collective
+(weak scaling: per-GPU batch fixed).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_IMG_ITER = {512: 2.2677e12, 1024: 10.3077e12}   # fwd + dgrad-only bwd, algorithmic
+CONV_IN_FLOP = {512: 4 * 0.906e9, 1024: 4 * 3.624e9}     # K4 (SIMT direct conv, fwd + dgrad) is not a GEMM launch
+EPS, STEP, LO, HI = 32 / 255, 4 / 255, -1.0, 1.0          # eps 16/255, step 2/255 on a [0,1] scale
+
+
+def read_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(res: int, B: int, world: int, mb: int):
+    return {"workload": f"SD-1.5 VAE-encoder PGD attack (BASELINE configs[1]): batch {B} x {res}^2 per GPU, "
+                        f"bf16 activations/weights, fp32 accumulate, fp32 iterate, linf eps=16/255 step=2/255, "
+                        f"random-init weights",
+            "global_batch": B * world, "per_gpu_batch": B, "micro_batch": mb, "resolution": res,
+            "parallelism": f"dp{world} (independent images, no collective)",
+            "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)"}
+
+
+def synth_inputs(batch: int, res: int, seed: int, pin: bool):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((batch, 3, res, res), generator=g) * 2 - 1
+    tgt = torch.randn((batch, 4, res // 8, res // 8), generator=g)
+    noise = torch.randn((batch, 4, res // 8, res // 8), generator=g)
+    if pin:
+        x, tgt, noise = x.pin_memory(), tgt.pin_memory(), noise.pin_memory()
+    return x, tgt, noise
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU path (oracle port; the reference cannot be imported: no diffusers)
+# --------------------------------------------------------------------------------------------------
+def time_cpu_oracle(res: int, images_per_step: int, steps: int, warmup: int, threads: int):
+    from oracle.encoder_oracle import make_oracle
+    from oracle.pgd_oracle import encoder_attack
+    torch.set_num_threads(threads)
+    model = make_oracle(0)
+    x, tgt, noise = synth_inputs(images_per_step, res, 0, pin=False)
+    if warmup:
+        encoder_attack(model, x, tgt, noise, warmup, EPS, STEP, LO, HI, kind=0)
+    t0 = time.perf_counter()
+    encoder_attack(model, x, tgt, noise, steps, EPS, STEP, LO, HI, kind=0)
+    dt = time.perf_counter() - t0
+    return images_per_step * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = 1
+    value, dt = time_cpu_oracle(args.res, per_step, args.steps, min(args.warmup, 1), threads)
+    sample = (f"bounded sample of the workload: {per_step} image(s) x {args.res}^2 fp32 per step, {args.steps} timed PGD steps after "
+              f"{min(args.warmup, 1)} warm-up, oracle port (torch CPU, {threads} threads)")
+    line = {
+        "impl": "reference", "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.res, args.batch, args.gpus, args.micro_batch),
+        "cpu_baseline": {"value": value, "unit": "image-PGD-iters/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# this framework
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from oracle.encoder_oracle import make_oracle  # random-init weights of the named architecture only
+    from tml_image_editing_defense_b200 import _lib, ops
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.trainer import Trainer
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    res, B, mb = args.res, args.batch, args.micro_batch
+    weights = make_oracle(0).state_dict()
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(weights)
+    del weights
+    cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
+                      n_optimization_steps=1, device=str(dev))
+    tr = Trainer(cfg, vae, micro_batch=mb)
+
+    xh, th, nh = synth_inputs(B, res, 1000 + rank, pin=True)
+    x = xh.to(dev)
+    tgt, noise = th.to(dev), nh.to(dev)
+    x_adv = x.clone()
+    grad = torch.empty_like(x)
+    tr.noises = [noise]
+
+    def step_device():
+        tr.compute_grad(x_adv, None, x, None, tgt, tr.noises, grad_out=grad, beta=0.0)
+        tr.perturbation_step(x_adv, grad, x, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput
+    n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm):
+        step_device()
+    barrier()
+    c0 = _lib.launch_counts()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.tml_gemm_timing_enable(200000)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gt = (C.c_double * 4)()
+    lib.tml_gemm_timing_collect(gt)
+    lib.tml_gemm_timing_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = _lib.launch_counts()
+    launches = (c1[0] - c0[0]) + (c1[1] - c0[1])
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_max / args.steps,
+                              "gemm_ms_per_step": gt[0] / args.steps, "gemm_launches": int(gt[2]),
+                              "launches": launches, "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ end to end with host buffers
+    # Per step: H2D of the step's inputs (current iterate, source image, target latent, noise) from
+    # pinned memory, the PGD iteration through the public Trainer API, D2H of the new iterate + losses.
+    xa_host = xh.clone().pin_memory()
+    out_host = torch.empty_like(xh).pin_memory()
+    loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    h2d = xa_host.numel() * 4 + xh.numel() * 4 + th.numel() * 4 + nh.numel() * 4
+    d2h = out_host.numel() * 4 + loss_host.numel() * 4
+
+    def step_e2e():
+        xa_d = xa_host.to(dev, non_blocking=True)
+        x_d = xh.to(dev, non_blocking=True)
+        t_d = th.to(dev, non_blocking=True)
+        n_d = nh.to(dev, non_blocking=True)
+        g_d, _, _, ld = tr.compute_grad(xa_d, None, x_d, None, t_d, [n_d])
+        xa_d = tr.perturbation_step(xa_d, g_d, x_d, None)
+        out_host.copy_(xa_d, non_blocking=True)
+        loss_host.copy_(ld["per_image"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the result after this
+        xa_host.copy_(out_host)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    k2 = max(2, min(args.steps, 5))
+    e0.record()
+    for _ in range(k2):
+        step_e2e()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * k2 / (float(t2.item()) / 1e3)
+
+    # ------------------------------------------------------------------ K9 standalone (HBM roofline)
+    pgd = None
+    if rank == 0:
+        n = x_adv.numel()
+        for _ in range(3):
+            ops.pgd_step_linf_(x_adv, grad, x, EPS, STEP, LO, HI)
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            ops.pgd_step_linf_(x_adv, grad, x, EPS, STEP, LO, HI)
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / reps
+        pgd = {"bytes": 16 * n, "us": us, "gbs": 16 * n / (us * 1e-6) / 1e9}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = read_peaks()
+    gemm_ms, _, gemm_n, gemm_drop = gt[0], gt[1], int(gt[2]), int(gt[3])
+    algo_flops_step = (FLOP_PER_IMG_ITER.get(res, 0.0) - CONV_IN_FLOP.get(res, 0.0)) * B
+    gemm_ms_step = gemm_ms / args.steps if args.steps else 0.0
+    achieved_tf = algo_flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else None
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    roofline = {
+        "bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+        "launches_timed": gemm_n, "launches_dropped": gemm_drop,
+        "gemm_ms_per_step": gemm_ms_step, "gemm_share_of_step": gemm_ms_step / (ms_max / args.steps),
+        "algorithmic_flops_per_step": algo_flops_step,
+        "whole_step_frac_of_burst": (value / world) * FLOP_PER_IMG_ITER.get(res, 0.0) / (peaks["bf16_tflops"] * 1e12),
+    }
+    roofline_pgd = None
+    if pgd:
+        roofline_pgd = {"bound": "hbm", "kernel": "pgd_linf_kernel", "achieved": pgd["gbs"], "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": pgd["gbs"] / peaks["hbm_gbs"], "bytes_per_launch": pgd["bytes"],
+                        "us_per_launch": pgd["us"], "peak_source": f"{peak_src} hbm_gbs",
+                        "note": "16 B/element algorithmic; working set 805 MB > 126 MB L2"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = time_cpu_oracle(res, 1, 2, 1, threads)
+        cpu = {"value": v, "unit": "image-PGD-iters/s", "cores": threads, "kind": "port",
+               "sample": f"1 image x {res}^2 fp32, 2 timed PGD steps after 1 warm-up ({dt:.1f} s), oracle port, "
+                         f"torch CPU {threads} threads"}
+
+    line = {
+        "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s", "n_gpus": world,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(res, B, world, mb),
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": k2},
+        "roofline": roofline, "roofline_pgd_update": roofline_pgd, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU (configs[1]: 64)")
+    ap.add_argument("--micro_batch", type=int, default=16, help="images per encoder pass")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,11 @@ int tml_universal_step(float* delta, const float* grad, const float* source, flo
 /* ---- introspection / test hooks ---- */
 /* number of kernels launched by this library since load: [0] tcgen05 GEMMs, [1] all other kernels */
 void tml_launch_counts(int64_t out[2]);
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel on its launch stream (bench.py roofline).
+ * enable(n): record up to n launches (0 = off).  collect (after a synchronize): out = {total ms,
+ * total algorithmic flops (2*M*N*K, conv padding not discounted), launches timed, launches dropped}. */
+void tml_gemm_timing_enable(int max_launches);
+void tml_gemm_timing_collect(double out[4]);
 /* 0 = tcgen05 kernel (default, the product path), 1 = SIMT debug kernel (tests only) */
 void tml_debug_set_gemm_impl(int impl);
 /* Generic implicit-GEMM entry used by the kernel unit tests (same operation the encoder issues). */

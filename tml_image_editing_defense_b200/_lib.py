@@ -63,6 +63,8 @@ SIGNATURES = {
     "tml_universal_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_int64, C.c_void_p, C.c_void_p]),
     "tml_launch_counts": (None, [C.POINTER(C.c_int64)]),
+    "tml_gemm_timing_enable": (None, [C.c_int]),
+    "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),
     "tml_debug_set_gemm_impl": (None, [C.c_int]),
     "tml_debug_gemm": (C.c_int, [C.POINTER(TmlGemmDesc), C.c_void_p]),
     "tml_debug_saved_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),

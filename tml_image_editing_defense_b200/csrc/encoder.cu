@@ -987,6 +987,13 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
     return gemm_launch(o, sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
+void tml_gemm_timing_enable(int max_launches) { gemm_timing_enable(max_launches); }
+void tml_gemm_timing_collect(double out[4]) {
+    long n = 0, d = 0;
+    gemm_timing_collect(&out[0], &out[1], &n, &d);
+    out[2] = (double)n; out[3] = (double)d;
+}
+
 void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots) {
     g_dump_base = reinterpret_cast<char*>(dev_buffer);
     g_dump_slot = slot_bytes;

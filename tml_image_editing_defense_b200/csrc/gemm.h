@@ -57,6 +57,9 @@ void gemm_set_impl(int impl);
 int gemm_get_impl();
 long gemm_launch_count();  // number of tcgen05 GEMM launches since process start
 
+void gemm_timing_enable(int max_launches);  // 0 disables and recycles the events
+void gemm_timing_collect(double* total_ms, double* total_flops, long* launches, long* dropped);
+
 void set_error(const char* fmt, ...);
 const char* last_error();
 

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <vector>
 
 #include "gemm.h"
 #include "ptx.cuh"
@@ -44,6 +45,41 @@ static std::atomic<long> g_tc_launches{0};
 void gemm_set_impl(int impl) { g_impl.store(impl); }
 int gemm_get_impl() { return g_impl.load(); }
 long gemm_launch_count() { return g_tc_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// optional per-launch CUDA-event timing of the tcgen05 kernel (bench.py's roofline numbers)
+// ------------------------------------------------------------------------------------------------
+struct TimedLaunch { cudaEvent_t a, b; double flops; };
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+static bool g_timing = false;
+static size_t g_timing_cap = 0;
+static long g_timing_dropped = 0;
+
+void gemm_timing_enable(int max_launches) {
+    g_timing = max_launches > 0;
+    g_timing_cap = max_launches > 0 ? (size_t)max_launches : 0;
+    g_timing_dropped = 0;
+    for (auto& t : g_timed) { g_event_pool.push_back(t.a); g_event_pool.push_back(t.b); }
+    g_timed.clear();
+    if (g_timing) g_timed.reserve(g_timing_cap);
+}
+static cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+// Sums elapsed time / algorithmic flops over the recorded launches (caller has synchronised).
+void gemm_timing_collect(double* total_ms, double* total_flops, long* launches, long* dropped) {
+    double ms = 0.0, fl = 0.0;
+    for (auto& t : g_timed) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, t.a, t.b) == cudaSuccess) ms += e;
+        fl += t.flops;
+    }
+    *total_ms = ms; *total_flops = fl; *launches = (long)g_timed.size(); *dropped = g_timing_dropped;
+}
 
 // ------------------------------------------------------------------------------------------------
 // tiling
@@ -420,7 +456,17 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     }
     const int total_tiles = op.A_B * t.tiles_h * t.tiles_w * t.n_tiles;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    const bool timed = g_timing && g_timed.size() < g_timing_cap;
+    TimedLaunch tl;
+    if (timed) {
+        tl.a = take_event(); tl.b = take_event();
+        tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)(op.n_store > 0 ? op.n_store : op.N) * (double)op.ntaps * op.A_C;
+        cudaEventRecord(tl.a, stream);
+    } else if (g_timing) {
+        ++g_timing_dropped;
+    }
     conv_gemm_tcgen05_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+    if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("%s: launch failed: %s", op.name, cudaGetErrorString(e)); return -5; }
     g_tc_launches.fetch_add(1);
