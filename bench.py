@@ -155,11 +155,11 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from oracle.encoder_oracle import make_oracle  # random-init weights of the named architecture only
     from tml_image_editing_defense_b200 import _lib, ops
     from tml_image_editing_defense_b200.configs import TrainConfig
     from tml_image_editing_defense_b200.trainer import Trainer
     from tml_image_editing_defense_b200.vae import AutoencoderKL
+    from tml_image_editing_defense_b200.weights import random_init_state_dict
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +174,7 @@ def run_ours(args):
     lib = _lib.load()
 
     res, B, mb = args.res, args.batch, args.micro_batch
-    weights = make_oracle(0).state_dict()
+    weights = random_init_state_dict(seed=0)
     vae = AutoencoderKL(device=str(dev)).load_state_dict(weights)
     del weights
     cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
