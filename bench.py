@@ -91,11 +91,11 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(res: int, B: int, world: int, mb: int):
+def workload_config(res: int, B: int, world: int, mb: int, streams: int = 2):
     return {"workload": f"SD-1.5 VAE-encoder PGD attack (BASELINE configs[1]): batch {B} x {res}^2 per GPU, "
                         f"bf16 activations/weights, fp32 accumulate, fp32 iterate, linf eps=16/255 step=2/255, "
                         f"random-init weights",
-            "global_batch": B * world, "per_gpu_batch": B, "micro_batch": mb, "resolution": res,
+            "global_batch": B * world, "per_gpu_batch": B, "micro_batch": mb, "streams": streams, "resolution": res,
             "parallelism": f"dp{world} (independent images, no collective)",
             "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)"}
 
@@ -140,7 +140,7 @@ def run_reference(args):
         "impl": "reference", "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.res, args.batch, args.gpus, args.micro_batch),
+        "config": workload_config(args.res, args.batch, args.gpus, args.micro_batch, args.streams),
         "cpu_baseline": {"value": value, "unit": "image-PGD-iters/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,7 +179,7 @@ def run_ours(args):
     del weights
     cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
                       n_optimization_steps=1, device=str(dev))
-    tr = Trainer(cfg, vae, micro_batch=mb)
+    tr = Trainer(cfg, vae, micro_batch=mb, num_streams=args.streams)
 
     xh, th, nh = synth_inputs(B, res, 1000 + rank, pin=True)
     x = xh.to(dev)
@@ -327,7 +327,7 @@ def run_ours(args):
         "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s", "n_gpus": world,
         "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(res, B, world, mb),
+        "config": workload_config(res, B, world, mb, args.streams),
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": k2},
@@ -348,6 +348,7 @@ def main():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (configs[1]: 64)")
     ap.add_argument("--micro_batch", type=int, default=16, help="images per encoder pass")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the micro-batches alternate on")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()

@@ -103,7 +103,7 @@ typedef struct TmlGemmDesc {
     int stride, ntaps; int dh[9], dw[9]; int OW, OH;
     const void* Bm; int N; int64_t B_sN, B_sBatch;
     float alpha; const float* bias; const void* resid; int64_t R_sB, R_sH, R_sW;
-    void* D; int out_fp32; int64_t D_sB, D_sH, D_sW, D_sN; int n_store;
+    void* D; int out_fp32; int64_t D_sB, D_sH, D_sW, D_sN; int n_store; float beta;
 } TmlGemmDesc;
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 /* Offsets (bytes into `saved`) and [B,H,W,C] dims of the bf16 NHWC activations the forward keeps:

@@ -34,7 +34,7 @@ class TmlGemmDesc(C.Structure):
         ("alpha", C.c_float), ("bias", C.c_void_p), ("resid", C.c_void_p),
         ("R_sB", C.c_int64), ("R_sH", C.c_int64), ("R_sW", C.c_int64),
         ("D", C.c_void_p), ("out_fp32", C.c_int),
-        ("D_sB", C.c_int64), ("D_sH", C.c_int64), ("D_sW", C.c_int64), ("D_sN", C.c_int64), ("n_store", C.c_int),
+        ("D_sB", C.c_int64), ("D_sH", C.c_int64), ("D_sW", C.c_int64), ("D_sN", C.c_int64), ("n_store", C.c_int), ("beta", C.c_float),
     ]
 
 

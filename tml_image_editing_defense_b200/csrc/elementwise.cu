@@ -158,76 +158,6 @@ void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf
 }
 
 // ================================================================================================
-// conv_in input gradient: bf16 NHWC dY [B,H,W,C0] -> fp32 NCHW dX [B,3,H,W]   (the tensor PGD
-// consumes; main.py:176).  One warp per 32 consecutive pixels of a row; lane = 4 channels; the 3
-// outputs per pixel are warp-reduced and parked in lane (pixel%32) so the final store is coalesced.
-// dX = beta*dX + result implements the grad_reps accumulation of main.py:88-102 in place.
-// ================================================================================================
-template <int C0>
-__global__ void __launch_bounds__(256) conv_in_dgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ w_kc,
-                                                            float* __restrict__ dx, float beta, int H, int W) {
-    static_assert(C0 == 128, "conv_in kernel is specialised for 128 output channels");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.z, h = blockIdx.y;
-    const int w0 = (blockIdx.x * 8 + warp) * 32;
-    if (w0 >= W) return;
-    // weights for this lane's 4 channels: wr[ci][tap][j] = W[co=4*lane+j][ci][r][s]
-    float wr[3][9][4];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 v = *reinterpret_cast<const float4*>(&w_kc[(ci * 9 + t) * C0 + lane * 4]);
-            wr[ci][t][0] = v.x; wr[ci][t][1] = v.y; wr[ci][t][2] = v.z; wr[ci][t][3] = v.w;
-        }
-    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f;
-    for (int p = 0; p < 32; ++p) {
-        const int w = w0 + p;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        if (w < W) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int oh = h + 1 - r;
-                if (oh < 0 || oh >= H) continue;
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    const int ow = w + 1 - s;
-                    if (ow < 0 || ow >= W) continue;
-                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(dy + (((size_t)b * H + oh) * W + ow) * C0 + lane * 4));
-                    const float g0 = bf_lo(u.x), g1 = bf_hi(u.x), g2 = bf_lo(u.y), g3 = bf_hi(u.y);
-                    const int t = r * 3 + s;
-                    a0 = fmaf(g0, wr[0][t][0], a0); a0 = fmaf(g1, wr[0][t][1], a0);
-                    a0 = fmaf(g2, wr[0][t][2], a0); a0 = fmaf(g3, wr[0][t][3], a0);
-                    a1 = fmaf(g0, wr[1][t][0], a1); a1 = fmaf(g1, wr[1][t][1], a1);
-                    a1 = fmaf(g2, wr[1][t][2], a1); a1 = fmaf(g3, wr[1][t][3], a1);
-                    a2 = fmaf(g0, wr[2][t][0], a2); a2 = fmaf(g1, wr[2][t][1], a2);
-                    a2 = fmaf(g2, wr[2][t][2], a2); a2 = fmaf(g3, wr[2][t][3], a2);
-                }
-            }
-        }
-        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-        if (lane == p) { keep0 = a0; keep1 = a1; keep2 = a2; }
-    }
-    const int w = w0 + lane;
-    if (w < W) {
-        const size_t plane = (size_t)H * W;
-        float* o = dx + (size_t)b * 3 * plane + (size_t)h * W + w;
-        if (beta != 0.f) {
-            o[0] = fmaf(beta, o[0], keep0); o[plane] = fmaf(beta, o[plane], keep1); o[2 * plane] = fmaf(beta, o[2 * plane], keep2);
-        } else {
-            o[0] = keep0; o[plane] = keep1; o[2 * plane] = keep2;
-        }
-    }
-}
-
-void launch_conv_in_dgrad(const bf16* dy, const float* w_kc, float* dx, float beta, int B, int H, int W, int C0,
-                          cudaStream_t s) {
-    dim3 grid((W + 255) / 256, H, B);
-    conv_in_dgrad_kernel<128><<<grid, 256, 0, s>>>(dy, w_kc, dx, beta, H, W);
-    COUNT_LAUNCH();
-}
-
-// ================================================================================================
 // GroupNorm (32 groups, affine) [+ SiLU] over bf16 NHWC.   diffusers ResnetBlock2D.norm1/norm2,
 // Attention.group_norm, Encoder.conv_norm_out.
 // Thread layout shared by the stats / apply / backward kernels: a block owns a contiguous chunk of
@@ -247,14 +177,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
     const int p0 = chunk * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
     float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
     const bf16* base = x + (size_t)b * HW * C + (size_t)oct * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
-        float f[8];
-        unpack8(u, f);
+    constexpr int U = 4;
+    for (int p = p0 + pl; p < p1; p += PL * U) {
+        uint4 u[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s_lo += f[j]; q_lo = fmaf(f[j], f[j], q_lo); }
+        for (int k = 0; k < U; ++k)
+            u[k] = (p + k * PL < p1) ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + k * PL) * C))
+                                     : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 4; j < 8; ++j) { s_hi += f[j]; q_hi = fmaf(f[j], f[j], q_hi); }
+        for (int k = 0; k < U; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s_lo += f[j]; q_lo = fmaf(f[j], f[j], q_lo); }
+#pragma unroll
+            for (int j = 4; j < 8; ++j) { s_hi += f[j]; q_hi = fmaf(f[j], f[j], q_hi); }
+        }
     }
     red[threadIdx.x][0] = s_lo; red[threadIdx.x][1] = q_lo; red[threadIdx.x][2] = s_hi; red[threadIdx.x][3] = q_hi;
     __syncthreads();
@@ -320,7 +258,7 @@ void launch_gn_finalize(const float* partial, const float* gamma, const float* b
     COUNT_LAUNCH();
 }
 
-__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+__device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ss,
                                                        bf16* __restrict__ y, int HW, int C, int silu) {
@@ -335,16 +273,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
         sc[j] = v.x; sh[j] = v.y;
     }
     const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-        float f[8];
-        unpack8(u, f);
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (int p = p0 + pl; p < p1; p += PL * U) {
+        uint4 u[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float v = fmaf(f[j], sc[j], sh[j]);
-            f[j] = silu ? silu_f(v) : v;
+        for (int k = 0; k < U; ++k)
+            if (p + k * PL < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + k * PL) * C));
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (p + k * PL >= p1) break;
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = fmaf(f[j], sc[j], sh[j]);
+                f[j] = silu ? silu_f(v) : v;
+            }
+            *reinterpret_cast<uint4*>(y + base + (size_t)(p + k * PL) * C) = pack8(f);
         }
-        *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = pack8(f);
     }
 }
 
@@ -357,7 +303,7 @@ void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, in
 // d(act(u))/du for act = SiLU (u*sigmoid(u)) or identity
 __device__ __forceinline__ float dact(float u, int silu) {
     if (!silu) return 1.f;
-    const float sg = 1.f / (1.f + __expf(-u));
+    const float sg = __fdividef(1.f, 1.f + __expf(-u));
     return sg * fmaf(u, 1.f - sg, 1.f);
 }
 
@@ -383,18 +329,30 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restr
     const float2 m_hi = __ldg(&mr[(size_t)b * 32 + (oct * 8 + 4) / cpg]);
     float a_lo = 0.f, b_lo = 0.f, a_hi = 0.f, b_hi = 0.f;
     const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        float fx[8], fd[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), fx);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C)), fd);
+    constexpr int U = 2;  // pixels per iteration: 4 independent 16-byte loads in flight per thread
+    for (int p = p0 + pl; p < p1; p += PL * U) {
+        uint4 ux[U], ud[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float u = fmaf(fx[j], sc[j], sh[j]);
-            const float dxh = fd[j] * dact(u, silu) * gm[j];
-            const float2 m = j < 4 ? m_lo : m_hi;
-            const float xh = (fx[j] - m.x) * m.y;
-            if (j < 4) { a_lo += dxh; b_lo = fmaf(dxh, xh, b_lo); }
-            else { a_hi += dxh; b_hi = fmaf(dxh, xh, b_hi); }
+        for (int k = 0; k < U; ++k)
+            if (p + k * PL < p1) {
+                ux[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + k * PL) * C));
+                ud[k] = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)(p + k * PL) * C));
+            }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (p + k * PL >= p1) break;
+            float fx[8], fd[8];
+            unpack8(ux[k], fx);
+            unpack8(ud[k], fd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float u = fmaf(fx[j], sc[j], sh[j]);
+                const float dxh = fd[j] * dact(u, silu) * gm[j];
+                const float2 m = j < 4 ? m_lo : m_hi;
+                const float xh = (fx[j] - m.x) * m.y;
+                if (j < 4) { a_lo += dxh; b_lo = fmaf(dxh, xh, b_lo); }
+                else { a_hi += dxh; b_hi = fmaf(dxh, xh, b_hi); }
+            }
         }
     }
     red[threadIdx.x][0] = a_lo; red[threadIdx.x][1] = b_lo; red[threadIdx.x][2] = a_hi; red[threadIdx.x][3] = b_hi;
@@ -465,23 +423,36 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
     const float2 m_lo = __ldg(&mr[(size_t)b * 32 + g_lo]), m_hi = __ldg(&mr[(size_t)b * 32 + g_hi]);
     const float2 k_lo = __ldg(&mm[(size_t)b * 32 + g_lo]), k_hi = __ldg(&mm[(size_t)b * 32 + g_hi]);
     const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        float fx[8], fd[8], fr[8], o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), fx);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C)), fd);
-        if (resid != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(resid + base + (size_t)p * C)), fr);
+    constexpr int U = 2;
+    for (int p = p0 + pl; p < p1; p += PL * U) {
+        uint4 ux[U], ud[U], ur[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float u = fmaf(fx[j], sc[j], sh[j]);
-            const float dxh = fd[j] * dact(u, silu) * gm[j];
-            const float2 m = j < 4 ? m_lo : m_hi;
-            const float2 k = j < 4 ? k_lo : k_hi;
-            const float xh = (fx[j] - m.x) * m.y;
-            float v = m.y * (dxh - k.x - xh * k.y);
-            if (resid != nullptr) v += fr[j];
-            o[j] = v;
+        for (int q = 0; q < U; ++q)
+            if (p + q * PL < p1) {
+                ux[q] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + q * PL) * C));
+                ud[q] = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)(p + q * PL) * C));
+                if (resid != nullptr) ur[q] = __ldg(reinterpret_cast<const uint4*>(resid + base + (size_t)(p + q * PL) * C));
+            }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (p + q * PL >= p1) break;
+            float fx[8], fd[8], fr[8], o[8];
+            unpack8(ux[q], fx);
+            unpack8(ud[q], fd);
+            if (resid != nullptr) unpack8(ur[q], fr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float u = fmaf(fx[j], sc[j], sh[j]);
+                const float dxh = fd[j] * dact(u, silu) * gm[j];
+                const float2 m = j < 4 ? m_lo : m_hi;
+                const float2 k = j < 4 ? k_lo : k_hi;
+                const float xh = (fx[j] - m.x) * m.y;
+                float v = m.y * (dxh - k.x - xh * k.y);
+                if (resid != nullptr) v += fr[j];
+                o[j] = v;
+            }
+            *reinterpret_cast<uint4*>(dx + base + (size_t)(p + q * PL) * C) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(dx + base + (size_t)p * C) = pack8(o);
     }
 }
 

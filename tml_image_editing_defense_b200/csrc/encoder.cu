@@ -201,6 +201,7 @@ struct TmlEncoder {
     // parameters
     float* conv_in_w = nullptr;  // [27][C0] fp32
     float* conv_in_b = nullptr;
+    Packed conv_in_bwd;          // dgrad as a GEMM: B[ci (3, padded to 16)][t*C0 + co]
     std::vector<Resnet> resnets;          // in forward order (down blocks then mid[0], mid[1])
     std::vector<Conv3> downs;
     bool has_attn = false;
@@ -712,6 +713,12 @@ int tml_encoder_finalize(TmlEncoder* e, void* stream) {
             for (int k = 0; k < 27; ++k) kc[(size_t)k * C0 + co] = w->v[(size_t)co * 27 + k];
         RC(upload<float>(e, kc, &e->conv_in_w));
         RC(upload<float>(e, b->v, &e->conv_in_b));
+        // input gradient runs on the tensor cores: N = 3 padded to 16 (UMMA needs N % 16 == 0 at M = 128)
+        std::vector<float> w16((size_t)C0 * 16 * 9, 0.f);
+        for (int co = 0; co < C0; ++co)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int k = 0; k < 9; ++k) w16[((size_t)co * 16 + ci) * 9 + k] = w->v[((size_t)co * 3 + ci) * 9 + k];
+        RC(make_packed(e, w16.data(), C0, 16, 1, &e->conv_in_bwd));
     }
     e->resnets.clear();
     e->downs.clear();
@@ -904,7 +911,14 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
             dump_grad(G[cur], act_bytes(B, L.res[ri].h, L.res[ri].w, e->resnets[ri].ci), r.st);
         }
     }
-    launch_conv_in_dgrad(G[cur], e->conv_in_w, dx, beta, B, H, W, e->cfg.block_out_channels[0], r.st);
+    {   // conv_in input gradient -> fp32 NCHW image gradient (the tensor PGD consumes, main.py:176);
+        // beta = 1 accumulates the grad_reps of main.py:88-102 in place.
+        const int C0 = e->cfg.block_out_channels[0];
+        GemmOp o = dense_conv_op("conv_in.dgrad", G[cur], B, H, W, C0, e->conv_in_bwd, 16, 1, H, W, nullptr, nullptr, nullptr);
+        o.D = dx; o.out_fp32 = 1; o.n_store = 3; o.beta = beta;
+        o.D_sB = (int64_t)3 * H * W; o.D_sH = W; o.D_sW = 1; o.D_sN = (int64_t)H * W;
+        RC(gemm_launch(o, e->num_sms, r.st));
+    }
     if (r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -982,6 +996,7 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
     o.R_sB = d->R_sB; o.R_sH = d->R_sH; o.R_sW = d->R_sW;
     o.D = d->D; o.out_fp32 = d->out_fp32;
     o.D_sB = d->D_sB; o.D_sH = d->D_sH; o.D_sW = d->D_sW; o.D_sN = d->D_sN; o.n_store = d->n_store;
+    o.beta = d->beta;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return gemm_launch(o, sms, reinterpret_cast<cudaStream_t>(stream));

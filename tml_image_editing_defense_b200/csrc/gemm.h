@@ -34,6 +34,7 @@ struct GemmOp {
     int out_fp32 = 0;  // 0: bf16, 1: fp32
     int64_t D_sB = 0, D_sH = 0, D_sW = 0, D_sN = 1;
     int n_store = 0;  // store only columns n < n_store (0 = N)
+    float beta = 0.f;  // fp32 outputs only: D = beta * D + result (grad_reps accumulation)
     const char* name = "";
 };
 

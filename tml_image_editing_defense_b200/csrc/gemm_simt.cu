@@ -26,6 +26,7 @@ struct SimtParams {
     int out_fp32;
     long long D_sB, D_sH, D_sW, D_sN;
     int n_store;
+    float beta;
 };
 
 __global__ void conv_gemm_simt_kernel(const SimtParams p) {
@@ -51,7 +52,7 @@ __global__ void conv_gemm_simt_kernel(const SimtParams p) {
         if (p.bias) v += p.bias[n];
         if (p.resid) v += __bfloat162float(p.resid[(long long)b * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW + n]);
         const long long o = (long long)b * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW + (long long)n * p.D_sN;
-        if (p.out_fp32) reinterpret_cast<float*>(p.D)[o] = v;
+        if (p.out_fp32) reinterpret_cast<float*>(p.D)[o] = p.beta != 0.f ? fmaf(p.beta, reinterpret_cast<float*>(p.D)[o], v) : v;
         else reinterpret_cast<__nv_bfloat16*>(p.D)[o] = __float2bfloat16_rn(v);
     }
 }
@@ -72,6 +73,7 @@ int gemm_launch_simt(const GemmOp& op, cudaStream_t stream) {
     p.D = op.D; p.out_fp32 = op.out_fp32;
     p.D_sB = op.D_sB; p.D_sH = op.D_sH; p.D_sW = op.D_sW; p.D_sN = op.D_sN;
     p.n_store = op.n_store > 0 ? op.n_store : op.N;
+    p.beta = op.out_fp32 ? op.beta : 0.f;
     const long long total = (long long)op.A_B * op.OH * op.OW * op.N;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;

@@ -150,6 +150,7 @@ struct TcParams {
     int out_fp32;
     long long D_sB, D_sH, D_sW, D_sN;
     int n_store;
+    float beta;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
             f[8 * j + 6] += bf16_lo(r.w); f[8 * j + 7] += bf16_hi(r.w);
         }
     }
-    if (p.D_sN == 1 && n0 + NC <= p.n_store) {
+    if (p.D_sN == 1 && n0 + NC <= p.n_store && p.beta == 0.f) {
         if (p.out_fp32) {
             float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n0);
 #pragma unroll
@@ -200,8 +201,12 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
         for (int j = 0; j < NC; ++j) {
             if (n0 + j < p.n_store) {
                 long long o = d_off + (long long)(n0 + j) * p.D_sN;
-                if (p.out_fp32) reinterpret_cast<float*>(p.D)[o] = f[j];
-                else reinterpret_cast<__nv_bfloat16*>(p.D)[o] = __float2bfloat16_rn(f[j]);
+                if (p.out_fp32) {
+                    float* dp = reinterpret_cast<float*>(p.D) + o;
+                    *dp = p.beta != 0.f ? fmaf(p.beta, *dp, f[j]) : f[j];
+                } else {
+                    reinterpret_cast<__nv_bfloat16*>(p.D)[o] = __float2bfloat16_rn(f[j]);
+                }
             }
         }
     }
@@ -446,6 +451,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.D = op.D; p.out_fp32 = op.out_fp32;
     p.D_sB = op.D_sB; p.D_sH = op.D_sH; p.D_sW = op.D_sW; p.D_sN = op.D_sN;
     p.n_store = op.n_store > 0 ? op.n_store : op.N;
+    p.beta = op.out_fp32 ? op.beta : 0.f;
 
     static bool attr_set = false;
     if (!attr_set) {

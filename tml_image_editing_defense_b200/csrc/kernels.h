@@ -11,9 +11,6 @@ typedef __nv_bfloat16 bf16;
 // conv_in (3 -> C0, 3x3 s1 p1): fp32 NCHW image -> bf16 NHWC.  w_kc: [27][C0] fp32 (k = ci*9+r*3+s).
 void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf16* y, int B, int H, int W, int C0,
                         cudaStream_t s);
-// its input gradient: bf16 NHWC dY -> fp32 NCHW dX (dX = beta*dX + result).  w_kc as above.
-void launch_conv_in_dgrad(const bf16* dy, const float* w_kc, float* dx, float beta, int B, int H, int W, int C0,
-                          cudaStream_t s);
 
 // GroupNorm(32 groups) over bf16 [B, HW, C].
 //   partial: [B][chunks][32][2] fp32 scratch;  ss: [B][C] float2 (scale, shift);  mr: [B][32] float2 (mean, rstd)

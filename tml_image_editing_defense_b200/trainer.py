@@ -24,7 +24,7 @@ from .vae import AutoencoderKL
 
 class Trainer:
     def __init__(self, cfg: TrainConfig, vae: AutoencoderKL, use_sdxl: bool = False, use_lcm: bool = False,
-                 micro_batch: int = 16):
+                 micro_batch: int = 16, num_streams: int = 2):
         self.cfg = cfg
         self.vae = vae
         self.use_sdxl = use_sdxl
@@ -32,6 +32,10 @@ class Trainer:
         self.device = torch.device(cfg.device)
         self.dtype = torch.float32  # main.py:33
         self.micro_batch = micro_batch
+        # Images are independent, so consecutive micro-batches run on alternating CUDA streams: the
+        # HBM-bound GroupNorm / SiLU passes of one overlap the tensor-core-bound GEMMs of the other.
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, num_streams))] \
+            if num_streams > 1 else []
         self.noises: Optional[List[torch.Tensor]] = None
         self._noise_shape = None
         self._rng = torch.Generator(device="cpu").manual_seed(cfg.seed)
@@ -74,11 +78,27 @@ class Trainer:
         grad = grad_out if grad_out is not None else torch.empty_like(cur_image)
         losses = torch.empty(B, dtype=torch.float32, device=self.device)
         mb = self.micro_batch
-        for s in range(0, B, mb):
-            e = min(B, s + mb)
-            _, l, _ = self.vae.attack_grad(cur_image[s:e], target_latent[s:e], eps[s:e], kind=self.cfg.loss_kind,
-                                           grad_out=grad[s:e], beta=beta, grad_scale=self.cfg.rec_loss_lambda)
-            losses[s:e] = l
+        chunks = [(s, min(B, s + mb)) for s in range(0, B, mb)]
+        if len(chunks) == 1 or not self._streams:
+            for s, e in chunks:
+                _, l, _ = self.vae.attack_grad(cur_image[s:e], target_latent[s:e], eps[s:e], kind=self.cfg.loss_kind,
+                                               grad_out=grad[s:e], beta=beta, grad_scale=self.cfg.rec_loss_lambda)
+                losses[s:e] = l
+        else:
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            used = self._streams[:min(len(self._streams), len(chunks))]
+            for st in used:
+                st.wait_event(ready)
+            for i, (s, e) in enumerate(chunks):
+                with torch.cuda.stream(used[i % len(used)]):
+                    _, l, _ = self.vae.attack_grad(cur_image[s:e], target_latent[s:e], eps[s:e],
+                                                   kind=self.cfg.loss_kind, grad_out=grad[s:e], beta=beta,
+                                                   grad_scale=self.cfg.rec_loss_lambda)
+                    losses[s:e] = l
+            for st in used:
+                main.wait_stream(st)
         rec = losses.mean()
         loss_dict = {"rec_loss": rec, "pert_loss": 0.0, "per_image": losses}
         return grad, rec * self.cfg.rec_loss_lambda, None, loss_dict

@@ -109,8 +109,10 @@ class AutoencoderKL:
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(self._lib.tml_encoder_create(C.byref(cfg), idx, C.byref(h)))
         self._h = h
-        self._ws: Optional[torch.Tensor] = None
-        self._scratch_saved: Optional[torch.Tensor] = None
+        # scratch is per CUDA stream: independent micro-batches may run concurrently on several
+        # streams (Trainer), each with its own workspace / saved-state buffer
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._scratch_saved: Dict[int, torch.Tensor] = {}
         self._finalized = False
 
     # ------------------------------------------------------------------ weights
@@ -157,10 +159,14 @@ class AutoencoderKL:
     def _buffers(self, B: int, H: int, W: int):
         ws_b, sv_b = C.c_size_t(), C.c_size_t()
         _lib.check(self._lib.tml_encoder_query(self._h, B, H, W, C.byref(ws_b), C.byref(sv_b)))
-        if self._ws is None or self._ws.numel() < ws_b.value:
-            self._ws = None
-            self._ws = torch.empty(ws_b.value, dtype=torch.uint8, device=self.device)
-        return self._ws, sv_b.value
+        key = torch.cuda.current_stream().cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < ws_b.value:
+            self._ws.pop(key, None)
+            ws = None
+            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws, sv_b.value
 
     def _forward_raw(self, x: torch.Tensor, keep: bool, saved: Optional[torch.Tensor] = None):
         if not self._finalized:
@@ -174,10 +180,13 @@ class AutoencoderKL:
             if keep:
                 saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
             else:
-                if self._scratch_saved is None or self._scratch_saved.numel() < sv_bytes:
-                    self._scratch_saved = None
-                    self._scratch_saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
-                saved = self._scratch_saved
+                key = torch.cuda.current_stream().cuda_stream
+                saved = self._scratch_saved.get(key)
+                if saved is None or saved.numel() < sv_bytes:
+                    self._scratch_saved.pop(key, None)
+                    saved = None
+                    saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
+                    self._scratch_saved[key] = saved
         L2 = 2 * self.config.latent_channels
         f = 2 ** (len(self.config.block_out_channels) - 1)
         moments = torch.empty((B, L2, H // f, W // f), dtype=torch.float32, device=self.device)
