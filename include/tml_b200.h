@@ -104,8 +104,12 @@ typedef struct TmlGemmDesc {
     const void* Bm; int N; int64_t B_sN, B_sBatch;
     float alpha; const float* bias; const void* resid; int64_t R_sB, R_sH, R_sW;
     void* D; int out_fp32; int64_t D_sB, D_sH, D_sW, D_sN; int n_store; float beta;
+    /* fused GroupNorm reductions of the output (see csrc/gemm.h): mode 1 = (sum, sumsq), 2 = backward sums */
+    int gn_mode; float* gn_partial; const void* gn_x; const void* gn_ss; const void* gn_mr; const float* gn_gamma; int gn_silu;
 } TmlGemmDesc;
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
+/* entries per image of the partial buffer a gn_mode GEMM writes: [B][tiles][32][2] floats */
+int tml_debug_gn_tiles_per_image(int OH, int OW);
 /* Offsets (bytes into `saved`) and [B,H,W,C] dims of the bf16 NHWC activations the forward keeps:
  * "conv_in", "resnet_h1"/"resnet_out" (index = resnet in forward order), "down_out", "attn_qkv",
  * "attn_P" ([B,tok,tok,1]), "attn_out". */

@@ -35,6 +35,8 @@ class TmlGemmDesc(C.Structure):
         ("R_sB", C.c_int64), ("R_sH", C.c_int64), ("R_sW", C.c_int64),
         ("D", C.c_void_p), ("out_fp32", C.c_int),
         ("D_sB", C.c_int64), ("D_sH", C.c_int64), ("D_sW", C.c_int64), ("D_sN", C.c_int64), ("n_store", C.c_int), ("beta", C.c_float),
+        ("gn_mode", C.c_int), ("gn_partial", C.c_void_p), ("gn_x", C.c_void_p), ("gn_ss", C.c_void_p),
+        ("gn_mr", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_silu", C.c_int),
     ]
 
 
@@ -67,6 +69,7 @@ SIGNATURES = {
     "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),
     "tml_debug_set_gemm_impl": (None, [C.c_int]),
     "tml_debug_gemm": (C.c_int, [C.POINTER(TmlGemmDesc), C.c_void_p]),
+    "tml_debug_gn_tiles_per_image": (C.c_int, [C.c_int, C.c_int]),
     "tml_debug_saved_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "tml_debug_set_grad_dump": (None, [C.c_void_p, C.c_size_t, C.c_int]),
     "tml_debug_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),

@@ -164,8 +164,10 @@ void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf
 // pixels of one image; thread = (channel octet, pixel lane); consecutive threads read consecutive
 // 16-byte vectors, so every access is a full 128-byte line.
 // ================================================================================================
-constexpr int kGnPixPerChunk = 512;
-int gn_num_chunks(int HW) { return (HW + kGnPixPerChunk - 1) / kGnPixPerChunk; }
+// Pixels per block: every thread owns ~16 pixels of one channel octet, whatever C is, so the small
+// 64x64 layers still launch ~1000 blocks (a fixed 512-pixel chunk left them at < 1 block per SM).
+__host__ __device__ inline int gn_pix_per_chunk(int C) { return 32768 / C; }
+int gn_num_chunks(int HW, int C) { const int p = gn_pix_per_chunk(C); return (HW + p - 1) / p; }
 
 // partial[b][chunk][g] = (sum, sumsq) over the chunk's pixels of group g
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW,
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
     const int C8 = C >> 3, PL = 256 / C8;
     const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
     const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-    const int p0 = chunk * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    const int p0 = chunk * gn_pix_per_chunk(C), p1 = min(HW, p0 + gn_pix_per_chunk(C));
     float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
     const bf16* base = x + (size_t)b * HW * C + (size_t)oct * 8;
     constexpr int U = 4;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
 }
 
 void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s) {
-    dim3 grid(gn_num_chunks(HW), B);
+    dim3 grid(gn_num_chunks(HW, C), B);
     gn_stats_kernel<<<grid, 256, 0, s>>>(x, partial, HW, C);
     COUNT_LAUNCH();
 }
@@ -225,16 +227,25 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
                                                           const float* __restrict__ beta, float2* __restrict__ ss,
                                                           float2* __restrict__ mr, int nchunks, int HW, int C,
                                                           float eps) {
+    __shared__ double red[8][32][2];
     __shared__ float2 smr[32];
     const int b = blockIdx.x;
+    {   // thread = (group, slice): 8 slices of the chunk list per group, combined in fixed order
+        const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        double s = 0.0, q = 0.0;
+        for (int c = sl; c < nchunks; c += 8) {
+            const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2);
+            s += (double)v.x;
+            q += (double)v.y;
+        }
+        red[sl][g][0] = s;
+        red[sl][g][1] = q;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         const int g = threadIdx.x;
         double s = 0.0, q = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            const float* in = partial + (((size_t)b * nchunks + c) * 32 + g) * 2;
-            s += (double)in[0];
-            q += (double)in[1];
-        }
+        for (int sl = 0; sl < 8; ++sl) { s += red[sl][g][0]; q += red[sl][g][1]; }
         const double n = (double)HW * (C / 32);
         const double mean = s / n;
         double var = q / n - mean * mean;
@@ -253,8 +264,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
 }
 
 void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
-                        int HW, int C, float eps, cudaStream_t s) {
-    gn_finalize_kernel<<<B, 256, 0, s>>>(partial, gamma, beta, ss, mr, gn_num_chunks(HW), HW, C, eps);
+                        int HW, int C, float eps, int nchunks, cudaStream_t s) {
+    gn_finalize_kernel<<<B, 256, 0, s>>>(partial, gamma, beta, ss, mr, nchunks, HW, C, eps);
     COUNT_LAUNCH();
 }
 
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     const int C8 = C >> 3, PL = 256 / C8;
     const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
     const int b = blockIdx.y;
-    const int p0 = blockIdx.x * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    const int p0 = blockIdx.x * gn_pix_per_chunk(C), p1 = min(HW, p0 + gn_pix_per_chunk(C));
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 }
 
 void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s) {
-    dim3 grid(gn_num_chunks(HW), B);
+    dim3 grid(gn_num_chunks(HW, C), B);
     gn_apply_kernel<<<grid, 256, 0, s>>>(x, ss, y, HW, C, silu);
     COUNT_LAUNCH();
 }
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restr
     const int C8 = C >> 3, PL = 256 / C8, cpg = C / 32;
     const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
     const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-    const int p0 = chunk * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    const int p0 = chunk * gn_pix_per_chunk(C), p1 = min(HW, p0 + gn_pix_per_chunk(C));
     float sc[8], sh[8], gm[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -375,29 +386,35 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restr
 
 void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
                            float* partial, int B, int HW, int C, int silu, cudaStream_t s) {
-    dim3 grid(gn_num_chunks(HW), B);
+    dim3 grid(gn_num_chunks(HW, C), B);
     gn_bwd_partial_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, gamma, partial, HW, C, silu);
     COUNT_LAUNCH();
 }
 
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float2* __restrict__ mm, int nchunks,
-                                       int HW, int C, int total) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = b*32 + g
-    if (i >= total) return;
-    const int b = i / 32, g = i % 32;
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial,
+                                                              float2* __restrict__ mm, int nchunks, int HW, int C) {
+    __shared__ double red[8][32][2];
+    const int b = blockIdx.x;
+    const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
     double s = 0.0, q = 0.0;
-    for (int c = 0; c < nchunks; ++c) {
-        const float* in = partial + (((size_t)b * nchunks + c) * 32 + g) * 2;
-        s += (double)in[0];
-        q += (double)in[1];
+    for (int c = sl; c < nchunks; c += 8) {
+        const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2);
+        s += (double)v.x;
+        q += (double)v.y;
     }
-    const double n = (double)HW * (C / 32);
-    mm[i] = make_float2((float)(s / n), (float)(q / n));
+    red[sl][g][0] = s;
+    red[sl][g][1] = q;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = 0.0; q = 0.0;
+        for (int k = 0; k < 8; ++k) { s += red[k][g][0]; q += red[k][g][1]; }
+        const double n = (double)HW * (C / 32);
+        mm[(size_t)b * 32 + g] = make_float2((float)(s / n), (float)(q / n));
+    }
 }
 
-void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, cudaStream_t s) {
-    const int total = B * 32;
-    gn_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partial, mm, gn_num_chunks(HW), HW, C, total);
+void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, int nchunks, cudaStream_t s) {
+    gn_bwd_finalize_kernel<<<B, 256, 0, s>>>(partial, mm, nchunks, HW, C);
     COUNT_LAUNCH();
 }
 
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
     const int C8 = C >> 3, PL = 256 / C8, cpg = C / 32;
     const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
     const int b = blockIdx.y;
-    const int p0 = blockIdx.x * kGnPixPerChunk, p1 = min(HW, p0 + kGnPixPerChunk);
+    const int p0 = blockIdx.x * gn_pix_per_chunk(C), p1 = min(HW, p0 + gn_pix_per_chunk(C));
     float sc[8], sh[8], gm[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
 void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
                          const float* gamma, const bf16* resid, bf16* dx, int B, int HW, int C, int silu,
                          cudaStream_t s) {
-    dim3 grid(gn_num_chunks(HW), B);
+    dim3 grid(gn_num_chunks(HW, C), B);
     gn_bwd_apply_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, mm, gamma, resid, dx, HW, C, silu);
     COUNT_LAUNCH();
 }
@@ -529,28 +546,48 @@ void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float sca
     COUNT_LAUNCH();
 }
 
-// out[b][c][r] = in[b][r][c]
+// out[b][c][r] = in[b][r][c].  64x64 tiles; each thread moves bf16 pairs (4-byte accesses, 128-byte
+// warp transactions on both sides); the +2 padding keeps the column reads bank-conflict free.
 __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R,
                                                         int C, long long ld_in, long long bs_in, long long ld_out,
                                                         long long bs_out) {
-    __shared__ bf16 tile[32][34];
+    __shared__ bf16 tile[64][66];
     const int b = blockIdx.z;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + tx;
-        if (r < R && c < C) tile[i][tx] = in[(size_t)b * bs_in + (size_t)r * ld_in + c];
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + tx;
-        if (r < R && c < C) out[(size_t)b * bs_out + (size_t)c * ld_out + r] = tile[tx][i];
+    const bool full = (r0 + 64 <= R) && (c0 + 64 <= C);
+    if (full) {
+#pragma unroll
+        for (int i = ty; i < 64; i += 8) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(in + (size_t)b * bs_in + (size_t)(r0 + i) * ld_in + c0 + 2 * tx);
+            *reinterpret_cast<uint32_t*>(&tile[i][2 * tx]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 64; i += 8) {
+            __nv_bfloat162 v;
+            v.x = tile[2 * tx][i];
+            v.y = tile[2 * tx + 1][i];
+            *reinterpret_cast<__nv_bfloat162*>(out + (size_t)b * bs_out + (size_t)(c0 + i) * ld_out + r0 + 2 * tx) = v;
+        }
+    } else {
+        for (int i = ty; i < 64; i += 8)
+            for (int j = tx; j < 64; j += 32) {
+                const int r = r0 + i, c = c0 + j;
+                if (r < R && c < C) tile[i][j] = in[(size_t)b * bs_in + (size_t)r * ld_in + c];
+            }
+        __syncthreads();
+        for (int i = ty; i < 64; i += 8)
+            for (int j = tx; j < 64; j += 32) {
+                const int c = c0 + i, r = r0 + j;
+                if (r < R && c < C) out[(size_t)b * bs_out + (size_t)c * ld_out + r] = tile[j][i];
+            }
     }
 }
 
 void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
                       long long ld_out, long long bs_out, cudaStream_t s) {
-    dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
+    dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
     transpose_kernel<<<grid, 256, 0, s>>>(in, out, R, C, ld_in, bs_in, ld_out, bs_out);
     COUNT_LAUNCH();
 }

@@ -305,7 +305,10 @@ static int make_resnet(TmlEncoder* e, const std::string& key, int Ci, int Co, Re
 // layout (what lives where in `saved`; how much scratch the walks need)
 // ------------------------------------------------------------------------------------------------
 static size_t act_bytes(int B, int h, int w, int c) { return (size_t)B * h * w * c * sizeof(bf16); }
-static size_t gn_partial_bytes(int B, int hw) { return (size_t)B * gn_num_chunks(hw) * 32 * 2 * sizeof(float); }
+// partial sums written by a GEMM epilogue: one entry per (image, 128-row tile, group)
+static size_t fused_partial_bytes(int B, int h, int w) { return (size_t)B * gemm_gn_tiles_per_image(h, w) * 32 * 2 * sizeof(float); }
+// sized for the smallest channel count (largest chunk count) so one bound covers every layer
+static size_t gn_partial_bytes(int B, int hw) { return (size_t)B * gn_num_chunks(hw, 512) * 32 * 2 * sizeof(float); }
 
 static GnSaved alloc_gn(Arena& a, int B, int C) {
     GnSaved g;
@@ -404,7 +407,7 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
         }
     }
     L.saved_bytes = S.peak + 256;
-    L.ws_bytes = ws_peak + 2 * (gmax + 256) + (64 << 10);
+    L.ws_bytes = ws_peak + 2 * (gmax + 256) + 3 * (fused_partial_bytes(B, H, W) + 256) + (64 << 10);
     return 0;
 }
 
@@ -445,6 +448,12 @@ static void dump_grad(const void* p, size_t bytes, cudaStream_t st) {
     ++g_dump_next;
 }
 
+// Partial GroupNorm sums already produced by a GEMM epilogue (null = run the reduction kernel).
+struct Partials {
+    float* p = nullptr;
+    int nchunks = 0;
+};
+
 struct Run {
     TmlEncoder* e;
     char* saved;
@@ -452,29 +461,72 @@ struct Run {
     Arena wsa;
     cudaStream_t st;
     int B;
+    float* statbuf[2] = {nullptr, nullptr};  // forward: ping-pong buffers for epilogue-fused GroupNorm statistics
+    Partials pending;                         // statistics of the current activation, if its producer fused them
     template <typename T> T* S(size_t off) const { return reinterpret_cast<T*>(saved + off); }
     template <typename T> T* Walloc(size_t bytes) { return reinterpret_cast<T*>(ws + wsa.alloc(bytes)); }
 };
 
-static int gn_forward(Run& r, const bf16* x, const Norm& n, const GnSaved& g, bf16* y, int hw, int silu) {
+
+static int gn_forward(Run& r, const bf16* x, const Norm& n, const GnSaved& g, bf16* y, int hw, int silu,
+                      const Partials& pre = Partials()) {
     const size_t m = r.wsa.mark();
-    float* part = r.Walloc<float>(gn_partial_bytes(r.B, hw));
-    launch_gn_stats(x, part, r.B, hw, n.C, r.st);
-    launch_gn_finalize(part, n.gamma, n.beta, r.S<float2>(g.ss), r.S<float2>(g.mr), r.B, hw, n.C, r.e->cfg.norm_eps, r.st);
+    const float* part = pre.p;
+    int nchunks = pre.nchunks;
+    if (!part) {
+        float* own = r.Walloc<float>(gn_partial_bytes(r.B, hw));
+        launch_gn_stats(x, own, r.B, hw, n.C, r.st);
+        part = own;
+        nchunks = gn_num_chunks(hw, n.C);
+    }
+    launch_gn_finalize(part, n.gamma, n.beta, r.S<float2>(g.ss), r.S<float2>(g.mr), r.B, hw, n.C, r.e->cfg.norm_eps,
+                       nchunks, r.st);
     launch_gn_apply(x, r.S<float2>(g.ss), y, r.B, hw, n.C, silu, r.st);
     r.wsa.reset(m);
     return 0;
 }
 static int gn_backward(Run& r, const bf16* x, const bf16* dy, const Norm& n, const GnSaved& g, const bf16* resid,
-                       bf16* dx, int hw, int silu) {
+                       bf16* dx, int hw, int silu, const Partials& pre = Partials()) {
     const size_t m = r.wsa.mark();
-    float* part = r.Walloc<float>(gn_partial_bytes(r.B, hw));
+    const float* part = pre.p;
+    int nchunks = pre.nchunks;
+    if (!part) {
+        float* own = r.Walloc<float>(gn_partial_bytes(r.B, hw));
+        launch_gn_bwd_partial(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), n.gamma, own, r.B, hw, n.C, silu, r.st);
+        part = own;
+        nchunks = gn_num_chunks(hw, n.C);
+    }
     float2* mm = r.Walloc<float2>((size_t)r.B * 32 * sizeof(float2));
-    launch_gn_bwd_partial(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), n.gamma, part, r.B, hw, n.C, silu, r.st);
-    launch_gn_bwd_finalize(part, mm, r.B, hw, n.C, r.st);
+    launch_gn_bwd_finalize(part, mm, r.B, hw, n.C, nchunks, r.st);
     launch_gn_bwd_apply(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), mm, n.gamma, resid, dx, r.B, hw, n.C, silu, r.st);
     r.wsa.reset(m);
     return 0;
+}
+// Ask a GEMM to also reduce (sum, sumsq) of its output per (image, tile, group).
+static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
+    if (gemm_get_impl() != 0) return Partials();  // the SIMT debug kernel has no fused reductions
+    o.gn_mode = 1;
+    o.gn_partial = buf;
+    Partials p;
+    p.p = buf;
+    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    return p;
+}
+// Ask a dgrad GEMM to also reduce the GroupNorm-backward sums of the norm whose output it differentiates.
+static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
+                            int oh, int ow) {
+    if (gemm_get_impl() != 0) return Partials();
+    o.gn_mode = 2;
+    o.gn_partial = buf;
+    o.gn_x = x;
+    o.gn_ss = r.S<float2>(g.ss);
+    o.gn_mr = r.S<float2>(g.mr);
+    o.gn_gamma = n.gamma;
+    o.gn_silu = silu;
+    Partials p;
+    p.p = buf;
+    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    return p;
 }
 
 static int resnet_forward(Run& r, const Resnet& p, const ResnetRec& rec) {
@@ -483,19 +535,22 @@ static int resnet_forward(Run& r, const Resnet& p, const ResnetRec& rec) {
     const bf16* x = r.S<bf16>(rec.x);
     const size_t m = r.wsa.mark();
     bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
-    RC(gn_forward(r, x, p.n1, rec.g1, a, hw, 1));
+    RC(gn_forward(r, x, p.n1, rec.g1, a, hw, 1, r.pending));
     bf16* h1 = r.S<bf16>(rec.h1);
-    RC(gemm_launch(dense_conv_op("resnet.conv1", a, B, h, w, p.ci, p.c1.fwd, p.co, 1, h, w, p.c1.bias, nullptr, h1), ns, r.st));
+    GemmOp c1 = dense_conv_op("resnet.conv1", a, B, h, w, p.ci, p.c1.fwd, p.co, 1, h, w, p.c1.bias, nullptr, h1);
+    const Partials s1 = fuse_stats(c1, r.statbuf[0], h, w);     // statistics of h1 for norm2, from the epilogue
+    RC(gemm_launch(c1, ns, r.st));
     bf16* a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
-    RC(gn_forward(r, h1, p.n2, rec.g2, a2, hw, 1));
+    RC(gn_forward(r, h1, p.n2, rec.g2, a2, hw, 1, s1));
     const bf16* resid = x;
     if (p.has_sc) {
         bf16* sc = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
         RC(gemm_launch(dense_lin_op("resnet.shortcut", x, B, h, w, p.ci, p.sc.fwd, p.co, p.sc.bias, nullptr, sc), ns, r.st));
         resid = sc;
     }
-    RC(gemm_launch(dense_conv_op("resnet.conv2", a2, B, h, w, p.co, p.c2.fwd, p.co, 1, h, w, p.c2.bias, resid,
-                                 r.S<bf16>(rec.out)), ns, r.st));
+    GemmOp c2 = dense_conv_op("resnet.conv2", a2, B, h, w, p.co, p.c2.fwd, p.co, 1, h, w, p.c2.bias, resid, r.S<bf16>(rec.out));
+    r.pending = fuse_stats(c2, r.statbuf[1], h, w);             // statistics of the block output for the next norm
+    RC(gemm_launch(c2, ns, r.st));
     r.wsa.reset(m);
     return 0;
 }
@@ -505,18 +560,23 @@ static int resnet_backward(Run& r, const Resnet& p, const ResnetRec& rec, const 
     const int B = r.B, h = rec.h, w = rec.w, hw = h * w;
     const int ns = r.e->num_sms;
     const size_t m = r.wsa.mark();
+    float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
     bf16* d_a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
-    RC(gemm_launch(dense_conv_op("resnet.conv2.dgrad", dout, B, h, w, p.co, p.c2.bwd, p.co, 1, h, w, nullptr, nullptr, d_a2), ns, r.st));
+    GemmOp g2 = dense_conv_op("resnet.conv2.dgrad", dout, B, h, w, p.co, p.c2.bwd, p.co, 1, h, w, nullptr, nullptr, d_a2);
+    const Partials p2 = fuse_gn_bwd(r, g2, r.S<bf16>(rec.h1), p.n2, rec.g2, 1, pbuf, h, w);
+    RC(gemm_launch(g2, ns, r.st));
     bf16* d_h1 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
-    RC(gn_backward(r, r.S<bf16>(rec.h1), d_a2, p.n2, rec.g2, nullptr, d_h1, hw, 1));
+    RC(gn_backward(r, r.S<bf16>(rec.h1), d_a2, p.n2, rec.g2, nullptr, d_h1, hw, 1, p2));
     bf16* d_a1 = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
-    RC(gemm_launch(dense_conv_op("resnet.conv1.dgrad", d_h1, B, h, w, p.co, p.c1.bwd, p.ci, 1, h, w, nullptr, nullptr, d_a1), ns, r.st));
+    GemmOp g1 = dense_conv_op("resnet.conv1.dgrad", d_h1, B, h, w, p.co, p.c1.bwd, p.ci, 1, h, w, nullptr, nullptr, d_a1);
+    const Partials p1 = fuse_gn_bwd(r, g1, r.S<bf16>(rec.x), p.n1, rec.g1, 1, pbuf, h, w);
+    RC(gemm_launch(g1, ns, r.st));
     if (p.has_sc) {
         bf16* tmp = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
-        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, nullptr, tmp, hw, 1));
+        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, nullptr, tmp, hw, 1, p1));
         RC(gemm_launch(dense_lin_op("resnet.shortcut.dgrad", dout, B, h, w, p.co, p.sc.bwd, p.ci, nullptr, tmp, dx), ns, r.st));
     } else {
-        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, dout, dx, hw, 1));
+        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, dout, dx, hw, 1, p1));
     }
     r.wsa.reset(m);
     return 0;
@@ -528,7 +588,7 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
     const bf16* x = r.S<bf16>(rec.x);
     const size_t m = r.wsa.mark();
     bf16* t = r.Walloc<bf16>(act_bytes(B, h, w, C));
-    RC(gn_forward(r, x, p.gn, rec.g, t, tok, 0));
+    RC(gn_forward(r, x, p.gn, rec.g, t, tok, 0, r.pending));
     bf16* qkv = r.S<bf16>(rec.qkv);
     RC(gemm_launch(dense_lin_op("attn.qkv", t, B, h, w, C, p.qkv.fwd, 3 * C, p.qkv.bias, nullptr, qkv), ns, r.st));
     // S = QK^T / sqrt(C)   (fp32, [B][tok][tok])
@@ -559,7 +619,9 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
         o.D = a; o.D_sW = C; o.D_sH = (int64_t)w * C; o.D_sB = (int64_t)tok * C; o.D_sN = 1;
         RC(gemm_launch(o, ns, r.st));
     }
-    RC(gemm_launch(dense_lin_op("attn.out", a, B, h, w, C, p.out.fwd, C, p.out.bias, x, r.S<bf16>(rec.out)), ns, r.st));
+    GemmOp oo = dense_lin_op("attn.out", a, B, h, w, C, p.out.fwd, C, p.out.bias, x, r.S<bf16>(rec.out));
+    r.pending = fuse_stats(oo, r.statbuf[1], h, w);
+    RC(gemm_launch(oo, ns, r.st));
     r.wsa.reset(m);
     return 0;
 }
@@ -613,8 +675,11 @@ static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* 
     RC(tok_gemm("attn.dK", dST, Qt, dqkv + C));
     RC(tok_gemm("attn.dV", PT, daT, dqkv + 2 * C));
     bf16* dt = r.Walloc<bf16>(act);
-    RC(gemm_launch(dense_lin_op("attn.qkv.dgrad", dqkv, B, h, w, 3 * C, p.qkv.bwd, C, nullptr, nullptr, dt), ns, r.st));
-    RC(gn_backward(r, r.S<bf16>(rec.x), dt, p.gn, rec.g, dout, dx, tok, 0));
+    GemmOp gq = dense_lin_op("attn.qkv.dgrad", dqkv, B, h, w, 3 * C, p.qkv.bwd, C, nullptr, nullptr, dt);
+    float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
+    const Partials pq = fuse_gn_bwd(r, gq, r.S<bf16>(rec.x), p.gn, rec.g, 0, pbuf, h, w);
+    RC(gemm_launch(gq, ns, r.st));
+    RC(gn_backward(r, r.S<bf16>(rec.x), dt, p.gn, rec.g, dout, dx, tok, 0, pq));
     r.wsa.reset(m);
     return 0;
 }
@@ -818,6 +883,8 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
     const Layout& L = e->lay;
     Run r{e, reinterpret_cast<char*>(saved), reinterpret_cast<char*>(ws), Arena(), reinterpret_cast<cudaStream_t>(stream), B};
     const int C0 = e->cfg.block_out_channels[0];
+    r.statbuf[0] = r.Walloc<float>(fused_partial_bytes(B, H, W));
+    r.statbuf[1] = r.Walloc<float>(fused_partial_bytes(B, H, W));
     launch_conv_in_fwd(x, e->conv_in_w, e->conv_in_b, r.S<bf16>(L.x0), B, H, W, C0, r.st);
     size_t ri = 0, di = 0;
     for (int i = 0; i < e->cfg.num_blocks; ++i) {
@@ -825,8 +892,10 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
         if (i != e->cfg.num_blocks - 1) {
             const DownRec& d = L.down[di];
             const Conv3& c = e->downs[di];
-            RC(gemm_launch(dense_conv_op("downsample", r.S<bf16>(d.x), B, d.h, d.w, c.ci, c.fwd, c.co, 2, d.h / 2, d.w / 2,
-                                         c.bias, nullptr, r.S<bf16>(d.out)), e->num_sms, r.st));
+            GemmOp dn = dense_conv_op("downsample", r.S<bf16>(d.x), B, d.h, d.w, c.ci, c.fwd, c.co, 2, d.h / 2, d.w / 2,
+                                      c.bias, nullptr, r.S<bf16>(d.out));
+            r.pending = fuse_stats(dn, r.statbuf[1], d.h / 2, d.w / 2);
+            RC(gemm_launch(dn, e->num_sms, r.st));
             ++di;
         }
     }
@@ -836,7 +905,7 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
     {   // conv_norm_out + SiLU + (conv_out o quant_conv) -> fp32 NCHW moments
         const int h = L.hl, w = L.wl, C = e->norm_out.C, L2 = 2 * e->cfg.latent_channels;
         bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, C));
-        RC(gn_forward(r, r.S<bf16>(L.xlast), e->norm_out, L.gout, a, h * w, 1));
+        RC(gn_forward(r, r.S<bf16>(L.xlast), e->norm_out, L.gout, a, h * w, 1, r.pending));
         GemmOp o = dense_conv_op("conv_out", a, B, h, w, C, e->conv_out.fwd, 16, 1, h, w, e->conv_out.bias, nullptr, nullptr);
         o.D = moments; o.out_fp32 = 1; o.n_store = L2;
         o.D_sB = (int64_t)L2 * h * w; o.D_sH = w; o.D_sW = 1; o.D_sN = (int64_t)h * w;
@@ -874,9 +943,11 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
         bf16* dm64 = r.Walloc<bf16>(act_bytes(B, h, w, 64));
         launch_dmoments_pack(dmoments, dm64, B, h, w, r.st);
         bf16* d_a = r.Walloc<bf16>(act_bytes(B, h, w, C));
-        RC(gemm_launch(dense_conv_op("conv_out.dgrad", dm64, B, h, w, 64, e->conv_out.bwd, C, 1, h, w, nullptr, nullptr, d_a),
-                       e->num_sms, r.st));
-        RC(gn_backward(r, r.S<bf16>(L.xlast), d_a, e->norm_out, L.gout, nullptr, G[cur], h * w, 1));
+        GemmOp go = dense_conv_op("conv_out.dgrad", dm64, B, h, w, 64, e->conv_out.bwd, C, 1, h, w, nullptr, nullptr, d_a);
+        float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
+        const Partials po = fuse_gn_bwd(r, go, r.S<bf16>(L.xlast), e->norm_out, L.gout, 1, pbuf, h, w);
+        RC(gemm_launch(go, e->num_sms, r.st));
+        RC(gn_backward(r, r.S<bf16>(L.xlast), d_a, e->norm_out, L.gout, nullptr, G[cur], h * w, 1, po));
         r.wsa.reset(m);
         dump_grad(G[cur], act_bytes(B, h, w, C), r.st);
     }
@@ -997,6 +1068,9 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
     o.D = d->D; o.out_fp32 = d->out_fp32;
     o.D_sB = d->D_sB; o.D_sH = d->D_sH; o.D_sW = d->D_sW; o.D_sN = d->D_sN; o.n_store = d->n_store;
     o.beta = d->beta;
+    o.gn_mode = d->gn_mode; o.gn_partial = d->gn_partial; o.gn_x = d->gn_x;
+    o.gn_ss = reinterpret_cast<const float2*>(d->gn_ss); o.gn_mr = reinterpret_cast<const float2*>(d->gn_mr);
+    o.gn_gamma = d->gn_gamma; o.gn_silu = d->gn_silu;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return gemm_launch(o, sms, reinterpret_cast<cudaStream_t>(stream));
@@ -1039,6 +1113,8 @@ int tml_debug_saved_tensor(TmlEncoder* e, const char* name, int index, size_t* o
     set_error("unknown tensor '%s'", name);
     return -1;
 }
+
+int tml_debug_gn_tiles_per_image(int OH, int OW) { return gemm_gn_tiles_per_image(OH, OW); }
 
 int tml_debug_pack_conv3x3(const float* w, int Co, int Ci, int mode, uint16_t* out, int* ntaps, int* dh, int* dw) {
     std::vector<uint16_t> h;

@@ -35,17 +35,31 @@ struct GemmOp {
     int64_t D_sB = 0, D_sH = 0, D_sW = 0, D_sN = 1;
     int n_store = 0;  // store only columns n < n_store (0 = N)
     float beta = 0.f;  // fp32 outputs only: D = beta * D + result (grad_reps accumulation)
+    // Fused GroupNorm reductions over the bf16 output (dense NHWC, D_sN == 1, N % 32 == 0):
+    //   gn_mode 1: partial[img][tile][g] = (sum, sumsq) of the output      -> statistics of the next GroupNorm
+    //   gn_mode 2: partial[img][tile][g] = (sum dxh, sum dxh*xh), dxh = out * act'(x*sc+sh) * gamma,
+    //              xh = (x-mean)*rstd                                       -> reductions of its backward
+    // partial is [A_B][gemm_gn_tiles_per_image(op)][32][2] floats.
+    int gn_mode = 0;
+    float* gn_partial = nullptr;
+    const void* gn_x = nullptr;        // bf16, same layout as D
+    const float2* gn_ss = nullptr;     // [A_B][N]
+    const float2* gn_mr = nullptr;     // [A_B][32]
+    const float* gn_gamma = nullptr;   // [N]
+    int gn_silu = 0;
     const char* name = "";
 };
 
 // Derived tiling, shared by both kernels (the debug kernel ignores the tile fields).
 struct GemmTiling {
-    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages;
+    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes;
     size_t smem_bytes;
 };
 
 // Returns 0 and fills `t`, or a negative value and sets the thread-local error message.
 int gemm_plan(const GemmOp& op, GemmTiling* t);
+// number of 128-row tiles per image (= chunk count of the fused GroupNorm partial buffer)
+int gemm_gn_tiles_per_image(int OH, int OW);
 
 // tcgen05/TMEM/TMA implicit-GEMM kernel (the product path).
 int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream);

@@ -97,20 +97,40 @@ static int largest_divisor_le(int n, int cap, int multiple_of) {
     return 0;
 }
 
+constexpr int kGnSmemBytes = 8192;  // epilogue scratch: per-tile GN constants + cross-warp reduction
+
+static void tile_shape(int OH, int OW, int* TW, int* TH) {
+    *TW = largest_divisor_le(OW, 128, 8);
+    *TH = *TW ? largest_divisor_le(OH, 128 / *TW, 1) : 0;
+}
+int gemm_gn_tiles_per_image(int OH, int OW) {
+    int TW, TH;
+    tile_shape(OH, OW, &TW, &TH);
+    return TW ? (OH / TH) * (OW / TW) : 0;
+}
+
 int gemm_plan(const GemmOp& op, GemmTiling* t) {
     if (op.A_C % kBlockK != 0) { set_error("%s: A_C=%d is not a multiple of 64", op.name, op.A_C); return -1; }
     if (op.N % 16 != 0) { set_error("%s: N=%d is not a multiple of 16", op.name, op.N); return -1; }
     if (op.stride != 1 && op.stride != 2) { set_error("%s: stride %d unsupported", op.name, op.stride); return -1; }
     if (op.ntaps < 1 || op.ntaps > kMaxTaps) { set_error("%s: ntaps=%d", op.name, op.ntaps); return -1; }
-    int TW = largest_divisor_le(op.OW, 128, 8);
+    int TW, TH;
+    tile_shape(op.OH, op.OW, &TW, &TH);
     if (TW == 0) { set_error("%s: output width %d has no tile width (multiple of 8, <=128)", op.name, op.OW); return -1; }
-    int TH = largest_divisor_le(op.OH, 128 / TW, 1);
     if (op.stride == 2 && (op.A_W % 2 != 0)) { set_error("%s: stride-2 input width must be even", op.name); return -1; }
     int BN = 0;
     if (op.N % 256 == 0) BN = 256;
     else if (op.N % 128 == 0) BN = 128;
     else if (op.N <= 256) BN = op.N;
     else { set_error("%s: N=%d unsupported (need N%%128==0 or N<=256)", op.name, op.N); return -1; }
+    if (op.gn_mode != 0) {
+        const int cpg = op.N / 32;
+        if (op.out_fp32 || op.D_sN != 1 || op.N % 32 || (cpg != 4 && cpg != 8 && cpg != 16) || BN % 32 ||
+            !op.gn_partial || (op.gn_mode == 2 && (!op.gn_x || !op.gn_ss || !op.gn_mr || !op.gn_gamma))) {
+            set_error("%s: fused GroupNorm reduction needs a dense bf16 output with N in {128,256,512}", op.name);
+            return -1;
+        }
+    }
     t->TW = TW;
     t->TH = TH;
     t->rows_valid = TW * TH;
@@ -119,14 +139,19 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     t->BN = BN;
     t->n_tiles = op.N / BN;
     t->kchunks = op.A_C / kBlockK;
-    int stage_bytes = kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
-    int stages = (kMaxSmem - 1024 - kBarrierBytes) / stage_bytes;
+    // Two 128-row sub-tiles per CTA tile when the accumulators fit (2 x 2 x BN <= 512 TMEM columns):
+    // every B (weight) tile is then fetched from L2 once per 256 output pixels instead of once per 128.
+    const long sub_tiles = (long)op.A_B * t->tiles_h * t->tiles_w;
+    t->mt = (BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
+    int stage_bytes = t->mt * kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
+    int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
     if (stages > 8) stages = 8;
     int kblocks = op.ntaps * t->kchunks;
     if (stages > kblocks && kblocks >= 2) stages = kblocks;
     if (stages < 2) stages = 2;
     t->stages = stages;
-    t->smem_bytes = size_t(stages) * stage_bytes + kBarrierBytes + 1024;
+    t->stage_bytes = stage_bytes;
+    t->smem_bytes = size_t(stages) * stage_bytes + kBarrierBytes + kGnSmemBytes + 1024;
     return 0;
 }
 
@@ -138,6 +163,7 @@ struct TcParams {
     int TW, TH, rows_valid;
     int tiles_w, tiles_h, nimg;
     int n_tiles, BN;
+    int mt;    // M sub-tiles (128 rows each) per CTA tile: 2 shares every B tile between two accumulators
     int kchunks, ntaps;
     int dh[kMaxTaps], dw[kMaxTaps];
     int b_batched;
@@ -151,6 +177,15 @@ struct TcParams {
     long long D_sB, D_sH, D_sW, D_sN;
     int n_store;
     float beta;
+    // fused GroupNorm reductions over the (bf16-rounded) output tile
+    int gn_mode;   // 0 none, 1 (sum, sumsq), 2 (sum dxh, sum dxh*xh) of the GroupNorm backward
+    int gn_cpg;    // channels per group of the output tensor (4, 8 or 16)
+    float* gn_partial;               // [nimg][tiles_h*tiles_w][32][2]
+    const __nv_bfloat16* gn_x;       // mode 2: the GroupNorm input, same layout as D
+    const float2* gn_ss;             // mode 2: [nimg][N] (scale, shift)
+    const float2* gn_mr;             // mode 2: [nimg][32] (mean, rstd)
+    const float* gn_gamma;           // mode 2: [N]
+    int gn_silu;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -159,15 +194,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
-// Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel).
+// Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel): alpha, bias,
+// residual, store.  On return f[] holds the values as stored (bf16-rounded for bf16 outputs).
 template <int NC>
-__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, bool valid, long long d_off,
-                                               long long r_off, int n0) {
-    if (!valid) return;
-    float f[NC];
+__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, float (&f)[NC], bool valid,
+                                               long long d_off, long long r_off, int n0) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    if (!valid) return;
     if (p.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < NC; ++j) f[j] += __ldg(p.bias + n0 + j);
@@ -191,9 +227,13 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
         } else {
             uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n0);
 #pragma unroll
-            for (int j = 0; j < NC / 8; ++j)
-                dp[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            for (int j = 0; j < NC / 8; ++j) {
+                const uint4 o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                dp[j] = o;
+                f[8 * j + 0] = bf16_lo(o.x); f[8 * j + 1] = bf16_hi(o.x); f[8 * j + 2] = bf16_lo(o.y); f[8 * j + 3] = bf16_hi(o.y);
+                f[8 * j + 4] = bf16_lo(o.z); f[8 * j + 5] = bf16_hi(o.z); f[8 * j + 6] = bf16_lo(o.w); f[8 * j + 7] = bf16_hi(o.w);
+            }
         }
     } else {
         // strided / partially stored columns (e.g. fp32 NCHW moments, transposed operands)
@@ -212,6 +252,70 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
     }
 }
 
+// 16 per-lane values -> their sums over the 32 lanes of the warp in 16 shuffles (halving butterfly).
+// On return, lane L holds in v[0] the total of value index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
+// The order of additions is fixed, so the result is bitwise reproducible.
+__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Per-thread partial sums over one 32-column chunk of one output row, per GroupNorm group:
+//   mode 1: gv[2g] = sum f, gv[2g+1] = sum f^2            (statistics of the tensor just produced)
+//   mode 2: gv[2g] = sum dxh, gv[2g+1] = sum dxh*xh        (GroupNorm backward reductions; f = dy)
+// CPG is a template parameter so gv[] stays in registers.
+template <int CPG>
+__device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f)[32], float (&gv)[16], bool valid,
+                                              long long d_off, int n0, int c, const float* gn_sc, const float* gn_sh,
+                                              const float* gn_gm, const float2* gn_mrs) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+    if (!valid) return;
+    if (p.gn_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            gv[2 * (j / CPG)] += f[j];
+            gv[2 * (j / CPG) + 1] = fmaf(f[j], f[j], gv[2 * (j / CPG) + 1]);
+        }
+    } else {
+        const uint4* xp = reinterpret_cast<const uint4*>(p.gn_x + d_off + n0);
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            const uint4 xr = __ldg(xp + j8);
+            const float xs[8] = {bf16_lo(xr.x), bf16_hi(xr.x), bf16_lo(xr.y), bf16_hi(xr.y),
+                                 bf16_lo(xr.z), bf16_hi(xr.z), bf16_lo(xr.w), bf16_hi(xr.w)};
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = j8 * 8 + jj;
+                const float u = fmaf(xs[jj], gn_sc[c + j], gn_sh[c + j]);
+                float da = 1.f;
+                if (p.gn_silu) {
+                    const float sg = __fdividef(1.f, 1.f + __expf(-u));
+                    da = sg * fmaf(u, 1.f - sg, 1.f);
+                }
+                const float dxh = f[j] * da * gn_gm[c + j];
+                const float2 m = gn_mrs[(c + j) / CPG];
+                const float xh = (xs[jj] - m.x) * m.y;
+                gv[2 * (j / CPG)] += dxh;
+                gv[2 * (j / CPG) + 1] = fmaf(dxh, xh, gv[2 * (j / CPG) + 1]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                          const TcParams p) {
@@ -223,6 +327,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     uint64_t* tfull_bar = empty_bar + 8;                               // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    // GN scratch (epilogue warps only): red[4 warps][8 chunks][16] floats, then per-tile constants
+    float* gn_red = reinterpret_cast<float*>(bar_base + kBarrierBytes);          // 2048 B
+    float* gn_sc = gn_red + 4 * 8 * 16;                                          // [256]
+    float* gn_sh = gn_sc + 256;                                                  // [256]
+    float* gn_gm = gn_sh + 256;                                                  // [256]
+    float2* gn_mrs = reinterpret_cast<float2*>(gn_gm + 256);                     // [64]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,10 +361,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int m_tiles = p.nimg * p.tiles_h * p.tiles_w;
+    const int sub_per_img = p.tiles_h * p.tiles_w;
+    const int m_tiles = (p.nimg * sub_per_img) / p.mt;
     const int total_tiles = m_tiles * p.n_tiles;
     const int kblocks = p.ntaps * p.kchunks;
-    const uint32_t tx_bytes = uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u;
+    const int a_bytes = p.mt * kATileBytes;
+    const uint32_t tx_bytes = uint32_t(p.mt) * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u;
+    const int acc_cols = p.mt * p.BN;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
@@ -263,27 +376,35 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
-                int mt = tile / p.n_tiles;
-                const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
-                const int th_i = mt % p.tiles_h;
-                const int img = mt / p.tiles_h;
-                const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH;
+                const int mtile = tile / p.n_tiles;
+                int img[2], ow0[2], oh0[2];
+                for (int sub = 0; sub < p.mt; ++sub) {
+                    int st = mtile * p.mt + sub;
+                    const int tw_i = st % p.tiles_w; st /= p.tiles_w;
+                    const int th_i = st % p.tiles_h;
+                    img[sub] = st / p.tiles_h;
+                    ow0[sub] = tw_i * p.TW;
+                    oh0[sub] = th_i * p.TH;
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     const int tap = kb / p.kchunks;
                     const int c0 = (kb - tap * p.kchunks) * kBlockK;
                     uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
-                    uint8_t* sB = sA + kATileBytes;
+                    uint8_t* sB = sA + a_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                    if (p.mode == 0) {
-                        tma_load_4d(sA, &mapA, &full_bar[stage], c0, ow0 + p.dw[tap], oh0 + p.dh[tap], img);
-                    } else {
-                        const int dw = p.dw[tap], dh = p.dh[tap];
-                        for (int i = 0; i < p.TH; ++i)
-                            tma_load_5d(sA + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
-                                        ow0 + (dw >> 1), 2 * (oh0 + i) + dh, img);
+                    for (int sub = 0; sub < p.mt; ++sub) {
+                        uint8_t* dst = sA + sub * kATileBytes;
+                        if (p.mode == 0) {
+                            tma_load_4d(dst, &mapA, &full_bar[stage], c0, ow0[sub] + p.dw[tap], oh0[sub] + p.dh[tap], img[sub]);
+                        } else {
+                            const int dw = p.dw[tap], dh = p.dh[tap];
+                            for (int i = 0; i < p.TH; ++i)
+                                tma_load_5d(dst + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
+                                            ow0[sub] + (dw >> 1), 2 * (oh0[sub] + i) + dh, img[sub]);
+                        }
                     }
-                    tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? img : 0);
+                    tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? img[0] : 0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -299,18 +420,20 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.BN);
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * acc_cols);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + size_t(stage) * p.stage_bytes);
-                    const uint64_t a_desc = umma_desc_sw128(a_addr);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + kATileBytes);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
+                    for (int sub = 0; sub < p.mt; ++sub) {
+                        const uint64_t a_desc = umma_desc_sw128(a_addr + sub * kATileBytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
-                        umma_bf16(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
+                            umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -323,36 +446,83 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     } else if (warp >= 4) {
         // ===================================================================== epilogue
         const int q = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
+        const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
         const int row = q * 32 + lane;
         const bool valid = row < p.rows_valid;
         const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
+        const int cpg = p.gn_cpg;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
-            int mt = tile / p.n_tiles;
-            const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
-            const int th_i = mt % p.tiles_h;
-            const int img = mt / p.tiles_h;
-            const int oh = th_i * p.TH + r_th, ow = tw_i * p.TW + r_tw;
-            const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
-            const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
-
+            const int mtile = tile / p.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
-            int c = 0;
-            for (; c + 32 <= p.BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(t_addr + uint32_t(c), v);
-                tmem_ld_wait();
-                epilogue_store<32>(p, v, valid, d_off, r_off, nt * p.BN + c);
-            }
-            if (c < p.BN) {  // BN % 32 == 16
-                uint32_t v[16];
-                tmem_ld16(t_addr + uint32_t(c), v);
-                tmem_ld_wait();
-                epilogue_store<16>(p, v, valid, d_off, r_off, nt * p.BN + c);
+            for (int sub = 0; sub < p.mt; ++sub) {
+                int st = mtile * p.mt + sub;
+                const int sub_in_img = st % sub_per_img;
+                const int tw_i = st % p.tiles_w; st /= p.tiles_w;
+                const int th_i = st % p.tiles_h;
+                const int img = st / p.tiles_h;
+                const int oh = th_i * p.TH + r_th, ow = tw_i * p.TW + r_tw;
+                const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
+                const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
+
+                if (p.gn_mode != 0) named_bar_sync(1, 128);  // previous readers of the scratch are done
+                if (p.gn_mode == 2) {
+                    // per-tile constants of the GroupNorm being differentiated: scale/shift/gamma per channel,
+                    // mean/rstd per group, for this image and this tile's channel range
+                    for (int c = et; c < p.BN; c += 128) {
+                        const int n = nt * p.BN + c;
+                        const float2 s2 = __ldg(&p.gn_ss[(size_t)img * (p.n_tiles * p.BN) + n]);
+                        gn_sc[c] = s2.x; gn_sh[c] = s2.y;
+                        gn_gm[c] = __ldg(&p.gn_gamma[n]);
+                    }
+                    for (int g = et; g < p.BN / cpg; g += 128)
+                        gn_mrs[g] = __ldg(&p.gn_mr[(size_t)img * 32 + (nt * p.BN) / cpg + g]);
+                    named_bar_sync(1, 128);
+                }
+
+                int c = 0;
+                for (; c + 32 <= p.BN; c += 32) {
+                    uint32_t v[32];
+                    float f[32];
+                    tmem_ld32(t_addr + uint32_t(c), v);
+                    tmem_ld_wait();
+                    epilogue_store<32>(p, v, f, valid, d_off, r_off, nt * p.BN + c);
+                    if (p.gn_mode != 0) {
+                        float gv[16];
+                        if (cpg == 4) gn_chunk_sums<4>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        else if (cpg == 8) gn_chunk_sums<8>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        else gn_chunk_sums<16>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        warp_reduce16(gv, lane);
+                        if ((lane & 1) == 0)
+                            gn_red[(q * 8 + (c >> 5)) * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
+                                   ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = gv[0];
+                    }
+                }
+                if (c < p.BN) {  // BN % 32 == 16
+                    uint32_t v[16];
+                    float f[16];
+                    tmem_ld16(t_addr + uint32_t(c), v);
+                    tmem_ld_wait();
+                    epilogue_store<16>(p, v, f, valid, d_off, r_off, nt * p.BN + c);
+                }
+                if (p.gn_mode != 0) {
+                    // cross-warp combine in fixed order, one (group, value) per thread
+                    named_bar_sync(1, 128);
+                    const int gpc = 32 / cpg;                 // groups per 32-column chunk
+                    const int ngroups = p.BN / cpg;           // groups in this tile
+                    if (et < ngroups * 2) {
+                        const int g = et >> 1, which = et & 1;
+                        const int chunk = g / gpc, gi = g - chunk * gpc;
+                        float tot = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) tot += gn_red[(w * 8 + chunk) * 16 + 2 * gi + which];
+                        p.gn_partial[(((size_t)img * sub_per_img + sub_in_img) * 32 + (nt * p.BN) / cpg + g) * 2 + which] = tot;
+                    }
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
@@ -438,12 +608,12 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.mode = op.stride == 2 ? 1 : 0;
     p.TW = t.TW; p.TH = t.TH; p.rows_valid = t.rows_valid;
     p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.nimg = op.A_B;
-    p.n_tiles = t.n_tiles; p.BN = t.BN;
+    p.n_tiles = t.n_tiles; p.BN = t.BN; p.mt = t.mt;
     p.kchunks = t.kchunks; p.ntaps = op.ntaps;
     for (int i = 0; i < op.ntaps; ++i) { p.dh[i] = op.dh[i]; p.dw[i] = op.dw[i]; }
     p.b_batched = op.B_sBatch != 0;
     p.stages = t.stages;
-    p.stage_bytes = kATileBytes + ((t.BN * 128 + 1023) / 1024) * 1024;
+    p.stage_bytes = t.stage_bytes;
     p.alpha = op.alpha;
     p.bias = op.bias;
     p.resid = reinterpret_cast<const __nv_bfloat16*>(op.resid);
@@ -452,6 +622,11 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.D_sB = op.D_sB; p.D_sH = op.D_sH; p.D_sW = op.D_sW; p.D_sN = op.D_sN;
     p.n_store = op.n_store > 0 ? op.n_store : op.N;
     p.beta = op.out_fp32 ? op.beta : 0.f;
+    p.gn_mode = op.gn_mode;
+    p.gn_cpg = op.gn_mode ? op.N / 32 : 4;
+    p.gn_partial = op.gn_partial;
+    p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
+    p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -460,7 +635,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set = true;
     }
-    const int total_tiles = op.A_B * t.tiles_h * t.tiles_w * t.n_tiles;
+    const int total_tiles = (op.A_B * t.tiles_h * t.tiles_w / t.mt) * t.n_tiles;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     const bool timed = g_timing && g_timed.size() < g_timing_cap;
     TimedLaunch tl;

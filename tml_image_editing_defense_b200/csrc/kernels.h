@@ -14,15 +14,17 @@ void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf
 
 // GroupNorm(32 groups) over bf16 [B, HW, C].
 //   partial: [B][chunks][32][2] fp32 scratch;  ss: [B][C] float2 (scale, shift);  mr: [B][32] float2 (mean, rstd)
-int gn_num_chunks(int HW);
+int gn_num_chunks(int HW, int C);
 void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s);
+// nchunks: number of partial entries per image (gn_num_chunks(HW, C) for launch_gn_stats, the tile count for
+// partials written by a GEMM epilogue)
 void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
-                        int HW, int C, float eps, cudaStream_t s);
+                        int HW, int C, float eps, int nchunks, cudaStream_t s);
 void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s);
 // backward of y = act(GN(x)):  dx = rstd*(dxh - mean(dxh) - xh*mean(dxh*xh)) (+ resid)
 void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
                            float* partial, int B, int HW, int C, int silu, cudaStream_t s);
-void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, cudaStream_t s);
+void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, int nchunks, cudaStream_t s);
 void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
                          const float* gamma, const bf16* resid, bf16* dx, int B, int HW, int C, int silu,
                          cudaStream_t s);

@@ -23,7 +23,7 @@ from tests.helpers import (BACKWARD_STAGE_NAMES, cosine, emulate_gemm, fetch_sav
 from tml_image_editing_defense_b200 import _lib, ops  # noqa
 
 
-def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid=False, alpha=1.0, seed=0):
+def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid=False, alpha=1.0, seed=0, gn=0):
     """conv3x3 in packing mode `mode` (0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity) or mode -1: 1x1."""
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
@@ -61,6 +61,19 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     d.R_sW = N; d.R_sH = OW * N; d.R_sB = OH * OW * N
     d.D = D.data_ptr(); d.out_fp32 = 0
     d.D_sW = N; d.D_sH = OW * N; d.D_sB = OH * OW * N; d.D_sN = 1; d.n_store = 0
+    keep = []
+    if gn:
+        ntile = lib.tml_debug_gn_tiles_per_image(OH, OW)
+        part = torch.full((B, ntile, 32, 2), float("nan"), dtype=torch.float32, device=dev)
+        d.gn_mode = gn; d.gn_partial = part.data_ptr()
+        if gn == 2:
+            xg = torch.randn(B, OH, OW, N, generator=g).to(torch.bfloat16)
+            ss = torch.stack([torch.rand(B, N, generator=g) + 0.5, torch.randn(B, N, generator=g) * 0.3], dim=-1)
+            mr = torch.stack([torch.randn(B, 32, generator=g) * 0.2, torch.rand(B, 32, generator=g) + 0.5], dim=-1)
+            gam = torch.randn(N, generator=g)
+            keep = [xg.to(dev), ss.contiguous().to(dev), mr.contiguous().to(dev), gam.to(dev)]
+            d.gn_x, d.gn_ss, d.gn_mr, d.gn_gamma = [t.data_ptr() for t in keep]
+            d.gn_silu = 1
     rc = lib.tml_debug_gemm(C.byref(d), torch.cuda.current_stream().cuda_stream)
     if rc:
         print(f"[gemm] {name}: launch error {lib.tml_last_error().decode()}")
@@ -70,6 +83,24 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     err = rel_err(out, ref)
     nan = int(torch.isnan(out).sum())
     ok = err < 1e-2 and nan == 0
+    if gn:
+        # reference reductions over the bf16 values the kernel stored
+        o64 = out.double().view(B, OH * OW, 32, N // 32)
+        got = part.double().sum(dim=1).cpu()       # [B, 32, 2]
+        if gn == 1:
+            want = torch.stack([o64.sum(dim=(1, 3)), (o64 * o64).sum(dim=(1, 3))], dim=-1)
+        else:
+            x64 = xg.double().view(B, OH * OW, 32, N // 32)
+            sc = ss[..., 0].double().view(B, 1, 32, N // 32)
+            sh = ss[..., 1].double().view(B, 1, 32, N // 32)
+            u = x64 * sc + sh
+            sg = torch.sigmoid(u)
+            dxh = o64 * (sg * (1 + u * (1 - sg))) * gam.double().view(1, 1, 32, N // 32)
+            xh = (x64 - mr[..., 0].double().view(B, 1, 32, 1)) * mr[..., 1].double().view(B, 1, 32, 1)
+            want = torch.stack([dxh.sum(dim=(1, 3)), (dxh * xh).sum(dim=(1, 3))], dim=-1)
+        gerr = float((got - want).abs().max() / (want.abs().max() + 1e-30))
+        print(f"        fused GN mode {gn}: max rel dev of group sums = {gerr:.3e} {'OK' if gerr < 2e-3 else 'FAIL'}")
+        ok = ok and gerr < 2e-3
     print(f"[gemm] {name:34s} B={B} {H}x{W} C={Cin} N={N} taps={len(dh)} s={stride}: rel_err={err:.3e} nan={nan} "
           f"{'OK' if ok else 'FAIL'}")
     if not ok:
@@ -104,6 +135,14 @@ def run_gemm_suite(lib, dev):
         ("s2 dgrad parity 10", dict(B=2, H=16, W=16, Cin=128, N=128, mode=5)),
         ("s2 dgrad parity 11", dict(B=2, H=16, W=16, Cin=128, N=128, mode=6)),
         ("multi-wave 128->128 64x64 B=8", dict(B=8, H=64, W=64, Cin=128, N=128, mode=0)),
+        ("mt=2 128->128 64x64 B=12 +stats", dict(B=12, H=64, W=64, Cin=128, N=128, mode=0, bias=True, gn=1)),
+        ("mt=2 s2 128 128->64 B=12", dict(B=12, H=128, W=128, Cin=128, N=128, mode=2, stride=2, bias=True)),
+        ("mt=2 dgrad 256->128 B=12 +gnbwd", dict(B=12, H=64, W=64, Cin=256, N=128, mode=1, gn=2)),
+        ("mt=2 parity 11 B=12", dict(B=12, H=64, W=64, Cin=128, N=128, mode=6)),
+        ("stats N=256 resid", dict(B=2, H=32, W=32, Cin=128, N=256, mode=0, resid=True, gn=1)),
+        ("stats N=512 2 n-tiles", dict(B=2, H=16, W=16, Cin=256, N=512, mode=0, bias=True, gn=1)),
+        ("gnbwd N=512 8x8", dict(B=2, H=8, W=8, Cin=512, N=512, mode=1, gn=2)),
+        ("gnbwd N=256", dict(B=3, H=32, W=32, Cin=256, N=256, mode=1, gn=2)),
     ]
     for name, kw in cases:
         try:
