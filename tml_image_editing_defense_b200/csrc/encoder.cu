@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -503,8 +504,13 @@ static int gn_backward(Run& r, const bf16* x, const bf16* dy, const Norm& n, con
     return 0;
 }
 // Ask a GEMM to also reduce (sum, sumsq) of its output per (image, tile, group).
+static bool env_off(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] == '1';
+}
 static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
-    if (gemm_get_impl() != 0) return Partials();  // the SIMT debug kernel has no fused reductions
+    static const bool off = env_off("TML_NO_FUSE_STATS");     // tuning switch
+    if (off || gemm_get_impl() != 0) return Partials();  // the SIMT debug kernel has no fused reductions
     o.gn_mode = 1;
     o.gn_partial = buf;
     Partials p;
@@ -515,7 +521,8 @@ static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
 // Ask a dgrad GEMM to also reduce the GroupNorm-backward sums of the norm whose output it differentiates.
 static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
                             int oh, int ow) {
-    if (gemm_get_impl() != 0) return Partials();
+    static const bool off = env_off("TML_NO_FUSE_GNBWD");     // tuning switch
+    if (off || gemm_get_impl() != 0) return Partials();
     o.gn_mode = 2;
     o.gn_partial = buf;
     o.gn_x = x;

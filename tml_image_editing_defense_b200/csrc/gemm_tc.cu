@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -89,7 +90,8 @@ constexpr int kUmmaM = 128;
 constexpr int kATileBytes = kUmmaM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBarrierBytes = 256;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 
 static int largest_divisor_le(int n, int cap, int multiple_of) {
     for (int d = (cap < n ? cap : n); d >= 1; --d)
@@ -123,6 +125,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     else if (op.N % 128 == 0) BN = 128;
     else if (op.N <= 256) BN = op.N;
     else { set_error("%s: N=%d unsupported (need N%%128==0 or N<=256)", op.name, op.N); return -1; }
+    if (op.resid && BN < 32) { set_error("%s: residual needs N >= 32", op.name); return -1; }
     if (op.gn_mode != 0) {
         const int cpg = op.N / 32;
         if (op.out_fp32 || op.D_sN != 1 || op.N % 32 || (cpg != 4 && cpg != 8 && cpg != 16) || BN % 32 ||
@@ -142,7 +145,8 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // Two 128-row sub-tiles per CTA tile when the accumulators fit (2 x 2 x BN <= 512 TMEM columns):
     // every B (weight) tile is then fetched from L2 once per 256 output pixels instead of once per 128.
     const long sub_tiles = (long)op.A_B * t->tiles_h * t->tiles_w;
-    t->mt = (BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
+    static const bool no_mt2 = getenv("TML_NO_MT2") && getenv("TML_NO_MT2")[0] == '1';   // tuning switch
+    t->mt = (!no_mt2 && BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
     int stage_bytes = t->mt * kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -197,10 +201,11 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
 // Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel): alpha, bias,
-// residual, store.  On return f[] holds the values as stored (bf16-rounded for bf16 outputs).
+// residual (already in registers: rres, loaded one chunk ahead), store.  On return f[] holds the
+// values as stored (bf16-rounded for bf16 outputs).
 template <int NC>
-__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, float (&f)[NC], bool valid,
-                                               long long d_off, long long r_off, int n0) {
+__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, float (&f)[NC],
+                                               const uint4 (&rres)[4], bool valid, long long d_off, int n0) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
     if (!valid) return;
@@ -209,10 +214,9 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
         for (int j = 0; j < NC; ++j) f[j] += __ldg(p.bias + n0 + j);
     }
     if (p.resid != nullptr) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + r_off + n0);
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
-            uint4 r = __ldg(rp + j);
+            const uint4 r = rres[j];
             f[8 * j + 0] += bf16_lo(r.x); f[8 * j + 1] += bf16_hi(r.x);
             f[8 * j + 2] += bf16_lo(r.y); f[8 * j + 3] += bf16_hi(r.y);
             f[8 * j + 4] += bf16_lo(r.z); f[8 * j + 5] += bf16_hi(r.z);
@@ -275,7 +279,7 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
 // CPG is a template parameter so gv[] stays in registers.
 template <int CPG>
 __device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f)[32], float (&gv)[16], bool valid,
-                                              long long d_off, int n0, int c, const float* gn_sc, const float* gn_sh,
+                                              const uint4 (&xreg)[4], int c, const float* gn_sc, const float* gn_sh,
                                               const float* gn_gm, const float2* gn_mrs) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) gv[i] = 0.f;
@@ -287,10 +291,9 @@ __device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f
             gv[2 * (j / CPG) + 1] = fmaf(f[j], f[j], gv[2 * (j / CPG) + 1]);
         }
     } else {
-        const uint4* xp = reinterpret_cast<const uint4*>(p.gn_x + d_off + n0);
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-            const uint4 xr = __ldg(xp + j8);
+            const uint4 xr = xreg[j8];
             const float xs[8] = {bf16_lo(xr.x), bf16_hi(xr.x), bf16_lo(xr.y), bf16_hi(xr.y),
                                  bf16_lo(xr.z), bf16_hi(xr.z), bf16_lo(xr.w), bf16_hi(xr.w)};
 #pragma unroll
@@ -348,7 +351,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], kEpiThreads);
         }
         fence_mbar_init();
     }
@@ -445,19 +448,26 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         }
     } else if (warp >= 4) {
         // ===================================================================== epilogue
-        const int q = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
-        const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
+        // 8 warps: warp e handles TMEM lane quadrant e % 4 (rows 32q .. 32q+31 of the sub-tile) and
+        // column half e / 4 of the tile, so every SM sub-partition runs two epilogue warps.
+        const int e = warp - 4;
+        const int q = e & 3;       // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
+        const int half = e >> 2;
+        const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
         const int row = q * 32 + lane;
         const bool valid = row < p.rows_valid;
         const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
         const int cpg = p.gn_cpg;
+        const int nch = p.BN >> 5;                      // 32-column chunks in the tile (0 when BN == 16)
+        const int ch_lo = half == 0 ? 0 : (nch + 1) / 2;  // this warp's chunk range
+        const int ch_hi = half == 0 ? (nch + 1) / 2 : nch;
+        const bool ld_res = p.resid != nullptr, ld_x = p.gn_mode == 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int mtile = tile / p.n_tiles;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
+            bool waited = false;
             for (int sub = 0; sub < p.mt; ++sub) {
                 int st = mtile * p.mt + sub;
                 const int sub_in_img = st % sub_per_img;
@@ -469,49 +479,83 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
 
-                if (p.gn_mode != 0) named_bar_sync(1, 128);  // previous readers of the scratch are done
+                // operands of the first chunk are requested before waiting for the accumulator
+                uint4 rres[4], xreg[4];
+                if (valid && ch_lo < ch_hi) {
+                    const int n0 = nt * p.BN + ch_lo * 32;
+                    if (ld_res) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(p.resid + r_off + n0) + j);
+                    }
+                    if (ld_x) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xreg[j] = __ldg(reinterpret_cast<const uint4*>(p.gn_x + d_off + n0) + j);
+                    }
+                }
+                if (p.gn_mode != 0) named_bar_sync(1, kEpiThreads);  // previous readers of the scratch are done
                 if (p.gn_mode == 2) {
                     // per-tile constants of the GroupNorm being differentiated: scale/shift/gamma per channel,
                     // mean/rstd per group, for this image and this tile's channel range
-                    for (int c = et; c < p.BN; c += 128) {
+                    for (int c = et; c < p.BN; c += kEpiThreads) {
                         const int n = nt * p.BN + c;
                         const float2 s2 = __ldg(&p.gn_ss[(size_t)img * (p.n_tiles * p.BN) + n]);
                         gn_sc[c] = s2.x; gn_sh[c] = s2.y;
                         gn_gm[c] = __ldg(&p.gn_gamma[n]);
                     }
-                    for (int g = et; g < p.BN / cpg; g += 128)
+                    for (int g = et; g < p.BN / cpg; g += kEpiThreads)
                         gn_mrs[g] = __ldg(&p.gn_mr[(size_t)img * 32 + (nt * p.BN) / cpg + g]);
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, kEpiThreads);
+                }
+                if (!waited) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    waited = true;
                 }
 
-                int c = 0;
-                for (; c + 32 <= p.BN; c += 32) {
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    const int c = ch * 32;
                     uint32_t v[32];
                     float f[32];
                     tmem_ld32(t_addr + uint32_t(c), v);
+                    // operands of the next chunk go in flight while this one is processed
+                    uint4 rnext[4], xnext[4];
+                    if (valid && ch + 1 < ch_hi) {
+                        const int n1 = nt * p.BN + c + 32;
+                        if (ld_res) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.resid + r_off + n1) + j);
+                        }
+                        if (ld_x) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) xnext[j] = __ldg(reinterpret_cast<const uint4*>(p.gn_x + d_off + n1) + j);
+                        }
+                    }
                     tmem_ld_wait();
-                    epilogue_store<32>(p, v, f, valid, d_off, r_off, nt * p.BN + c);
+                    epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
                     if (p.gn_mode != 0) {
                         float gv[16];
-                        if (cpg == 4) gn_chunk_sums<4>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
-                        else if (cpg == 8) gn_chunk_sums<8>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
-                        else gn_chunk_sums<16>(p, f, gv, valid, d_off, nt * p.BN + c, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        if (cpg == 4) gn_chunk_sums<4>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        else if (cpg == 8) gn_chunk_sums<8>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
+                        else gn_chunk_sums<16>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
                         warp_reduce16(gv, lane);
                         if ((lane & 1) == 0)
-                            gn_red[(q * 8 + (c >> 5)) * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
+                            gn_red[(q * 8 + ch) * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
                                    ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = gv[0];
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { rres[j] = rnext[j]; xreg[j] = xnext[j]; }
                 }
-                if (c < p.BN) {  // BN % 32 == 16
+                if (nch == 0 && half == 0) {  // BN == 16 (padded thin outputs)
                     uint32_t v[16];
                     float f[16];
-                    tmem_ld16(t_addr + uint32_t(c), v);
+                    tmem_ld16(t_addr, v);
                     tmem_ld_wait();
-                    epilogue_store<16>(p, v, f, valid, d_off, r_off, nt * p.BN + c);
+                    epilogue_store<16>(p, v, f, rres, valid, d_off, nt * p.BN);
                 }
                 if (p.gn_mode != 0) {
-                    // cross-warp combine in fixed order, one (group, value) per thread
-                    named_bar_sync(1, 128);
+                    // cross-warp combine in fixed order, one (group, value) per thread: the chunk of a group
+                    // was handled by the four row-quadrant warps of one column half
+                    named_bar_sync(1, kEpiThreads);
                     const int gpc = 32 / cpg;                 // groups per 32-column chunk
                     const int ngroups = p.BN / cpg;           // groups in this tile
                     if (et < ngroups * 2) {
