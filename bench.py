@@ -91,7 +91,7 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(res: int, B: int, world: int, mb: int, streams: int = 2):
+def workload_config(res: int, B: int, world: int, mb: int, streams: int = 1):
     name = "SDXL VAE-encoder PGD attack (BASELINE configs[2])" if res == 1024 else \
         "SD-1.5 VAE-encoder PGD attack (BASELINE configs[1])"
     return {"workload": f"{name}: batch {B} x {res}^2 per GPU, "
@@ -219,6 +219,18 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     gt = (C.c_double * 4)()
     lib.tml_gemm_timing_collect(gt)
+    if args.gemm_table and rank == 0:
+        buf = C.create_string_buffer(1 << 16)
+        n = lib.tml_gemm_timing_report(buf, len(buf))
+        rows = []
+        for ln in buf.raw[:n].decode().strip().split("\n"):
+            f = ln.split("|")
+            rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), float(f[6]), float(f[7])))
+        rows.sort(key=lambda r: -r[6])
+        print(f"{'gemm':24s} {'M':>9s} {'N':>5s} {'K':>5s} {'mode':>4s} {'n':>4s} {'ms/step':>8s} {'TFLOP/s':>8s}", file=sys.stderr)
+        for r in rows:
+            print(f"{r[0]:24s} {r[1]:9d} {r[2]:5d} {r[3]:5d} {r[4]:4d} {r[5]:4d} {r[6] / args.steps:8.3f} "
+                  f"{r[7] / (r[6] * 1e-3) / 1e12:8.1f}", file=sys.stderr)
     lib.tml_gemm_timing_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     c1 = _lib.launch_counts()
@@ -368,8 +380,9 @@ def main():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (configs[1]: 64)")
     ap.add_argument("--micro_batch", type=int, default=16, help="images per encoder pass")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the micro-batches alternate on")
+    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the micro-batches alternate on")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--gemm_table", action="store_true", help="print per-shape GEMM times (stderr)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -95,6 +95,8 @@ void tml_launch_counts(int64_t out[2]);
  * total algorithmic flops (2*M*N*K, conv padding not discounted), launches timed, launches dropped}. */
 void tml_gemm_timing_enable(int max_launches);
 void tml_gemm_timing_collect(double out[4]);
+/* per-shape table of the timed launches, one "name|M|N|K|mode|count|ms|flops" line each; returns bytes written */
+size_t tml_gemm_timing_report(char* buf, size_t cap);
 /* 0 = tcgen05 kernel (default, the product path), 1 = SIMT debug kernel (tests only) */
 void tml_debug_set_gemm_impl(int impl);
 /* Generic implicit-GEMM entry used by the kernel unit tests (same operation the encoder issues). */

@@ -1090,6 +1090,8 @@ void tml_gemm_timing_collect(double out[4]) {
     out[2] = (double)n; out[3] = (double)d;
 }
 
+size_t tml_gemm_timing_report(char* buf, size_t cap) { return gemm_timing_report(buf, cap); }
+
 void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots) {
     g_dump_base = reinterpret_cast<char*>(dev_buffer);
     g_dump_slot = slot_bytes;

@@ -74,6 +74,7 @@ long gemm_launch_count();  // number of tcgen05 GEMM launches since process star
 
 void gemm_timing_enable(int max_launches);  // 0 disables and recycles the events
 void gemm_timing_collect(double* total_ms, double* total_flops, long* launches, long* dropped);
+size_t gemm_timing_report(char* buf, size_t cap);
 
 void set_error(const char* fmt, ...);
 const char* last_error();

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <string>
 #include <vector>
 
 #include "gemm.h"
@@ -50,7 +51,7 @@ long gemm_launch_count() { return g_tc_launches.load(); }
 // ------------------------------------------------------------------------------------------------
 // optional per-launch CUDA-event timing of the tcgen05 kernel (bench.py's roofline numbers)
 // ------------------------------------------------------------------------------------------------
-struct TimedLaunch { cudaEvent_t a, b; double flops; };
+struct TimedLaunch { cudaEvent_t a, b; double flops; char key[96]; };
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
 static bool g_timing = false;
@@ -80,6 +81,27 @@ void gemm_timing_collect(double* total_ms, double* total_flops, long* launches, 
         fl += t.flops;
     }
     *total_ms = ms; *total_flops = fl; *launches = (long)g_timed.size(); *dropped = g_timing_dropped;
+}
+
+// Per-shape table of the recorded launches: "name|M|N|K|gn|count|ms|flops" lines (caller has synchronised).
+size_t gemm_timing_report(char* buf, size_t cap) {
+    struct Agg { std::string key; int n = 0; double ms = 0, fl = 0; };
+    std::vector<Agg> aggs;
+    for (auto& t : g_timed) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, t.a, t.b) != cudaSuccess) continue;
+        Agg* a = nullptr;
+        for (auto& x : aggs) if (x.key == t.key) { a = &x; break; }
+        if (!a) { aggs.push_back(Agg()); a = &aggs.back(); a->key = t.key; }
+        a->n++; a->ms += e; a->fl += t.flops;
+    }
+    size_t off = 0;
+    for (auto& a : aggs) {
+        int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s|%d|%.4f|%.6g\n", a.key.c_str(), a.n, a.ms, a.fl);
+        if (w < 0 || off + (size_t)w >= cap) break;
+        off += (size_t)w;
+    }
+    return off;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,6 +708,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     if (timed) {
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)(op.n_store > 0 ? op.n_store : op.N) * (double)op.ntaps * op.A_C;
+        snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
+                 op.ntaps * op.A_C, op.gn_mode * 10 + t.mt);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;

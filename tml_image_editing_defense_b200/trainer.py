@@ -24,7 +24,7 @@ from .vae import AutoencoderKL
 
 class Trainer:
     def __init__(self, cfg: TrainConfig, vae: AutoencoderKL, use_sdxl: bool = False, use_lcm: bool = False,
-                 micro_batch: int = 16, num_streams: int = 2):
+                 micro_batch: int = 16, num_streams: int = 1):
         self.cfg = cfg
         self.vae = vae
         self.use_sdxl = use_sdxl
