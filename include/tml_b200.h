@@ -108,6 +108,7 @@ typedef struct TmlGemmDesc {
     void* D; int out_fp32; int64_t D_sB, D_sH, D_sW, D_sN; int n_store; float beta;
     /* fused GroupNorm reductions of the output (see csrc/gemm.h): mode 1 = (sum, sumsq), 2 = backward sums */
     int gn_mode; float* gn_partial; const void* gn_x; const void* gn_ss; const void* gn_mr; const float* gn_gamma; int gn_silu;
+    int dbg_shift, dbg_bo; /* hardware experiment: row-shifted UMMA descriptor (tests only) */
 } TmlGemmDesc;
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 /* entries per image of the partial buffer a gn_mode GEMM writes: [B][tiles][32][2] floats */

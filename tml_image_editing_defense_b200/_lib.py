@@ -37,6 +37,7 @@ class TmlGemmDesc(C.Structure):
         ("D_sB", C.c_int64), ("D_sH", C.c_int64), ("D_sW", C.c_int64), ("D_sN", C.c_int64), ("n_store", C.c_int), ("beta", C.c_float),
         ("gn_mode", C.c_int), ("gn_partial", C.c_void_p), ("gn_x", C.c_void_p), ("gn_ss", C.c_void_p),
         ("gn_mr", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_silu", C.c_int),
+        ("dbg_shift", C.c_int), ("dbg_bo", C.c_int),
     ]
 
 

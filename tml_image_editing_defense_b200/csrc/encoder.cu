@@ -1078,6 +1078,7 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
     o.gn_mode = d->gn_mode; o.gn_partial = d->gn_partial; o.gn_x = d->gn_x;
     o.gn_ss = reinterpret_cast<const float2*>(d->gn_ss); o.gn_mr = reinterpret_cast<const float2*>(d->gn_mr);
     o.gn_gamma = d->gn_gamma; o.gn_silu = d->gn_silu;
+    o.dbg_shift = d->dbg_shift; o.dbg_bo = d->dbg_bo;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return gemm_launch(o, sms, reinterpret_cast<cudaStream_t>(stream));

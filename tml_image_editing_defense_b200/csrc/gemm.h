@@ -47,12 +47,15 @@ struct GemmOp {
     const float2* gn_mr = nullptr;     // [A_B][32]
     const float* gn_gamma = nullptr;   // [N]
     int gn_silu = 0;
+    // hardware experiment (tests only): A tile loaded `dbg_shift` pixels early into a (TW+8)-row box and
+    // consumed through a row-shifted UMMA descriptor; dbg_bo = 1 also sets the descriptor base_offset field
+    int dbg_shift = 0, dbg_bo = 0;
     const char* name = "";
 };
 
 // Derived tiling, shared by both kernels (the debug kernel ignores the tile fields).
 struct GemmTiling {
-    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes;
+    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes, halo, halo_bytes;
     size_t smem_bytes;
 };
 

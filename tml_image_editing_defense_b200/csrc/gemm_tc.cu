@@ -156,6 +156,20 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
             return -1;
         }
     }
+    // Halo mode: stride-1 3x3 convolutions whose output rows split into 128-pixel segments.
+    static const bool no_halo = getenv("TML_NO_HALO") && getenv("TML_NO_HALO")[0] == '1';   // tuning switch
+    bool halo = !no_halo && op.stride == 1 && op.ntaps == 9 && op.OW % 128 == 0 && op.B_sBatch == 0 &&
+                op.dbg_shift == 0 && op.OW == op.A_W && op.OH == op.A_H;
+    if (halo) {
+        unsigned seen = 0;
+        for (int i = 0; i < 9; ++i) {
+            if (op.dh[i] < -1 || op.dh[i] > 1 || op.dw[i] < -1 || op.dw[i] > 1) { halo = false; break; }
+            seen |= 1u << ((op.dh[i] + 1) * 3 + op.dw[i] + 1);
+        }
+        if (seen != 0x1FFu) halo = false;
+    }
+    if (halo) { TW = 128; TH = 1; }
+    t->halo = halo ? 1 : 0;
     t->TW = TW;
     t->TH = TH;
     t->rows_valid = TW * TH;
@@ -164,6 +178,18 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     t->BN = BN;
     t->n_tiles = op.N / BN;
     t->kchunks = op.A_C / kBlockK;
+    if (halo) {
+        t->mt = (BN <= 128 && op.OH % 2 == 0) ? 2 : 1;
+        t->halo_bytes = (((t->mt + 2) * 130 * 128) + 1023) / 1024 * 1024;
+        t->stage_bytes = BN * 128;                        // the ring holds weight tiles only
+        int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - 2 * t->halo_bytes) / t->stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) { set_error("%s: halo tiles do not fit", op.name); return -1; }
+        t->stages = stages;
+        t->smem_bytes = size_t(2) * t->halo_bytes + size_t(stages) * t->stage_bytes + kBarrierBytes + kGnSmemBytes + 1024;
+        return 0;
+    }
+    t->halo_bytes = 0;
     // Two 128-row sub-tiles per CTA tile when the accumulators fit (2 x 2 x BN <= 512 TMEM columns):
     // every B (weight) tile is then fetched from L2 once per 256 output pixels instead of once per 128.
     const long sub_tiles = (long)op.A_B * t->tiles_h * t->tiles_w;
@@ -212,7 +238,36 @@ struct TcParams {
     const float2* gn_mr;             // mode 2: [nimg][32] (mean, rstd)
     const float* gn_gamma;           // mode 2: [N]
     int gn_silu;
+    int dbg_shift, dbg_bo;
+    // halo mode (3x3 stride-1 convolutions, output rows of 128 pixels): one (mt+2) x 130-pixel halo tile per
+    // 64-channel chunk serves all nine taps through row-shifted UMMA descriptors
+    int halo, halo_bytes;
 };
+
+constexpr int kHaloW = 130;  // 128 output pixels + one halo pixel on each side
+
+struct SubTile { int img, oh0, ow0, sub_in_img; };
+__device__ __forceinline__ SubTile decode_sub(const TcParams& p, int mtile, int sub) {
+    SubTile s;
+    if (p.halo) {
+        const int tw_i = mtile % p.tiles_w;
+        const int r = mtile / p.tiles_w;
+        const int hp_n = p.tiles_h / p.mt;
+        s.img = r / hp_n;
+        s.oh0 = (r - s.img * hp_n) * p.mt + sub;   // TH == 1: one output row per sub-tile
+        s.ow0 = tw_i * p.TW;
+        s.sub_in_img = s.oh0 * p.tiles_w + tw_i;
+    } else {
+        int st = mtile * p.mt + sub;
+        s.sub_in_img = st % (p.tiles_h * p.tiles_w);
+        const int tw_i = st % p.tiles_w; st /= p.tiles_w;
+        const int th_i = st % p.tiles_h;
+        s.img = st / p.tiles_h;
+        s.ow0 = tw_i * p.TW;
+        s.oh0 = th_i * p.TH;
+    }
+    return s;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -346,12 +401,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                          const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* bar_base = smem + size_t(p.stages) * p.stage_bytes;
+    uint8_t* ring = smem + 2 * size_t(p.halo_bytes);                   // halo mode: two halo tiles come first
+    uint8_t* bar_base = ring + size_t(p.stages) * p.stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);        // [stages]
     uint64_t* empty_bar = full_bar + 8;                                // [stages]
     uint64_t* tfull_bar = empty_bar + 8;                               // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* hfull_bar = tempty_bar + 2;                              // [2]
+    uint64_t* hempty_bar = hfull_bar + 2;                              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + 2);
     // GN scratch (epilogue warps only): red[4 warps][8 chunks][16] floats, then per-tile constants
     float* gn_red = reinterpret_cast<float*>(bar_base + kBarrierBytes);          // 2048 B
     float* gn_sc = gn_red + 4 * 8 * 16;                                          // [256]
@@ -374,6 +432,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], kEpiThreads);
+            mbar_init(&hfull_bar[a], 1);
+            mbar_init(&hempty_bar[a], 1);
         }
         fence_mbar_init();
     }
@@ -387,11 +447,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     const int sub_per_img = p.tiles_h * p.tiles_w;
-    const int m_tiles = (p.nimg * sub_per_img) / p.mt;
+    const int m_tiles = (p.nimg * sub_per_img) / p.mt;   // (halo: sub-tiles of a CTA tile are consecutive rows)
     const int total_tiles = m_tiles * p.n_tiles;
     const int kblocks = p.ntaps * p.kchunks;
     const int a_bytes = p.mt * kATileBytes;
-    const uint32_t tx_bytes = uint32_t(p.mt) * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u;
+    const uint32_t tx_bytes = uint32_t(p.mt) * uint32_t(p.rows_valid + (p.dbg_shift ? 8 : 0)) * 128u + uint32_t(p.BN) * 128u;
     const int acc_cols = p.mt * p.BN;
 
     if (warp == 0) {
@@ -402,35 +462,60 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int mtile = tile / p.n_tiles;
-                int img[2], ow0[2], oh0[2];
-                for (int sub = 0; sub < p.mt; ++sub) {
-                    int st = mtile * p.mt + sub;
-                    const int tw_i = st % p.tiles_w; st /= p.tiles_w;
-                    const int th_i = st % p.tiles_h;
-                    img[sub] = st / p.tiles_h;
-                    ow0[sub] = tw_i * p.TW;
-                    oh0[sub] = th_i * p.TH;
+                if (p.halo) {
+                    // B (weight) tiles only, in (chunk, tap) order; the halo tiles come from warp 3
+                    for (int ch = 0; ch < p.kchunks; ++ch)
+                        for (int tap = 0; tap < p.ntaps; ++tap) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
+                            tma_load_3d(ring + size_t(stage) * p.stage_bytes, &mapB, &full_bar[stage],
+                                        (tap * p.kchunks + ch) * kBlockK, nt * p.BN, 0);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+                    continue;
                 }
+                SubTile sb[2];
+                for (int sub = 0; sub < p.mt; ++sub) sb[sub] = decode_sub(p, mtile, sub);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     const int tap = kb / p.kchunks;
                     const int c0 = (kb - tap * p.kchunks) * kBlockK;
-                    uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
+                    uint8_t* sA = ring + size_t(stage) * p.stage_bytes;
                     uint8_t* sB = sA + a_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
                         uint8_t* dst = sA + sub * kATileBytes;
                         if (p.mode == 0) {
-                            tma_load_4d(dst, &mapA, &full_bar[stage], c0, ow0[sub] + p.dw[tap], oh0[sub] + p.dh[tap], img[sub]);
+                            tma_load_4d(dst, &mapA, &full_bar[stage], c0, sb[sub].ow0 + p.dw[tap] - p.dbg_shift,
+                                        sb[sub].oh0 + p.dh[tap], sb[sub].img);
                         } else {
                             const int dw = p.dw[tap], dh = p.dh[tap];
                             for (int i = 0; i < p.TH; ++i)
                                 tma_load_5d(dst + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
-                                            ow0[sub] + (dw >> 1), 2 * (oh0[sub] + i) + dh, img[sub]);
+                                            sb[sub].ow0 + (dw >> 1), 2 * (sb[sub].oh0 + i) + dh, sb[sub].img);
                         }
                     }
-                    tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? img[0] : 0);
+                    tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? sb[0].img : 0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================================== halo producer (halo mode)
+        if (lane == 0 && p.halo) {
+            int hs = 0;
+            uint32_t hphase = 0;
+            const uint32_t halo_tx = uint32_t(p.mt + 2) * kHaloW * 128u;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const SubTile s0 = decode_sub(p, tile / p.n_tiles, 0);
+                for (int ch = 0; ch < p.kchunks; ++ch) {
+                    mbar_wait(&hempty_bar[hs], hphase ^ 1u);
+                    mbar_arrive_expect_tx(&hfull_bar[hs], halo_tx);
+                    // rows oh0-1 .. oh0+mt, pixels ow0-1 .. ow0+128: out-of-range pixels arrive as zeros (= padding)
+                    tma_load_4d(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
+                                s0.oh0 - 1, s0.img);
+                    hs ^= 1;
+                    if (hs == 0) hphase ^= 1u;
                 }
             }
         }
@@ -440,19 +525,50 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             const uint32_t idesc = umma_idesc_bf16(kUmmaM, p.BN);
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            int acc = 0, hs = 0;
+            uint32_t acc_phase = 0, hphase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(acc * acc_cols);
+                if (p.halo) {
+                    for (int ch = 0; ch < p.kchunks; ++ch) {
+                        mbar_wait(&hfull_bar[hs], hphase);
+                        tc_fence_after();
+                        const uint32_t h_addr = smem_u32(smem + size_t(hs) * p.halo_bytes);
+                        for (int tap = 0; tap < p.ntaps; ++tap) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            const uint64_t b_desc = umma_desc_sw128(smem_u32(ring + size_t(stage) * p.stage_bytes));
+                            for (int sub = 0; sub < p.mt; ++sub) {
+                                // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
+                                const uint32_t row0 = uint32_t((sub + p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
+                                const uint64_t a_desc = umma_desc_sw128(h_addr + row0 * 128u);
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
+                                              idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&empty_bar[stage]);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+                        umma_commit(&hempty_bar[hs]);  // halo tile free once its nine taps have retired
+                        hs ^= 1;
+                        if (hs == 0) hphase ^= 1u;
+                    }
+                    umma_commit(&tfull_bar[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + size_t(stage) * p.stage_bytes);
+                    const uint32_t a_addr = smem_u32(ring + size_t(stage) * p.stage_bytes);
                     const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
-                        const uint64_t a_desc = umma_desc_sw128(a_addr + sub * kATileBytes);
+                        uint64_t a_desc = umma_desc_sw128(a_addr + sub * kATileBytes + uint32_t(p.dbg_shift) * 128u);
+                        if (p.dbg_bo) a_desc |= uint64_t(((a_addr + sub * kATileBytes + uint32_t(p.dbg_shift) * 128u) >> 7) & 7u) << 49;
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
@@ -491,12 +607,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             const int mtile = tile / p.n_tiles;
             bool waited = false;
             for (int sub = 0; sub < p.mt; ++sub) {
-                int st = mtile * p.mt + sub;
-                const int sub_in_img = st % sub_per_img;
-                const int tw_i = st % p.tiles_w; st /= p.tiles_w;
-                const int th_i = st % p.tiles_h;
-                const int img = st / p.tiles_h;
-                const int oh = th_i * p.TH + r_th, ow = tw_i * p.TW + r_tw;
+                const SubTile stl = decode_sub(p, mtile, sub);
+                const int sub_in_img = stl.sub_in_img, img = stl.img;
+                const int oh = stl.oh0 + r_th, ow = stl.ow0 + r_tw;
                 const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
                 const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
@@ -650,7 +763,9 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     if (op.stride == 1) {
         cuuint64_t dims[4] = {(cuuint64_t)op.A_C, (cuuint64_t)op.A_W, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
         cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)t.TW, (cuuint32_t)t.TH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(t.TW + (op.dbg_shift ? 8 : 0)), (cuuint32_t)t.TH, 1};
+        if (t.halo) { box[1] = 130; box[2] = (cuuint32_t)(t.mt + 2); }
+        if (op.dbg_shift && (t.TH != 1 || t.TW > 64 || t.mt != 1)) { set_error("dbg_shift needs TH=1, TW<=64, mt=1"); return -1; }
         if ((rc = encode_map(&mapA, op.A, 4, dims, str, box, op.name))) return rc;
     } else {
         cuuint64_t dims[5] = {(cuuint64_t)op.A_C, 2, (cuuint64_t)op.A_W / 2, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
@@ -693,6 +808,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.gn_partial = op.gn_partial;
     p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
+    p.dbg_shift = op.dbg_shift; p.dbg_bo = op.dbg_bo;
+    p.halo = t.halo; p.halo_bytes = t.halo_bytes;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -709,7 +826,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)(op.n_store > 0 ? op.n_store : op.N) * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
-                 op.ntaps * op.A_C, op.gn_mode * 10 + t.mt);
+                 op.ntaps * op.A_C, t.halo * 100 + op.gn_mode * 10 + t.mt);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;

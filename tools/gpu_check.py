@@ -143,6 +143,12 @@ def run_gemm_suite(lib, dev):
         ("stats N=512 2 n-tiles", dict(B=2, H=16, W=16, Cin=256, N=512, mode=0, bias=True, gn=1)),
         ("gnbwd N=512 8x8", dict(B=2, H=8, W=8, Cin=512, N=512, mode=1, gn=2)),
         ("gnbwd N=256", dict(B=3, H=32, W=32, Cin=256, N=256, mode=1, gn=2)),
+        ("halo mt2 128->128 8x128 +stats", dict(B=2, H=8, W=128, Cin=128, N=128, mode=0, bias=True, gn=1)),
+        ("halo mt2 dgrad 256->128 4x256 +gnbwd", dict(B=2, H=4, W=256, Cin=256, N=128, mode=1, gn=2)),
+        ("halo mt1 512->512 3x128 resid", dict(B=1, H=3, W=128, Cin=512, N=512, mode=0, resid=True)),
+        ("halo mt1 256->256 5x128 +stats", dict(B=2, H=5, W=128, Cin=256, N=256, mode=0, bias=True, gn=1)),
+        ("halo N=16 dgrad 4x128", dict(B=1, H=4, W=128, Cin=128, N=16, mode=1)),
+        ("halo multi-wave 128->128 128x128 B=4", dict(B=4, H=128, W=128, Cin=128, N=128, mode=0, resid=True)),
     ]
     for name, kw in cases:
         try:
