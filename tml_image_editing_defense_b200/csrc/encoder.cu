@@ -522,7 +522,8 @@ static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
 static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
                             int oh, int ow) {
     static const bool off = env_off("TML_NO_FUSE_GNBWD");     // tuning switch
-    if (off || gemm_get_impl() != 0) return Partials();
+    static const int min_k = getenv("TML_GNBWD_MIN_K") ? atoi(getenv("TML_GNBWD_MIN_K")) : 0;
+    if (off || gemm_get_impl() != 0 || o.ntaps * o.A_C < min_k) return Partials();
     o.gn_mode = 2;
     o.gn_partial = buf;
     o.gn_x = x;

@@ -353,6 +353,8 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
 // Per-thread partial sums over one 32-column chunk of one output row, per GroupNorm group:
 //   mode 1: gv[2g] = sum f, gv[2g+1] = sum f^2            (statistics of the tensor just produced)
 //   mode 2: gv[2g] = sum dxh, gv[2g+1] = sum dxh*xh        (GroupNorm backward reductions; f = dy)
+// In mode 2 the inner loop accumulates sum(dxh) and sum(dxh*x); xh = (x - mean)*rstd is applied once
+// per group afterwards: sum(dxh*xh) = rstd*(sum(dxh*x) - mean*sum(dxh)).
 // CPG is a template parameter so gv[] stays in registers.
 template <int CPG>
 __device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f)[32], float (&gv)[16], bool valid,
@@ -368,6 +370,7 @@ __device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f
             gv[2 * (j / CPG) + 1] = fmaf(f[j], f[j], gv[2 * (j / CPG) + 1]);
         }
     } else {
+        const bool silu = p.gn_silu != 0;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
             const uint4 xr = xreg[j8];
@@ -376,18 +379,20 @@ __device__ __forceinline__ void gn_chunk_sums(const TcParams& p, const float (&f
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const int j = j8 * 8 + jj;
-                const float u = fmaf(xs[jj], gn_sc[c + j], gn_sh[c + j]);
-                float da = 1.f;
-                if (p.gn_silu) {
+                float dxh = f[j] * gn_gm[c + j];
+                if (silu) {
+                    const float u = fmaf(xs[jj], gn_sc[c + j], gn_sh[c + j]);
                     const float sg = __fdividef(1.f, 1.f + __expf(-u));
-                    da = sg * fmaf(u, 1.f - sg, 1.f);
+                    dxh *= sg * fmaf(u, 1.f - sg, 1.f);
                 }
-                const float dxh = f[j] * da * gn_gm[c + j];
-                const float2 m = gn_mrs[(c + j) / CPG];
-                const float xh = (xs[jj] - m.x) * m.y;
                 gv[2 * (j / CPG)] += dxh;
-                gv[2 * (j / CPG) + 1] = fmaf(dxh, xh, gv[2 * (j / CPG) + 1]);
+                gv[2 * (j / CPG) + 1] = fmaf(dxh, xs[jj], gv[2 * (j / CPG) + 1]);
             }
+        }
+#pragma unroll
+        for (int g = 0; g < 32 / CPG; ++g) {
+            const float2 m = gn_mrs[c / CPG + g];
+            gv[2 * g + 1] = m.y * fmaf(-m.x, gv[2 * g], gv[2 * g + 1]);
         }
     }
 }
