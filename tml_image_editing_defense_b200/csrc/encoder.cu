@@ -522,7 +522,9 @@ static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
 static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
                             int oh, int ow) {
     static const bool off = env_off("TML_NO_FUSE_GNBWD");     // tuning switch
-    static const int min_k = getenv("TML_GNBWD_MIN_K") ? atoi(getenv("TML_GNBWD_MIN_K")) : 0;
+    // Measured on B200: for K = 9*128 the main loop of a tile is too short to hide this epilogue (exp + rcp per
+    // element and an extra read of x), so 128-channel layers keep the standalone reduction kernel.
+    static const int min_k = getenv("TML_GNBWD_MIN_K") ? atoi(getenv("TML_GNBWD_MIN_K")) : 2000;
     if (off || gemm_get_impl() != 0 || o.ntaps * o.A_C < min_k) return Partials();
     o.gn_mode = 2;
     o.gn_partial = buf;
