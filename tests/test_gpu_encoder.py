@@ -175,3 +175,30 @@ def test_universal_step_single_rank(dev, models):
     # the same shard processed with another micro-batching gives the same summed gradient
     d2 = ut.step(torch.zeros_like(delta), imgs, tg, None, n_global=3, micro_batch=3)
     torch.testing.assert_close(d1, d2, rtol=0, atol=1e-6)
+
+
+def test_grad_cosine_512_vs_oracle_on_gpu(dev, models):
+    """The benchmark resolution (BASELINE configs[1]): one 512^2 image, gradient vs the fp32 oracle."""
+    from oracle.encoder_oracle import encoder_attack_grad
+    oracle, vae = models
+    g = torch.Generator().manual_seed(13)
+    x = (torch.rand((1, 3, 512, 512), generator=g) * 2 - 1).to(dev)
+    t = torch.randn((1, 4, 64, 64), generator=g).to(dev)
+    n = torch.randn((1, 4, 64, 64), generator=g).to(dev)
+    od = oracle.to(dev)
+    g_ref, l_ref, _ = encoder_attack_grad(od, x, t, n, 0)
+    oracle.to("cpu")
+    torch.cuda.empty_cache()
+    gg, l, _ = vae.attack_grad(x, t, n, 0)
+    assert cosine(gg, g_ref) >= 0.999
+    torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
+
+
+def test_cli_main_runs_small(dev, tmp_path):
+    from tml_image_editing_defense_b200.main import main
+    rc = main(["--num_images", "3", "--resolution", "64", "--max_train_steps", "4", "--train_batch_size", "2",
+               "--output_dir", str(tmp_path)])
+    assert rc == 0
+    out = torch.load(tmp_path / "adversarial_rank0.pt")
+    assert out["x_adv"].shape == (3, 3, 64, 64) and out["indices"] == [0, 1, 2]
+    assert float(out["x_adv"].abs().max()) <= 1.0

@@ -1,0 +1,107 @@
+"""Command-line driver of the PGD immunization hot path (the `__main__` of the reference's main.py:592-651
+and the image loop of run_all.py:23-93, for the VAE-encoder attack).
+
+    python -m tml_image_editing_defense_b200.main --num_images 64 --max_train_steps 200
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m tml_image_editing_defense_b200.main --num_images 512
+    torchrun ... -m tml_image_editing_defense_b200.main --universal        # shared perturbation (old/train_noise.py)
+
+One process per GPU; rank r immunizes images r::world (no communication; run_all.py:14-21 split the list by
+hand over two GPUs).  Results: `<output_dir>/adversarial_rank{r}.pt` (+ PNGs when torchvision is present, as
+main.py:618) and one JSON line of metrics per rank (the reference logged to wandb).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+from .configs import TrainConfig, UniversalConfig
+from .dataset import ImagePromptDataset, SyntheticImageDataset, shard_indices
+from .parser import parse_args
+from .trainer import Trainer
+from .universal import UniversalTrainer
+from .vae import SD15_VAE, SDXL_VAE, AutoencoderKL
+from .weights import load_checkpoint, random_init_state_dict
+
+
+def main(argv=None) -> int:
+    args = parse_args(argv)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if args.local_rank < 0 else args.local_rank
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    out_dir = Path(args.output_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+
+    cfg_vae = SDXL_VAE if args.sdxl else SD15_VAE
+    sd = load_checkpoint(args.pretrained_vae_model_name_or_path) if args.pretrained_vae_model_name_or_path \
+        else random_init_state_dict(cfg_vae, seed=args.seed)
+    vae = AutoencoderKL(cfg_vae, device=dev).load_state_dict(sd)
+
+    if args.train_data_dir:
+        ds = ImagePromptDataset(args.train_data_dir, "", resolution=args.resolution)
+        n = len(ds)
+        fetch = lambda idx: torch.stack([ds[i][0] for i in idx])  # noqa: E731
+    else:
+        sds = SyntheticImageDataset(args.num_images, resolution=args.resolution, seed=args.seed)
+        n = len(sds)
+        fetch = sds.batch
+    idx = shard_indices(n, rank, world)
+    images = fetch(idx).to(dev) if idx else torch.empty((0, 3, args.resolution, args.resolution), device=dev)
+    # target latent: encoding of a fixed other image (main.py:75); synthetic: a seeded N(0,1) latent
+    g = torch.Generator().manual_seed(args.seed + 17)
+    lat = (1, 4, args.resolution // 8, args.resolution // 8)
+    target = torch.randn(lat, generator=g).to(dev)
+
+    t0 = time.perf_counter()
+    if args.universal:
+        ucfg = UniversalConfig(grad_reps=args.grad_reps, eps=args.eps, step_size=args.step_size,
+                               resolution=args.resolution, latent_loss=args.latent_loss, max_steps=args.max_train_steps)
+        ut = UniversalTrainer.for_b200(ucfg, vae)
+        delta = torch.zeros((1, 3, args.resolution, args.resolution), device=dev)
+        tg = target.expand(len(idx), -1, -1, -1).contiguous()
+        for _ in range(args.max_train_steps):
+            delta = ut.step(delta, images, tg, None, n_global=n, micro_batch=args.train_batch_size)
+        same = ut.check_replicas_identical(delta)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        torch.save(delta.cpu(), out_dir / f"universal_delta_rank{rank}.pt")
+        print(json.dumps({"rank": rank, "mode": "universal", "steps": args.max_train_steps, "images": len(idx),
+                          "seconds": dt, "image_grad_evals_per_s": len(idx) * args.max_train_steps * args.grad_reps / dt,
+                          "replicas_identical": same, "delta_abs_max": float(delta.abs().max())}), flush=True)
+    else:
+        cfg = TrainConfig(norm_type=args.norm_type, eps=args.eps, step_size=args.step_size, grad_reps=args.grad_reps,
+                          min_value=args.min_value, max_value=args.max_value, override_from_norm_type=False,
+                          n_optimization_steps=args.max_train_steps, latent_loss=args.latent_loss, seed=args.seed,
+                          device=dev, resolution=args.resolution, output_path=out_dir)
+        tr = Trainer(cfg, vae, micro_batch=args.train_batch_size)
+        x_adv = tr.run(images, target_latent=target) if len(idx) else images
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        torch.save({"indices": idx, "x_adv": x_adv.cpu()}, out_dir / f"adversarial_rank{rank}.pt")
+        try:
+            for i, im in zip(idx[:4], Trainer.to_pil(x_adv[:4])):
+                im.save(out_dir / f"adversarial_image_{i}.png")   # main.py:618
+        except Exception:
+            pass
+        hist = tr.loss_history
+        print(json.dumps({"rank": rank, "mode": "per-image", "steps": args.max_train_steps, "images": len(idx),
+                          "seconds": dt, "image_pgd_iters_per_s": len(idx) * args.max_train_steps / dt,
+                          "loss_first": hist[0] if hist else None, "loss_last": hist[-1] if hist else None}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
