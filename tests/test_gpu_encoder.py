@@ -202,3 +202,50 @@ def test_cli_main_runs_small(dev, tmp_path):
     out = torch.load(tmp_path / "adversarial_rank0.pt")
     assert out["x_adv"].shape == (3, 3, 64, 64) and out["indices"] == [0, 1, 2]
     assert float(out["x_adv"].abs().max()) <= 1.0
+
+
+def test_non_square_and_ragged_batch(dev, models):
+    """H != W, batch not a multiple of the micro-batch, MSE loss kind (losses.py:39-41)."""
+    from oracle.encoder_oracle import encoder_attack_grad
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.trainer import Trainer
+    oracle, vae = models
+    g = torch.Generator().manual_seed(31)
+    x = (torch.rand((3, 3, 64, 128), generator=g) * 2 - 1).to(dev)
+    t = torch.randn((3, 4, 8, 16), generator=g).to(dev)
+    n = torch.randn((3, 4, 8, 16), generator=g).to(dev)
+    od = oracle.to(dev)
+    g_ref, l_ref, _ = encoder_attack_grad(od, x, t, n, 1)
+    oracle.to("cpu")
+    cfg = TrainConfig(norm_type="linf", eps=0.1, step_size=0.01, grad_reps=1, override_from_norm_type=False,
+                      latent_loss="mse", device=str(dev))
+    tr = Trainer(cfg, vae, micro_batch=2)
+    grad, loss, _, ld = tr.compute_grad(x, None, x, None, t, [n])
+    assert cosine(grad, g_ref) >= 0.999
+    torch.testing.assert_close(ld["per_image"], l_ref, rtol=2e-2, atol=0)
+
+
+def test_bad_shapes_fail_loudly(dev, models):
+    from tml_image_editing_defense_b200._lib import TmlError
+    _, vae = models
+    with pytest.raises(TmlError):
+        vae.moments(torch.zeros((1, 3, 60, 64), device=dev))      # H not a multiple of 8
+    with pytest.raises(TmlError):
+        vae.moments(torch.zeros((1, 3, 64, 32), device=dev))      # W/8 < 8: below the tile minimum
+    with pytest.raises(TmlError):
+        vae.moments(torch.zeros((1, 3, 64, 64)))                   # CPU tensor: no fallback
+
+
+def test_target_encode_mode_and_sample_seam(dev, models):
+    """target_latent = vae.encode(target).latent_dist.sample() (main.py:75) and .mode() / retrieve_latents."""
+    oracle, vae = models
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand((2, 3, 64, 64), generator=g) * 2 - 1)
+    with torch.no_grad():
+        ref = oracle.encode(x).latent_dist
+        out = vae.encode(x.to(dev)).latent_dist
+        assert rel_err(out.mode().cpu(), ref.mode()) < 3e-2
+        assert rel_err(out.std.cpu(), ref.std) < 3e-2
+        s = out.sample(generator=torch.Generator(device=dev).manual_seed(0))
+        assert s.shape == (2, 4, 8, 8) and torch.isfinite(s).all()
+    assert vae.config.scaling_factor == 0.18215 and tuple(vae.config.block_out_channels) == (128, 256, 512, 512)

@@ -138,3 +138,33 @@ def test_tcgen05_gemm_suite(dev, lib):
     after = np.zeros(2, np.int64)
     lib.tml_launch_counts(after.ctypes.data_as(C.POINTER(C.c_int64)))
     assert after[0] - before[0] >= 32, "the tcgen05 kernel did not run"
+
+
+def test_pgd_l2_full_size_properties(dev):
+    """Size-independent properties at a large size: every image ends inside its L2 ball and the clamp
+    range; a zero gradient leaves an in-ball iterate untouched."""
+    from tml_image_editing_defense_b200 import ops
+    B, C, H, W = 16, 3, 512, 512
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.rand((B, C, H, W), generator=g, device=dev) * 2 - 1
+    xa = x.clone()
+    gr = torch.randn((B, C, H, W), generator=g, device=dev)
+    eps, step = 8.0, 3.0
+    for _ in range(4):
+        ops.pgd_step_l2_(xa, gr, x, None, eps, step, -1.0, 1.0)
+    d = (xa - x).reshape(B, -1).norm(dim=1)
+    assert float(d.max()) <= eps * (1 + 1e-5)
+    assert float(d.min()) > 0.5 * eps            # 4 steps of 3.0 along a fixed direction saturate the ball
+    assert float(xa.min()) >= -1 and float(xa.max()) <= 1
+    before = xa.clone()
+    ops.pgd_step_l2_(xa, torch.zeros_like(gr), x, None, eps * 2, step, -1.0, 1.0)
+    assert torch.equal(xa, before)
+
+
+def test_pgd_empty_and_unaligned(dev):
+    from tml_image_editing_defense_b200 import _lib, ops
+    e = torch.empty(0, device=dev)
+    assert ops.pgd_step_linf_(e, e.clone(), e.clone(), 0.1, 0.01, -1.0, 1.0).numel() == 0
+    base = torch.zeros(9, device=dev)
+    with pytest.raises(_lib.TmlError):
+        ops.pgd_step_linf_(base[1:], base[1:].clone(), torch.zeros(8, device=dev), 0.1, 0.01, -1.0, 1.0)

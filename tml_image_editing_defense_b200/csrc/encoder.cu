@@ -1017,6 +1017,7 @@ int tml_latent_loss(int kind, const float* moments, const float* noise, const fl
 
 int tml_pgd_step_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
                       int64_t n, void* stream) {
+    if (n <= 0) return 0;
     if (!x_adv || !grad || !x) { set_error("null buffer"); return -1; }
     if (((uintptr_t)x_adv | (uintptr_t)grad | (uintptr_t)x) & 15) { set_error("buffers must be 16-byte aligned"); return -1; }
     if (n <= 0) return 0;

@@ -242,6 +242,8 @@ struct TcParams {
     // halo mode (3x3 stride-1 convolutions, output rows of 128 pixels): one (mt+2) x 130-pixel halo tile per
     // 64-channel chunk serves all nine taps through row-shifted UMMA descriptors
     int halo, halo_bytes;
+    int dbg_no_epi;    // experiment: 1 = the epilogue only hands the accumulator back, 2 = no global memory ops, 3 = no GN math
+    int dbg_mma_only;  // experiment: operands are loaded for the first pass over the ring only
 };
 
 constexpr int kHaloW = 130;  // 128 output pixels + one halo pixel on each side
@@ -300,6 +302,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
             f[8 * j + 6] += bf16_lo(r.w); f[8 * j + 7] += bf16_hi(r.w);
         }
     }
+    if (p.dbg_no_epi == 2) return;
     if (p.D_sN == 1 && n0 + NC <= p.n_store && p.beta == 0.f) {
         if (p.out_fp32) {
             float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n0);
@@ -472,6 +475,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     for (int ch = 0; ch < p.kchunks; ++ch)
                         for (int tap = 0; tap < p.ntaps; ++tap) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            if (p.dbg_mma_only && (phase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                             mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
                             tma_load_3d(ring + size_t(stage) * p.stage_bytes, &mapB, &full_bar[stage],
                                         (tap * p.kchunks + ch) * kBlockK, nt * p.BN, 0);
@@ -487,6 +491,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     const int c0 = (kb - tap * p.kchunks) * kBlockK;
                     uint8_t* sA = ring + size_t(stage) * p.stage_bytes;
                     uint8_t* sB = sA + a_bytes;
+                    if (p.dbg_mma_only && (phase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
                         uint8_t* dst = sA + sub * kATileBytes;
@@ -515,6 +520,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 const SubTile s0 = decode_sub(p, tile / p.n_tiles, 0);
                 for (int ch = 0; ch < p.kchunks; ++ch) {
                     mbar_wait(&hempty_bar[hs], hphase ^ 1u);
+                    if (p.dbg_mma_only && (hphase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&hfull_bar[hs]); hs ^= 1; if (hs == 0) hphase ^= 1u; continue; }
                     mbar_arrive_expect_tx(&hfull_bar[hs], halo_tx);
                     // rows oh0-1 .. oh0+mt, pixels ow0-1 .. ow0+128: out-of-range pixels arrive as zeros (= padding)
                     tma_load_4d(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
@@ -604,14 +610,18 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         const int nch = p.BN >> 5;                      // 32-column chunks in the tile (0 when BN == 16)
         const int ch_lo = half == 0 ? 0 : (nch + 1) / 2;  // this warp's chunk range
         const int ch_hi = half == 0 ? (nch + 1) / 2 : nch;
-        const bool ld_res = p.resid != nullptr, ld_x = p.gn_mode == 2;
+        const bool ld_res = p.resid != nullptr && p.dbg_no_epi != 2, ld_x = p.gn_mode == 2 && p.dbg_no_epi != 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int mtile = tile / p.n_tiles;
             bool waited = false;
-            for (int sub = 0; sub < p.mt; ++sub) {
+            if (p.dbg_no_epi == 1) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+            }
+            for (int sub = 0; sub < p.mt && p.dbg_no_epi != 1; ++sub) {
                 const SubTile stl = decode_sub(p, mtile, sub);
                 const int sub_in_img = stl.sub_in_img, img = stl.img;
                 const int oh = stl.oh0 + r_th, ow = stl.ow0 + r_tw;
@@ -672,7 +682,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     }
                     tmem_ld_wait();
                     epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
-                    if (p.gn_mode != 0) {
+                    if (p.gn_mode != 0 && p.dbg_no_epi != 3) {
                         float gv[16];
                         if (cpg == 4) gn_chunk_sums<4>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
                         else if (cpg == 8) gn_chunk_sums<8>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
@@ -815,6 +825,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.dbg_shift = op.dbg_shift; p.dbg_bo = op.dbg_bo;
     p.halo = t.halo; p.halo_bytes = t.halo_bytes;
+    { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
+      static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne; }
 
     static bool attr_set = false;
     if (!attr_set) {
