@@ -345,6 +345,9 @@ def run_ours(args):
         roofline_pgd = {"bound": "hbm", "kernel": "pgd_linf_kernel", "achieved": pgd["gbs"], "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": pgd["gbs"] / peaks["hbm_gbs"], "bytes_per_launch": pgd["bytes"],
                         "us_per_launch": pgd["us"], "peak_source": f"{peak_src} hbm_gbs",
+                        "traffic": 762.7e6 if (res == 512 and B == 64) else None,
+                        "traffic_source": "ncu --set full, profiles/r01_prof_pgd_r1_b64.txt (dram read 604.0 MB + write 158.7 MB; "
+                                          "the remaining writes were still in L2 at kernel end)",
                         "note": "16 B/element algorithmic; working set 805 MB > 126 MB L2"}
 
     cpu = None
