@@ -97,6 +97,9 @@ void tml_gemm_timing_enable(int max_launches);
 void tml_gemm_timing_collect(double out[4]);
 /* per-shape table of the timed launches, one "name|M|N|K|mode|count|ms|flops" line each; returns bytes written */
 size_t tml_gemm_timing_report(char* buf, size_t cap);
+/* id of the mbarrier wait that timed out in the last failed GEMM launch (0 = none): 1 weight-tile slot,
+ * 2 halo slot, 3 accumulator free, 4 halo ready, 5 weight tile ready, 6 accumulator ready; +100 on the peer CTA */
+int tml_debug_last_hang(void);
 /* 0 = tcgen05 kernel (default, the product path), 1 = SIMT debug kernel (tests only) */
 void tml_debug_set_gemm_impl(int impl);
 /* Generic implicit-GEMM entry used by the kernel unit tests (same operation the encoder issues). */

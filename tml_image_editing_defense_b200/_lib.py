@@ -69,6 +69,7 @@ SIGNATURES = {
     "tml_gemm_timing_enable": (None, [C.c_int]),
     "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),
     "tml_gemm_timing_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "tml_debug_last_hang": (C.c_int, []),
     "tml_debug_set_gemm_impl": (None, [C.c_int]),
     "tml_debug_gemm": (C.c_int, [C.POINTER(TmlGemmDesc), C.c_void_p]),
     "tml_debug_gn_tiles_per_image": (C.c_int, [C.c_int, C.c_int]),

@@ -1096,6 +1096,7 @@ void tml_gemm_timing_collect(double out[4]) {
 }
 
 size_t tml_gemm_timing_report(char* buf, size_t cap) { return gemm_timing_report(buf, cap); }
+int tml_debug_last_hang(void) { return gemm_last_hang(); }
 
 void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots) {
     g_dump_base = reinterpret_cast<char*>(dev_buffer);

@@ -55,7 +55,7 @@ struct GemmOp {
 
 // Derived tiling, shared by both kernels (the debug kernel ignores the tile fields).
 struct GemmTiling {
-    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes, halo, halo_bytes;
+    int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes, halo, halo_bytes, pair;
     size_t smem_bytes;
 };
 
@@ -78,6 +78,7 @@ long gemm_launch_count();  // number of tcgen05 GEMM launches since process star
 void gemm_timing_enable(int max_launches);  // 0 disables and recycles the events
 void gemm_timing_collect(double* total_ms, double* total_flops, long* launches, long* dropped);
 size_t gemm_timing_report(char* buf, size_t cap);
+int gemm_last_hang();  // id of the mbarrier wait that timed out in the last failed launch (0 = none)
 
 void set_error(const char* fmt, ...);
 const char* last_error();

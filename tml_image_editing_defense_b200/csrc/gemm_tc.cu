@@ -178,10 +178,16 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     t->BN = BN;
     t->n_tiles = op.N / BN;
     t->kchunks = op.A_C / kBlockK;
+    t->pair = 0;
     if (halo) {
         t->mt = (BN <= 128 && op.OH % 2 == 0) ? 2 : 1;
         t->halo_bytes = (((t->mt + 2) * 130 * 128) + 1023) / 1024 * 1024;
-        t->stage_bytes = BN * 128;                        // the ring holds weight tiles only
+        // CTA pairs (cta_group::2, M = 256 over two SMs): each CTA stages its own halo tile and half of every
+        // weight tile, which halves the shared-memory operand reads per SM.
+        static const bool no_pair = getenv("TML_NO_PAIR") && getenv("TML_NO_PAIR")[0] == '1';   // tuning switch
+        const long cta_m_tiles = (long)op.A_B * (op.OH / t->mt) * t->tiles_w;
+        t->pair = (!no_pair && cta_m_tiles % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
+        t->stage_bytes = (t->pair ? BN / 2 : BN) * 128;   // the ring holds weight tiles only
         int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - 2 * t->halo_bytes) / t->stage_bytes;
         if (stages > 8) stages = 8;
         if (stages < 2) { set_error("%s: halo tiles do not fit", op.name); return -1; }
@@ -242,6 +248,8 @@ struct TcParams {
     // halo mode (3x3 stride-1 convolutions, output rows of 128 pixels): one (mt+2) x 130-pixel halo tile per
     // 64-channel chunk serves all nine taps through row-shifted UMMA descriptors
     int halo, halo_bytes;
+    int pair;          // halo mode on CTA pairs: cta_group::2 MMA (M = 256 over two SMs), each CTA stages half of B
+    volatile int* hang_where;  // mapped host word that receives the id of a wait that timed out
     int dbg_no_epi;    // experiment: 1 = the epilogue only hands the accumulator back, 2 = no global memory ops, 3 = no GN math
     int dbg_mma_only;  // experiment: operands are loaded for the first pass over the ring only
 };
@@ -433,30 +441,39 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         tma_prefetch_desc(&mapB);
     }
     if (warp == 1 && lane == 0) {
+        // pair mode: the "full" barriers live in the leader CTA and collect one arrival per CTA plus the
+        // transaction bytes of both CTAs' TMA loads; the accumulator-empty barrier collects both epilogues
+        const uint32_t nprod = p.pair ? 2u : 1u;
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], nprod);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kEpiThreads);
-            mbar_init(&hfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], kEpiThreads * nprod);
+            mbar_init(&hfull_bar[a], nprod);
             mbar_init(&hempty_bar[a], 1);
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if (p.pair) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.pair) cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = p.pair ? cluster_ctarank() : 0u;
+    volatile int* hw = p.hang_where;
+    const int htag = int(crank) * 100;
 
     const int sub_per_img = p.tiles_h * p.tiles_w;
     const int m_tiles = (p.nimg * sub_per_img) / p.mt;   // (halo: sub-tiles of a CTA tile are consecutive rows)
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int total_tiles = p.pair ? (m_tiles / 2) * p.n_tiles : m_tiles * p.n_tiles;   // pair mode: tiles of the PAIR
+    const int tile0 = p.pair ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int tile_step = p.pair ? int(gridDim.x >> 1) : int(gridDim.x);
     const int kblocks = p.ntaps * p.kchunks;
     const int a_bytes = p.mt * kATileBytes;
     const uint32_t tx_bytes = uint32_t(p.mt) * uint32_t(p.rows_valid + (p.dbg_shift ? 8 : 0)) * 128u + uint32_t(p.BN) * 128u;
@@ -467,15 +484,24 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int nt = tile % p.n_tiles;
-                const int mtile = tile / p.n_tiles;
+                const int mtile = p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
                 if (p.halo) {
                     // B (weight) tiles only, in (chunk, tap) order; the halo tiles come from warp 3
                     for (int ch = 0; ch < p.kchunks; ++ch)
                         for (int tap = 0; tap < p.ntaps; ++tap) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1u);
-                            if (p.dbg_mma_only && (phase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
+                            mbar_wait(&empty_bar[stage], phase ^ 1u, hw, htag + 1);
+                            if (p.pair) {
+                                // each CTA stages its half of the weight tile; bytes are counted on the leader's barrier
+                                if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
+                                else mbar_arrive_remote(&full_bar[stage], 0);
+                                tma_load_3d_2sm(ring + size_t(stage) * p.stage_bytes, &mapB, &full_bar[stage],
+                                                (tap * p.kchunks + ch) * kBlockK, nt * p.BN + int(crank) * (p.BN / 2), 0);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                                continue;
+                            }
+                            if (p.dbg_mma_only && (phase != 0 || tile != tile0)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                             mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
                             tma_load_3d(ring + size_t(stage) * p.stage_bytes, &mapB, &full_bar[stage],
                                         (tap * p.kchunks + ch) * kBlockK, nt * p.BN, 0);
@@ -491,7 +517,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     const int c0 = (kb - tap * p.kchunks) * kBlockK;
                     uint8_t* sA = ring + size_t(stage) * p.stage_bytes;
                     uint8_t* sB = sA + a_bytes;
-                    if (p.dbg_mma_only && (phase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
+                    if (p.dbg_mma_only && (phase != 0 || tile != tile0)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
                         uint8_t* dst = sA + sub * kATileBytes;
@@ -516,11 +542,20 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             int hs = 0;
             uint32_t hphase = 0;
             const uint32_t halo_tx = uint32_t(p.mt + 2) * kHaloW * 128u;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const SubTile s0 = decode_sub(p, tile / p.n_tiles, 0);
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const SubTile s0 = decode_sub(p, p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles, 0);
                 for (int ch = 0; ch < p.kchunks; ++ch) {
-                    mbar_wait(&hempty_bar[hs], hphase ^ 1u);
-                    if (p.dbg_mma_only && (hphase != 0 || tile != (int)blockIdx.x)) { mbar_arrive(&hfull_bar[hs]); hs ^= 1; if (hs == 0) hphase ^= 1u; continue; }
+                    mbar_wait(&hempty_bar[hs], hphase ^ 1u, hw, htag + 2);
+                    if (p.pair) {
+                        if (crank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], 2u * halo_tx);
+                        else mbar_arrive_remote(&hfull_bar[hs], 0);
+                        tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
+                                        s0.oh0 - 1, s0.img);
+                        hs ^= 1;
+                        if (hs == 0) hphase ^= 1u;
+                        continue;
+                    }
+                    if (p.dbg_mma_only && (hphase != 0 || tile != tile0)) { mbar_arrive(&hfull_bar[hs]); hs ^= 1; if (hs == 0) hphase ^= 1u; continue; }
                     mbar_arrive_expect_tx(&hfull_bar[hs], halo_tx);
                     // rows oh0-1 .. oh0+mt, pixels ow0-1 .. ow0+128: out-of-range pixels arrive as zeros (= padding)
                     tma_load_4d(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
@@ -532,42 +567,50 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kUmmaM, p.BN);
+        if (lane == 0 && crank == 0) {   // pair mode: only the leader CTA issues
+            const uint32_t idesc = umma_idesc_bf16(p.pair ? 2 * kUmmaM : kUmmaM, p.BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0, hs = 0;
             uint32_t acc_phase = 0, hphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, hw, htag + 3);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(acc * acc_cols);
                 if (p.halo) {
                     for (int ch = 0; ch < p.kchunks; ++ch) {
-                        mbar_wait(&hfull_bar[hs], hphase);
+                        mbar_wait(&hfull_bar[hs], hphase, hw, htag + 4);
                         tc_fence_after();
                         const uint32_t h_addr = smem_u32(smem + size_t(hs) * p.halo_bytes);
                         for (int tap = 0; tap < p.ntaps; ++tap) {
-                            mbar_wait(&full_bar[stage], phase);
+                            mbar_wait(&full_bar[stage], phase, hw, htag + 5);
                             tc_fence_after();
                             const uint64_t b_desc = umma_desc_sw128(smem_u32(ring + size_t(stage) * p.stage_bytes));
                             for (int sub = 0; sub < p.mt; ++sub) {
                                 // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
                                 const uint32_t row0 = uint32_t((sub + p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
                                 const uint64_t a_desc = umma_desc_sw128(h_addr + row0 * 128u);
+                                if (p.pair) {
 #pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k)
-                                    umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
-                                              idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                                    for (int k = 0; k < kBlockK / 16; ++k)
+                                        umma_bf16_2sm(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k),
+                                                      b_desc + uint64_t(2 * k), idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k)
+                                        umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
+                                                  idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                                }
                             }
-                            umma_commit(&empty_bar[stage]);
+                            if (p.pair) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
-                        umma_commit(&hempty_bar[hs]);  // halo tile free once its nine taps have retired
+                        // halo tile free once its nine taps have retired
+                        if (p.pair) umma_commit_2sm(&hempty_bar[hs], 3); else umma_commit(&hempty_bar[hs]);
                         hs ^= 1;
                         if (hs == 0) hphase ^= 1u;
                     }
-                    umma_commit(&tfull_bar[acc]);
+                    if (p.pair) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
@@ -613,9 +656,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         const bool ld_res = p.resid != nullptr && p.dbg_no_epi != 2, ld_x = p.gn_mode == 2 && p.dbg_no_epi != 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int nt = tile % p.n_tiles;
-            const int mtile = tile / p.n_tiles;
+            const int mtile = p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
             bool waited = false;
             if (p.dbg_no_epi == 1) {
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -657,7 +700,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     named_bar_sync(1, kEpiThreads);
                 }
                 if (!waited) {
-                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    mbar_wait(&tfull_bar[acc], acc_phase, hw, htag + 6);
                     tc_fence_after();
                     waited = true;
                 }
@@ -719,7 +762,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
+            else mbar_arrive(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -727,9 +771,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 
     tc_fence_before();
     __syncthreads();
+    if (p.pair) cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (p.pair) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -769,6 +815,27 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     return 0;
 }
 
+// One mapped host word per process: a kernel whose mbarrier wait times out stores the id of that wait here
+// before trapping, so the failure can be attributed after the context is gone.
+static int* g_hang_host = nullptr;
+static int* g_hang_dev = nullptr;
+static volatile int* hang_word_device() {
+    if (!g_hang_host) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_hang_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            g_hang_host = nullptr;
+            return nullptr;
+        }
+        *g_hang_host = 0;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_hang_dev), g_hang_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            g_hang_dev = nullptr;
+        }
+    }
+    return g_hang_dev;
+}
+int gemm_last_hang() { return g_hang_host ? *g_hang_host : 0; }
+
 int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     GemmTiling t;
     int rc = gemm_plan(op, &t);
@@ -795,7 +862,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)op.N, (cuuint64_t)nb};
         cuuint64_t sb = op.B_sBatch ? (cuuint64_t)op.B_sBatch * 2 : (cuuint64_t)op.B_sN * 2 * (cuuint64_t)op.N;
         cuuint64_t str[2] = {(cuuint64_t)op.B_sN * 2, sb};
-        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)t.BN, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(t.pair ? t.BN / 2 : t.BN), 1};
         if ((rc = encode_map(&mapB, op.Bm, 3, dims, str, box, op.name))) return rc;
     }
 
@@ -825,6 +892,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.dbg_shift = op.dbg_shift; p.dbg_bo = op.dbg_bo;
     p.halo = t.halo; p.halo_bytes = t.halo_bytes;
+    p.pair = t.pair;
+    p.hang_where = hang_word_device();
     { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne; }
 
@@ -836,19 +905,36 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr_set = true;
     }
     const int total_tiles = (op.A_B * t.tiles_h * t.tiles_w / t.mt) * t.n_tiles;
-    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    if (t.pair) grid &= ~1;
     const bool timed = g_timing && g_timed.size() < g_timing_cap;
     TimedLaunch tl;
     if (timed) {
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)(op.n_store > 0 ? op.n_store : op.N) * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
-                 op.ntaps * op.A_C, t.halo * 100 + op.gn_mode * 10 + t.mt);
+                 op.ntaps * op.A_C, t.pair * 1000 + t.halo * 100 + op.gn_mode * 10 + t.mt);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;
     }
-    conv_gemm_tcgen05_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+    if (t.pair) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = t.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel, mapA, mapB, p);
+        if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
+    } else {
+        conv_gemm_tcgen05_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+    }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("%s: launch failed: %s", op.name, cudaGetErrorString(e)); return -5; }

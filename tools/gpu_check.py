@@ -78,7 +78,11 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     if rc:
         print(f"[gemm] {name}: launch error {lib.tml_last_error().decode()}")
         return False
-    torch.cuda.synchronize()
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:
+        print(f"[gemm] {name}: kernel failed ({e}); last hang id = {lib.tml_debug_last_hang()}")
+        raise
     out = D.float().cpu()
     err = rel_err(out, ref)
     nan = int(torch.isnan(out).sum())
@@ -148,6 +152,8 @@ def run_gemm_suite(lib, dev):
         ("halo mt1 512->512 3x128 resid", dict(B=1, H=3, W=128, Cin=512, N=512, mode=0, resid=True)),
         ("halo mt1 256->256 5x128 +stats", dict(B=2, H=5, W=128, Cin=256, N=256, mode=0, bias=True, gn=1)),
         ("halo N=16 dgrad 4x128", dict(B=1, H=4, W=128, Cin=128, N=16, mode=1)),
+        ("halo pair 512->512 4x128 2 n-tiles", dict(B=2, H=4, W=128, Cin=512, N=512, mode=0, resid=True, bias=True, gn=1)),
+        ("halo pair N=16 dgrad 8x256", dict(B=2, H=8, W=256, Cin=128, N=16, mode=1)),
         ("halo multi-wave 128->128 128x128 B=4", dict(B=4, H=128, W=128, Cin=128, N=128, mode=0, resid=True)),
     ]
     for name, kw in cases:
