@@ -412,6 +412,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// PAIR = true is the cta_group::2 instantiation (launched as clusters of two CTAs); the PAIR = false
+// instantiation contains no cluster instruction and is launched as an ordinary grid.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                          const TcParams p) {
@@ -443,7 +446,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     if (warp == 1 && lane == 0) {
         // pair mode: the "full" barriers live in the leader CTA and collect one arrival per CTA plus the
         // transaction bytes of both CTAs' TMA loads; the accumulator-empty barrier collects both epilogues
-        const uint32_t nprod = p.pair ? 2u : 1u;
+        const uint32_t nprod = PAIR ? 2u : 1u;
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], nprod);
             mbar_init(&empty_bar[s], 1);
@@ -457,23 +460,24 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         fence_mbar_init();
     }
     if (warp == 2) {
-        if (p.pair) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        if constexpr (PAIR) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
         else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
-    if (p.pair) cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
+    if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t crank = p.pair ? cluster_ctarank() : 0u;
+    uint32_t crank = 0u;
+    if constexpr (PAIR) crank = cluster_ctarank();
     volatile int* hw = p.hang_where;
     const int htag = int(crank) * 100;
 
     const int sub_per_img = p.tiles_h * p.tiles_w;
     const int m_tiles = (p.nimg * sub_per_img) / p.mt;   // (halo: sub-tiles of a CTA tile are consecutive rows)
-    const int total_tiles = p.pair ? (m_tiles / 2) * p.n_tiles : m_tiles * p.n_tiles;   // pair mode: tiles of the PAIR
-    const int tile0 = p.pair ? int(blockIdx.x >> 1) : int(blockIdx.x);
-    const int tile_step = p.pair ? int(gridDim.x >> 1) : int(gridDim.x);
+    const int total_tiles = PAIR ? (m_tiles / 2) * p.n_tiles : m_tiles * p.n_tiles;   // pair mode: tiles of the PAIR
+    const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int tile_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
     const int kblocks = p.ntaps * p.kchunks;
     const int a_bytes = p.mt * kATileBytes;
     const uint32_t tx_bytes = uint32_t(p.mt) * uint32_t(p.rows_valid + (p.dbg_shift ? 8 : 0)) * 128u + uint32_t(p.BN) * 128u;
@@ -486,13 +490,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             uint32_t phase = 0;
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int nt = tile % p.n_tiles;
-                const int mtile = p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
+                const int mtile = PAIR ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
                 if (p.halo) {
                     // B (weight) tiles only, in (chunk, tap) order; the halo tiles come from warp 3
                     for (int ch = 0; ch < p.kchunks; ++ch)
                         for (int tap = 0; tap < p.ntaps; ++tap) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u, hw, htag + 1);
-                            if (p.pair) {
+                            if constexpr (PAIR) {
                                 // each CTA stages its half of the weight tile; bytes are counted on the leader's barrier
                                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
                                 else mbar_arrive_remote(&full_bar[stage], 0);
@@ -543,10 +547,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             uint32_t hphase = 0;
             const uint32_t halo_tx = uint32_t(p.mt + 2) * kHaloW * 128u;
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-                const SubTile s0 = decode_sub(p, p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles, 0);
+                const SubTile s0 = decode_sub(p, PAIR ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles, 0);
                 for (int ch = 0; ch < p.kchunks; ++ch) {
                     mbar_wait(&hempty_bar[hs], hphase ^ 1u, hw, htag + 2);
-                    if (p.pair) {
+                    if constexpr (PAIR) {
                         if (crank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], 2u * halo_tx);
                         else mbar_arrive_remote(&hfull_bar[hs], 0);
                         tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
@@ -568,7 +572,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0 && crank == 0) {   // pair mode: only the leader CTA issues
-            const uint32_t idesc = umma_idesc_bf16(p.pair ? 2 * kUmmaM : kUmmaM, p.BN);
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kUmmaM : kUmmaM, p.BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0, hs = 0;
@@ -590,7 +594,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                 // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
                                 const uint32_t row0 = uint32_t((sub + p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
                                 const uint64_t a_desc = umma_desc_sw128(h_addr + row0 * 128u);
-                                if (p.pair) {
+                                if constexpr (PAIR) {
 #pragma unroll
                                     for (int k = 0; k < kBlockK / 16; ++k)
                                         umma_bf16_2sm(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k),
@@ -602,15 +606,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                                   idesc, (ch | tap | k) != 0 ? 1u : 0u);
                                 }
                             }
-                            if (p.pair) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                            if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
                         // halo tile free once its nine taps have retired
-                        if (p.pair) umma_commit_2sm(&hempty_bar[hs], 3); else umma_commit(&hempty_bar[hs]);
+                        if constexpr (PAIR) umma_commit_2sm(&hempty_bar[hs], 3); else umma_commit(&hempty_bar[hs]);
                         hs ^= 1;
                         if (hs == 0) hphase ^= 1u;
                     }
-                    if (p.pair) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
+                    if constexpr (PAIR) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
@@ -658,7 +662,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int nt = tile % p.n_tiles;
-            const int mtile = p.pair ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
+            const int mtile = PAIR ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
             bool waited = false;
             if (p.dbg_no_epi == 1) {
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -762,8 +766,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 }
             }
             tc_fence_before();
-            if (crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
-            else mbar_arrive(&tempty_bar[acc]);
+            if constexpr (PAIR) {
+                if (crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
+                else mbar_arrive(&tempty_bar[acc]);
+            } else {
+                mbar_arrive(&tempty_bar[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -771,10 +779,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 
     tc_fence_before();
     __syncthreads();
-    if (p.pair) cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its TMEM
+    if constexpr (PAIR) cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its TMEM
     if (warp == 2) {
         tc_fence_after();
-        if (p.pair) tmem_dealloc_2sm(tmem_base, 512);
+        if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 512);
         else tmem_dealloc(tmem_base, 512);
     }
 }
@@ -899,8 +907,10 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set = true;
     }
@@ -930,10 +940,10 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel, mapA, mapB, p);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true>, mapA, mapB, p);
         if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
     } else {
-        conv_gemm_tcgen05_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+        conv_gemm_tcgen05_kernel<false><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
     }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
