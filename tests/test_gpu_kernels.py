@@ -168,3 +168,18 @@ def test_pgd_empty_and_unaligned(dev):
     base = torch.zeros(9, device=dev)
     with pytest.raises(_lib.TmlError):
         ops.pgd_step_linf_(base[1:], base[1:].clone(), torch.zeros(8, device=dev), 0.1, 0.01, -1.0, 1.0)
+
+
+def test_tcgen05_gemm_suite_cta_pairs(dev):
+    """The cta_group::2 (CTA-pair) instantiation of the halo kernel, enabled with TML_PAIR=1 (off by default:
+    it is correct but slower).  Runs in a subprocess because the switch is read once."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, TML_PAIR="1")
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_check.py"), "--gemm-only"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL OK" in r.stdout

@@ -183,10 +183,12 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
         t->mt = (BN <= 128 && op.OH % 2 == 0) ? 2 : 1;
         t->halo_bytes = (((t->mt + 2) * 130 * 128) + 1023) / 1024 * 1024;
         // CTA pairs (cta_group::2, M = 256 over two SMs): each CTA stages its own halo tile and half of every
-        // weight tile, which halves the shared-memory operand reads per SM.
-        static const bool no_pair = getenv("TML_NO_PAIR") && getenv("TML_NO_PAIR")[0] == '1';   // tuning switch
+        // weight tile.  Correct (tests run it) but OFF by default: measured on B200 the MMA-only ceiling is the
+        // same as cta_group::1 (1160 / 1590 TFLOP/s at N = 128 / 256: the power-limited tensor peak, not shared-
+        // memory bandwidth), while the cross-CTA barrier round trips make the real kernel 25-35 % slower.
+        static const bool use_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '1';   // experiment switch
         const long cta_m_tiles = (long)op.A_B * (op.OH / t->mt) * t->tiles_w;
-        t->pair = (!no_pair && cta_m_tiles % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
+        t->pair = (use_pair && cta_m_tiles % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
         t->stage_bytes = (t->pair ? BN / 2 : BN) * 128;   // the ring holds weight tiles only
         int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - 2 * t->halo_bytes) / t->stage_bytes;
         if (stages > 8) stages = 8;
@@ -497,6 +499,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         for (int tap = 0; tap < p.ntaps; ++tap) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u, hw, htag + 1);
                             if constexpr (PAIR) {
+                                if (p.dbg_mma_only && (phase != 0 || tile != tile0)) {
+                                    if (crank == 0) mbar_arrive(&full_bar[stage]); else mbar_arrive_remote(&full_bar[stage], 0);
+                                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                                    continue;
+                                }
                                 // each CTA stages its half of the weight tile; bytes are counted on the leader's barrier
                                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
                                 else mbar_arrive_remote(&full_bar[stage], 0);
@@ -551,6 +558,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 for (int ch = 0; ch < p.kchunks; ++ch) {
                     mbar_wait(&hempty_bar[hs], hphase ^ 1u, hw, htag + 2);
                     if constexpr (PAIR) {
+                        if (p.dbg_mma_only && (hphase != 0 || tile != tile0)) {
+                            if (crank == 0) mbar_arrive(&hfull_bar[hs]); else mbar_arrive_remote(&hfull_bar[hs], 0);
+                            hs ^= 1;
+                            if (hs == 0) hphase ^= 1u;
+                            continue;
+                        }
                         if (crank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], 2u * halo_tx);
                         else mbar_arrive_remote(&hfull_bar[hs], 0);
                         tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,

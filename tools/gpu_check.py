@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--impl", default="both")
     ap.add_argument("--skip-gemm", action="store_true")
+    ap.add_argument("--gemm-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -243,7 +244,8 @@ def main():
             if not args.skip_gemm:
                 allok &= run_gemm_suite(lib, dev)
             sys.stdout.flush()
-            allok &= run_encoder(dev, args.res, args.batch, 0, label)
+            if not args.gemm_only:
+                allok &= run_encoder(dev, args.res, args.batch, 0, label)
         except Exception:
             allok = False
             traceback.print_exc()
