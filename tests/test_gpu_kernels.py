@@ -179,7 +179,7 @@ def test_tcgen05_gemm_suite_cta_pairs(dev):
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
     env = dict(os.environ, TML_PAIR="1")
-    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_check.py"), "--gemm-only"], env=env, capture_output=True,
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_check.py"), "--gemm-only", "--impl", "tc"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "ALL OK" in r.stdout

@@ -23,6 +23,9 @@ from tests.helpers import (BACKWARD_STAGE_NAMES, cosine, emulate_gemm, fetch_sav
 from tml_image_editing_defense_b200 import _lib, ops  # noqa
 
 
+IMPL = {"simt": False}
+
+
 def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid=False, alpha=1.0, seed=0, gn=0):
     """conv3x3 in packing mode `mode` (0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity) or mode -1: 1x1."""
     g = torch.Generator().manual_seed(seed)
@@ -62,6 +65,8 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     d.D = D.data_ptr(); d.out_fp32 = 0
     d.D_sW = N; d.D_sH = OW * N; d.D_sB = OH * OW * N; d.D_sN = 1; d.n_store = 0
     keep = []
+    if gn and IMPL["simt"]:
+        gn = 0   # the SIMT debug kernel has no fused reductions
     if gn:
         ntile = lib.tml_debug_gn_tiles_per_image(OH, OW)
         part = torch.full((B, ntile, 32, 2), float("nan"), dtype=torch.float32, device=dev)
@@ -239,6 +244,7 @@ def main():
     for impl in impls:
         label = "tc" if impl == 0 else "simt"
         lib.tml_debug_set_gemm_impl(impl)
+        IMPL["simt"] = impl == 1
         print(f"===== GEMM impl = {label} =====", flush=True)
         try:
             if not args.skip_gemm:
