@@ -92,6 +92,13 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not _LIB_PATH.exists():
+        # not built yet (fresh checkout): compile the CUDA sources in tree; still no non-CUDA fallback
+        try:
+            from .build import build_extension
+            build_extension()
+        except Exception as e:  # noqa: BLE001
+            raise TmlError(f"{_LIB_PATH} is missing and building it failed: {e}") from e
+    if not _LIB_PATH.exists():
         raise TmlError(
             f"{_LIB_PATH} not found: build it with `python -m tml_image_editing_defense_b200.build` "
             "(there is no CPU / PyTorch fallback for the hot path)")

@@ -40,11 +40,23 @@ def _digest() -> str:
 
 
 def build_extension(force: bool = False, verbose: bool = False) -> Path:
+    """Compile if the sources changed since the last build.  Safe to call from several processes at once
+    (one rank per GPU): an exclusive file lock serialises the build, the others find it up to date."""
+    import fcntl
+    (CSRC / "build").mkdir(exist_ok=True)
+    with open(CSRC / "build" / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     stamp = CSRC / "build" / "stamp.txt"
     digest = _digest()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
-    (CSRC / "build").mkdir(exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
