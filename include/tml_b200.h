@@ -62,6 +62,25 @@ int tml_encoder_forward(TmlEncoder* enc, const float* x_nchw, int B, int H, int 
 int tml_encoder_backward(TmlEncoder* enc, const float* dmoments_nchw, int B, int H, int W, const void* saved,
                          float* dx_nchw, float beta, void* ws, void* stream);
 
+/* ---- decoder: replaces pipeline.vae.decode(output_latent).sample (main.py:156) and its backward.  Uses the
+ *      same handle: register the "decoder.*" and "post_quant_conv.*" tensors with tml_encoder_set_weight before
+ *      tml_encoder_finalize.  z: fp32 NCHW [B,4,h,w] -> image fp32 NCHW [B,3,8h,8w]. ---- */
+int tml_decoder_query(TmlEncoder* vae, int B, int h, int w, size_t* workspace_bytes, size_t* saved_bytes);
+int tml_decoder_forward(TmlEncoder* vae, const float* z_nchw, int B, int h, int w, float* image_nchw, void* saved,
+                        void* ws, void* stream);
+int tml_decoder_backward(TmlEncoder* vae, const float* dimage_nchw, int B, int h, int w, const void* saved,
+                         float* dz_nchw, void* ws, void* stream);
+/* image-space losses per image: rec = ||out - target||_2 (main.py:160), pert = mean((out - source)^2)
+ * (losses/losses.py:39-41, main.py:168); dout = rec_lambda * d rec + pert_lambda * d pert (main.py:169).
+ * source / rec / pert / dout may be NULL; ws of tml_image_loss_workspace(B) bytes. */
+size_t tml_image_loss_workspace(int B);
+int tml_image_loss(const float* out, const float* target, const float* source, int B, int64_t per_image,
+                   float rec_lambda, float pert_lambda, float* rec, float* pert, float* dout, void* ws, void* stream);
+/* latent_dist.sample() / mode() (noise NULL) as a stand-alone op and its backward w.r.t. the moments */
+int tml_posterior_sample(const float* moments, const float* noise, float* z, int B, int h, int w, void* stream);
+int tml_posterior_sample_backward(const float* moments, const float* noise, const float* dz, float* dmoments, int B,
+                                  int h, int w, void* stream);
+
 /* ---- posterior sample + latent loss + gradient: replaces latent_dist.sample() (main.py:191),
  *      (output_latent - target_latent).norm(p=2) (main.py:162, kind 0) and F.mse_loss
  *      (losses/losses.py:39-41, kind 1).  noise may be NULL (-> latent_dist.mode()).
@@ -120,6 +139,7 @@ int tml_debug_gn_tiles_per_image(int OH, int OW);
  * "conv_in", "resnet_h1"/"resnet_out" (index = resnet in forward order), "down_out", "attn_qkv",
  * "attn_P" ([B,tok,tok,1]), "attn_out". */
 int tml_debug_saved_tensor(TmlEncoder* enc, const char* name, int index, size_t* offset, int dims[4]);
+int tml_debug_decoder_saved_tensor(TmlEncoder* vae, const char* name, int index, size_t* offset, int dims[4]);
 /* Every backward stage copies its output gradient (bf16 NHWC) into slot k of dev_buffer (NULL = off). */
 void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots);
 /* Host-only helpers (no CUDA calls) used by the CPU tests of the weight packing. */

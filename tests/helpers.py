@@ -121,3 +121,60 @@ def fetch_saved(vae, saved, name, index=0):
     n = B * H * W * Cc
     t = saved[off.value: off.value + 2 * n].view(torch.bfloat16).view(B, H, W, Cc)
     return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder tracing
+# ------------------------------------------------------------------------------------------------
+DEC_BACKWARD_STAGE_NAMES = ["res13_out", "res12_out", "res11_out", "up2_out", "res10_out", "res9_out", "res8_out",
+                            "up1_out", "res7_out", "res6_out", "res5_out", "up0_out", "res4_out", "res3_out",
+                            "res2_out", "res1_out", "attn_out", "res0_out", "conv_in"]
+
+
+def oracle_decoder_resnets(model):
+    dec = model.decoder
+    out = list(dec.mid_block.resnets)
+    for blk in dec.up_blocks:
+        out.extend(list(blk.resnets))
+    return out
+
+
+def oracle_decoder_trace(model, z, dimage):
+    """Decoder activations and their gradients for a given upstream gradient d(image)."""
+    acts, handles = {}, []
+
+    def keep(name):
+        def hook(mod, inp, out):
+            out.retain_grad()
+            acts[name] = out
+        return hook
+
+    dec = model.decoder
+    handles.append(dec.conv_in.register_forward_hook(keep("conv_in")))
+    for i, r in enumerate(oracle_decoder_resnets(model)):
+        handles.append(r.register_forward_hook(keep(f"res{i}_out")))
+    for i, blk in enumerate(dec.up_blocks):
+        if blk.upsamplers is not None:
+            handles.append(blk.upsamplers[0].register_forward_hook(keep(f"up{i}_out")))
+    if dec.mid_block.attentions is not None:
+        handles.append(dec.mid_block.attentions[0].register_forward_hook(keep("attn_out")))
+    with torch.enable_grad():
+        zz = z.clone().requires_grad_(True)
+        img = model.decode(zz)
+        img.backward(dimage)
+    for h in handles:
+        h.remove()
+    grads = {k: v.grad.detach() for k, v in acts.items() if v.grad is not None}
+    acts = {k: v.detach() for k, v in acts.items()}
+    return acts, grads, img.detach(), zz.grad.detach()
+
+
+def fetch_decoder_saved(vae, saved, name, index=0):
+    from tml_image_editing_defense_b200 import _lib
+    off = C.c_size_t()
+    dims = (C.c_int * 4)()
+    _lib.check(vae._lib.tml_debug_decoder_saved_tensor(vae._h, name.encode(), index, C.byref(off), dims))
+    B, H, W, Cc = list(dims)
+    n = B * H * W * Cc
+    t = saved[off.value: off.value + 2 * n].view(torch.bfloat16).view(B, H, W, Cc)
+    return t.float().permute(0, 3, 1, 2).contiguous()

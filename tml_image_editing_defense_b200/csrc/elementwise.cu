@@ -671,6 +671,233 @@ void launch_dmoments_pack(const float* dm, bf16* out, int B, int h, int w, cudaS
 }
 
 // ================================================================================================
+// Decoder-side helpers (vae.decode at main.py:156; image-space losses main.py:160,168)
+// ================================================================================================
+__global__ void latent_pack_kernel(const float* __restrict__ z, const float* __restrict__ wpq,
+                                   const float* __restrict__ bpq, bf16* __restrict__ out, int hw, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (pixel, octet)
+    if (i >= total) return;
+    const int oct = int(i & 7);
+    const long long pix = i >> 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (oct == 0) {
+        const long long b = pix / hw, p = pix % hw;
+        float zi[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zi[c] = z[(b * 4 + c) * hw + p];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a = bpq[o];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a = fmaf(wpq[o * 4 + c], zi[c], a);
+            f[o] = a;
+        }
+    }
+    *reinterpret_cast<uint4*>(out + pix * 64 + oct * 8) = pack8(f);
+}
+void launch_latent_pack(const float* z, const float* wpq, const float* bpq, bf16* out, int B, int hw, cudaStream_t s) {
+    const long long total = (long long)B * hw * 8;
+    latent_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, wpq, bpq, out, hw, total);
+    COUNT_LAUNCH();
+}
+
+__global__ void latent_unpack_bwd_kernel(const bf16* __restrict__ d, const float* __restrict__ wpq,
+                                         float* __restrict__ dz, int hw, long long total) {
+    const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const uint2 u = *reinterpret_cast<const uint2*>(d + pix * 64);
+    const float g[4] = {bf_lo(u.x), bf_hi(u.x), bf_lo(u.y), bf_hi(u.y)};
+    const long long b = pix / hw, p = pix % hw;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a = fmaf(wpq[o * 4 + c], g[o], a);
+        dz[(b * 4 + c) * hw + p] = a;
+    }
+}
+void launch_latent_unpack_bwd(const bf16* d, const float* wpq, float* dz, int B, int hw, cudaStream_t s) {
+    const long long total = (long long)B * hw;
+    latent_unpack_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d, wpq, dz, hw, total);
+    COUNT_LAUNCH();
+}
+
+// one thread per (low-res pixel, channel octet): read once, write the four copies
+__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int h,
+                                                         int w, int C8, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int oct = int(i % C8);
+        long long pix = i / C8;
+        const int x = int(pix % w); pix /= w;
+        const int y = int(pix % h);
+        const long long b = pix / h;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+        const long long W2 = 2LL * w;
+        uint4* o = reinterpret_cast<uint4*>(out) + ((b * 2 * h + 2 * y) * W2 + 2 * x) * C8 + oct;
+        o[0] = v; o[C8] = v; o[W2 * C8] = v; o[W2 * C8 + C8] = v;
+    }
+}
+void launch_upsample2x(const bf16* in, bf16* out, int B, int h, int w, int C, cudaStream_t s) {
+    const long long total = (long long)B * h * w * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    upsample2x_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, h, w, C / 8, total);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
+                                                             int h, int w, int C8, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int oct = int(i % C8);
+        long long pix = i / C8;
+        const int x = int(pix % w); pix /= w;
+        const int y = int(pix % h);
+        const long long b = pix / h;
+        const long long W2 = 2LL * w;
+        const uint4* o = reinterpret_cast<const uint4*>(dout) + ((b * 2 * h + 2 * y) * W2 + 2 * x) * C8 + oct;
+        float a[8], t[8];
+        unpack8(__ldg(o), a);
+        unpack8(__ldg(o + C8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += t[j];
+        unpack8(__ldg(o + W2 * C8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += t[j];
+        unpack8(__ldg(o + W2 * C8 + C8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += t[j];
+        reinterpret_cast<uint4*>(din)[i] = pack8(a);
+    }
+}
+void launch_upsample2x_bwd(const bf16* dout, bf16* din, int B, int h, int w, int C, cudaStream_t s) {
+    const long long total = (long long)B * h * w * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    upsample2x_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(dout, din, h, w, C / 8, total);
+    COUNT_LAUNCH();
+}
+
+__global__ void image_pack_kernel(const float* __restrict__ dimg, bf16* __restrict__ out, long long hw, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (pixel, octet)
+    if (i >= total) return;
+    const int oct = int(i & 7);
+    const long long pix = i >> 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (oct == 0) {
+        const long long b = pix / hw, p = pix % hw;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] = dimg[(b * 3 + c) * hw + p];
+    }
+    *reinterpret_cast<uint4*>(out + pix * 64 + oct * 8) = pack8(f);
+}
+void launch_image_pack(const float* dimg, bf16* out, int B, long long hw, cudaStream_t s) {
+    const long long total = (long long)B * hw * 8;
+    image_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dimg, out, hw, total);
+    COUNT_LAUNCH();
+}
+
+// image-space losses, per image (main.py:160 rec_loss = (output_image - target_image).norm(p=2);
+// :168 pert_loss = F.mse_loss(output_image, source_image)), two-stage fixed-order reduction
+constexpr int kImgChunks = 64;
+size_t image_loss_workspace_bytes(int B) { return (size_t)B * kImgChunks * 2 * sizeof(double); }
+
+__global__ void __launch_bounds__(256) image_loss_partial_kernel(const float* __restrict__ out,
+                                                                 const float* __restrict__ target,
+                                                                 const float* __restrict__ source,
+                                                                 double* __restrict__ part, long long per_image) {
+    __shared__ double red[33];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const long long c0 = per_image * chunk / kImgChunks, c1 = per_image * (chunk + 1) / kImgChunks;
+    const size_t off = (size_t)b * per_image;
+    double a = 0.0, q = 0.0;
+    for (long long i = c0 + threadIdx.x; i < c1; i += 256) {
+        const float o = out[off + i];
+        const float dt = o - target[off + i];
+        a += (double)dt * dt;
+        if (source) { const float ds = o - source[off + i]; q += (double)ds * ds; }
+    }
+    a = block_sum_d(a, red);
+    q = block_sum_d(q, red);
+    if (threadIdx.x == 0) {
+        part[((size_t)b * kImgChunks + chunk) * 2] = a;
+        part[((size_t)b * kImgChunks + chunk) * 2 + 1] = q;
+    }
+}
+__global__ void __launch_bounds__(256) image_loss_grad_kernel(const float* __restrict__ out,
+                                                              const float* __restrict__ target,
+                                                              const float* __restrict__ source,
+                                                              const double* __restrict__ part, float rec_l,
+                                                              float pert_l, float* __restrict__ rec,
+                                                              float* __restrict__ pert, float* __restrict__ dout,
+                                                              long long per_image) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    double a = 0.0, q = 0.0;
+    for (int c = 0; c < kImgChunks; ++c) {
+        a += part[((size_t)b * kImgChunks + c) * 2];
+        q += part[((size_t)b * kImgChunks + c) * 2 + 1];
+    }
+    const float nrm = (float)sqrt(a);
+    const float mse = (float)(q / (double)per_image);
+    if (chunk == 0 && threadIdx.x == 0) {
+        if (rec) rec[b] = nrm;
+        if (pert) pert[b] = mse;
+    }
+    if (!dout) return;
+    const float cr = nrm > 0.f ? rec_l / nrm : 0.f;
+    const float cp = (source && pert_l != 0.f) ? pert_l * 2.f / (float)per_image : 0.f;
+    const long long c0 = per_image * chunk / kImgChunks, c1 = per_image * (chunk + 1) / kImgChunks;
+    const size_t off = (size_t)b * per_image;
+    for (long long i = c0 + threadIdx.x; i < c1; i += 256) {
+        const float o = out[off + i];
+        float g = cr * (o - target[off + i]);
+        if (cp != 0.f) g = fmaf(cp, o - source[off + i], g);
+        dout[off + i] = g;
+    }
+}
+void launch_image_loss(const float* out, const float* target, const float* source, int B, long long per_image,
+                       float rec_l, float pert_l, float* rec, float* pert, float* dout, void* ws, cudaStream_t s) {
+    double* part = reinterpret_cast<double*>(ws);
+    dim3 grid(kImgChunks, B);
+    image_loss_partial_kernel<<<grid, 256, 0, s>>>(out, target, source, part, per_image);
+    image_loss_grad_kernel<<<grid, 256, 0, s>>>(out, target, source, part, rec_l, pert_l, rec, pert, dout, per_image);
+    COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
+__global__ void posterior_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                        float* __restrict__ z, int n4, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / n4, k = i % n4;
+    const float mu = moments[b * 2 * n4 + k];
+    const float lv = fminf(fmaxf(moments[b * 2 * n4 + n4 + k], -30.f), 20.f);
+    z[i] = noise ? fmaf(expf(0.5f * lv), noise[i], mu) : mu;
+}
+void launch_posterior_sample(const float* moments, const float* noise, float* z, int B, int hw, cudaStream_t s) {
+    const long long total = (long long)B * 4 * hw;
+    posterior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(moments, noise, z, 4 * hw, total);
+    COUNT_LAUNCH();
+}
+__global__ void posterior_sample_bwd_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                            const float* __restrict__ dz, float* __restrict__ dm, int n4,
+                                            long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / n4, k = i % n4;
+    const float lv_raw = moments[b * 2 * n4 + n4 + k];
+    const float lv = fminf(fmaxf(lv_raw, -30.f), 20.f);
+    const float g = dz[i];
+    dm[b * 2 * n4 + k] = g;
+    dm[b * 2 * n4 + n4 + k] = (noise && lv_raw >= -30.f && lv_raw <= 20.f) ? g * noise[i] * expf(0.5f * lv) * 0.5f : 0.f;
+}
+void launch_posterior_sample_bwd(const float* moments, const float* noise, const float* dz, float* dmoments, int B,
+                                 int hw, cudaStream_t s) {
+    const long long total = (long long)B * 4 * hw;
+    posterior_sample_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(moments, noise, dz, dmoments, 4 * hw, total);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
 // PGD updates (main.py:248-276).  L-inf: one fused, 16-byte vectorised, grid-stride
 // kernel — 16 B/element of HBM traffic (read X_adv, grad, X; write X_adv) instead of the 8 ATen
 // launches of the reference.  Bit-exact with the ATen sequence including its special values:

@@ -55,6 +55,25 @@ void launch_batch_sum(const float* g, float* out, int B, long long per_image, fl
 void launch_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
                            float hi, long long n, void* ws, cudaStream_t s);
 
+// ---- decoder-side helpers (vae.decode, main.py:156; image-space losses main.py:160,168) ----
+// z fp32 NCHW [B,4,hw] -> post_quant_conv (4x4 1x1 conv + bias, fp32) -> bf16 NHWC [B,hw,64], channels 4..63 zero
+void launch_latent_pack(const float* z, const float* wpq, const float* bpq, bf16* out, int B, int hw, cudaStream_t s);
+// its backward: d bf16 NHWC [B,hw,64] (first 4 channels) -> dz fp32 NCHW = Wpq^T d
+void launch_latent_unpack_bwd(const bf16* d, const float* wpq, float* dz, int B, int hw, cudaStream_t s);
+// nearest-neighbour 2x upsample of bf16 NHWC [B,h,w,C] -> [B,2h,2w,C], and its backward (sum of the 4 copies)
+void launch_upsample2x(const bf16* in, bf16* out, int B, int h, int w, int C, cudaStream_t s);
+void launch_upsample2x_bwd(const bf16* dout, bf16* din, int B, int h, int w, int C, cudaStream_t s);
+// fp32 NCHW [B,3,HW] -> bf16 NHWC [B,HW,64] (channels 3..63 zero): the A operand of decoder.conv_out's dgrad
+void launch_image_pack(const float* dimg, bf16* out, int B, long long hw, cudaStream_t s);
+// per image: rec = ||out - target||_2, pert = mean((out - source)^2), dout = rec_l*d rec + pert_l*d pert
+size_t image_loss_workspace_bytes(int B);
+void launch_image_loss(const float* out, const float* target, const float* source, int B, long long per_image,
+                       float rec_l, float pert_l, float* rec, float* pert, float* dout, void* ws, cudaStream_t s);
+// z = mean + exp(.5*clamp(logvar))*noise and its backward w.r.t. the moments
+void launch_posterior_sample(const float* moments, const float* noise, float* z, int B, int hw, cudaStream_t s);
+void launch_posterior_sample_bwd(const float* moments, const float* noise, const float* dz, float* dmoments, int B,
+                                 int hw, cudaStream_t s);
+
 long kernel_launch_count();
 
 }  // namespace tml

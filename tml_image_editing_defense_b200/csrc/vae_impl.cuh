@@ -1,0 +1,719 @@
+// Shared implementation pieces of the VAE encoder and decoder walks: host-side weight packing, the layer
+// parameter / saved-state records, the scratch arena, and the ResnetBlock2D / GroupNorm / attention
+// forward and input-gradient sequences that both networks are built from.  Included by encoder.cu and
+// decoder.cu (everything here has internal linkage).
+#pragma once
+// (decoder.cu) builds the decoder parameters from the registered host tensors; called by tml_encoder_finalize
+struct TmlEncoder;
+int decoder_finalize(TmlEncoder* e);
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tml_b200.h"
+#include "gemm.h"
+#include "kernels.h"
+
+using namespace tml;
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+static uint16_t f2bf(float f) {  // round-to-nearest-even, NaN preserved
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float half2f(uint16_t h) {
+    uint32_t s = (h >> 15) & 1, e = (h >> 10) & 31, m = h & 1023, u;
+    if (e == 0) {
+        if (m == 0) u = s << 31;
+        else { int sh = 0; while (!(m & 1024)) { m <<= 1; ++sh; } m &= 1023; u = (s << 31) | ((113 - sh) << 23) | (m << 13); }
+    } else if (e == 31) u = (s << 31) | 0x7F800000u | (m << 13);
+    else u = (s << 31) | ((e + 112) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+#define CUDA_OK(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -10;                                                                      \
+        }                                                                                    \
+    } while (0)
+#define RC(call)              \
+    do {                      \
+        int _r = (call);      \
+        if (_r) return _r;    \
+    } while (0)
+
+struct HostTensor {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+};
+
+// 3x3 tap tables + packed matrices -------------------------------------------------------------
+// mode 0: forward s1 p1      B[co][t*Ci+ci] = W[co][ci][r][s], t=r*3+s, (dh,dw) = (r-1, s-1)
+// mode 1: dgrad of s1 p1     B[ci][t*Co+co] = W[co][ci][r][s],           (dh,dw) = (1-r, 1-s)
+// mode 2: forward s2, pad (0,1,0,1): same matrix as mode 0,             (dh,dw) = (r, s)
+// mode 3..6: dgrad of s2 for output parity (ph,pw): dX[2i+ph, 2j+pw] = sum over taps with
+//            r = ph (mod 2), s = pw (mod 2) of dY[i + (ph-r)/2, j + (pw-s)/2] * W[co][ci][r][s]
+static int pack_conv3x3(const float* w, int Co, int Ci, int mode, std::vector<uint16_t>& out, int* ntaps, int* dh,
+                        int* dw) {
+    auto W = [&](int co, int ci, int r, int s) { return w[(((size_t)co * Ci + ci) * 3 + r) * 3 + s]; };
+    if (mode == 0 || mode == 2) {
+        *ntaps = 9;
+        out.assign((size_t)Co * 9 * Ci, 0);
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+                const int t = r * 3 + s;
+                dh[t] = mode == 0 ? r - 1 : r;
+                dw[t] = mode == 0 ? s - 1 : s;
+                for (int co = 0; co < Co; ++co)
+                    for (int ci = 0; ci < Ci; ++ci) out[(size_t)co * 9 * Ci + (size_t)t * Ci + ci] = f2bf(W(co, ci, r, s));
+            }
+        return 0;
+    }
+    if (mode == 1) {
+        *ntaps = 9;
+        out.assign((size_t)Ci * 9 * Co, 0);
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+                const int t = r * 3 + s;
+                dh[t] = 1 - r;
+                dw[t] = 1 - s;
+                for (int ci = 0; ci < Ci; ++ci)
+                    for (int co = 0; co < Co; ++co) out[(size_t)ci * 9 * Co + (size_t)t * Co + co] = f2bf(W(co, ci, r, s));
+            }
+        return 0;
+    }
+    if (mode >= 3 && mode <= 6) {
+        const int ph = (mode - 3) >> 1, pw = (mode - 3) & 1;
+        int rs[2], ss[2], nr = 0, ns = 0;
+        for (int r = 0; r < 3; ++r) if ((r & 1) == ph) rs[nr++] = r;
+        for (int s = 0; s < 3; ++s) if ((s & 1) == pw) ss[ns++] = s;
+        *ntaps = nr * ns;
+        out.assign((size_t)Ci * (*ntaps) * Co, 0);
+        int t = 0;
+        for (int a = 0; a < nr; ++a)
+            for (int b = 0; b < ns; ++b, ++t) {
+                const int r = rs[a], s = ss[b];
+                dh[t] = (ph - r) / 2;  // 0 or -1
+                dw[t] = (pw - s) / 2;
+                for (int ci = 0; ci < Ci; ++ci)
+                    for (int co = 0; co < Co; ++co)
+                        out[(size_t)ci * (*ntaps) * Co + (size_t)t * Co + co] = f2bf(W(co, ci, r, s));
+            }
+        return 0;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side layer parameters
+// ------------------------------------------------------------------------------------------------
+struct Packed {
+    bf16* w = nullptr;  // [N][ntaps*K]
+    int ntaps = 1;
+    int dh[kMaxTaps] = {0}, dw[kMaxTaps] = {0};
+};
+struct Conv3 {
+    int ci = 0, co = 0, stride = 1;
+    Packed fwd, bwd, bwd_par[4];
+    float* bias = nullptr;
+};
+struct Lin {  // 1x1 conv or linear: fwd [co][ci], bwd [ci][co]
+    int ci = 0, co = 0;
+    bf16* fwd = nullptr;
+    bf16* bwd = nullptr;
+    float* bias = nullptr;
+};
+struct Norm {
+    int C = 0;
+    float* gamma = nullptr;
+    float* beta = nullptr;
+};
+struct Resnet {
+    int ci = 0, co = 0;
+    Norm n1, n2;
+    Conv3 c1, c2;
+    bool has_sc = false;
+    Lin sc;
+};
+struct Attn {
+    int C = 0;
+    Norm gn;
+    Lin qkv;  // fwd [3C][C], bwd [C][3C]
+    Lin out;
+};
+
+// saved-state record of one GroupNorm: scale/shift per (b,c) and mean/rstd per (b,g)
+struct GnSaved { size_t ss = 0, mr = 0; };
+struct ResnetRec { size_t x = 0, h1 = 0, out = 0; GnSaved g1, g2; int h = 0, w = 0; };
+struct DownRec { size_t x = 0, out = 0; int h = 0, w = 0; };
+struct AttnRec { size_t x = 0, qkv = 0, P = 0, out = 0; GnSaved g; int h = 0, w = 0; };
+
+struct Arena {
+    size_t off = 0, peak = 0;
+    size_t alloc(size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) & ~size_t(255);
+        if (off > peak) peak = off;
+        return o;
+    }
+    size_t mark() const { return off; }
+    void reset(size_t m) { off = m; }
+};
+
+struct Layout {
+    int B = 0, H = 0, W = 0;
+    size_t saved_bytes = 0, ws_bytes = 0;
+    size_t x0 = 0;  // conv_in output
+    std::vector<ResnetRec> res;
+    std::vector<DownRec> down;
+    AttnRec attn;
+    GnSaved gout;
+    size_t xlast = 0;
+    int hl = 0, wl = 0;
+};
+
+struct UpRec { size_t out = 0; int h = 0, w = 0; };   // Upsample2D: (h, w) = input size, out = conv output at (2h, 2w)
+struct DecLayout {
+    int B = 0, h = 0, w = 0;             // latent size
+    size_t saved_bytes = 0, ws_bytes = 0;
+    size_t x0 = 0;                       // decoder.conv_in output
+    std::vector<ResnetRec> res;
+    AttnRec attn;
+    std::vector<UpRec> ups;
+    GnSaved gout;
+    size_t xlast = 0;
+    int Hl = 0, Wl = 0;                  // output image size
+};
+
+struct TmlEncoder {
+    TmlEncoderCfg cfg;
+    int device = 0;
+    int num_sms = 148;
+    bool finalized = false;
+    std::map<std::string, HostTensor> host;
+    std::vector<void*> dev_allocs;
+    // parameters
+    float* conv_in_w = nullptr;  // [27][C0] fp32
+    float* conv_in_b = nullptr;
+    Packed conv_in_bwd;          // dgrad as a GEMM: B[ci (3, padded to 16)][t*C0 + co]
+    std::vector<Resnet> resnets;          // in forward order (down blocks then mid[0], mid[1])
+    std::vector<Conv3> downs;
+    bool has_attn = false;
+    Attn attn;
+    Norm norm_out;
+    Conv3 conv_out;  // folded with quant_conv, N padded to 16; bwd has K = 64 (8 real)
+    Layout lay;
+    // ---- decoder (optional: present when "decoder.*" / "post_quant_conv.*" weights were registered) ----
+    bool has_decoder = false;
+    float* pq_w = nullptr;                // post_quant_conv [4][4] fp32
+    float* pq_b = nullptr;
+    Conv3 dec_conv_in;                    // 4 (padded to 64) -> C: fwd [C][9*64], bwd [64][9*C]
+    std::vector<Resnet> dec_resnets;      // mid[0], mid[1], then the up blocks' resnets in forward order
+    bool dec_has_attn = false;
+    Attn dec_attn;
+    std::vector<Conv3> ups;               // Upsample2D convs
+    Norm dec_norm_out;
+    Conv3 dec_conv_out;                   // C0 -> 3: fwd N padded to 16; bwd A = d(image) padded to 64 channels
+    DecLayout dlay;
+};
+
+// ------------------------------------------------------------------------------------------------
+// weight upload
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(TmlEncoder* e, const std::vector<T>& h, T** out) {
+    void* d = nullptr;
+    CUDA_OK(cudaMalloc(&d, h.size() * sizeof(T) + 256));
+    CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    e->dev_allocs.push_back(d);
+    *out = reinterpret_cast<T*>(d);
+    return 0;
+}
+static int upload_bf16(TmlEncoder* e, const std::vector<uint16_t>& h, bf16** out) {
+    uint16_t* d = nullptr;
+    RC(upload<uint16_t>(e, h, &d));
+    *out = reinterpret_cast<bf16*>(d);
+    return 0;
+}
+
+static const HostTensor* find(TmlEncoder* e, const std::string& key, size_t expect_numel) {
+    auto it = e->host.find(key);
+    if (it == e->host.end()) { set_error("missing weight '%s'", key.c_str()); return nullptr; }
+    if (it->second.v.size() != expect_numel) {
+        set_error("weight '%s' has %zu elements, expected %zu", key.c_str(), it->second.v.size(), expect_numel);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+static int make_norm(TmlEncoder* e, const std::string& key, int C, Norm* n) {
+    const HostTensor* g = find(e, key + ".weight", C);
+    const HostTensor* b = find(e, key + ".bias", C);
+    if (!g || !b) return -20;
+    n->C = C;
+    RC(upload<float>(e, g->v, &n->gamma));
+    RC(upload<float>(e, b->v, &n->beta));
+    return 0;
+}
+
+static int make_packed(TmlEncoder* e, const float* w, int Co, int Ci, int mode, Packed* p) {
+    std::vector<uint16_t> h;
+    if (pack_conv3x3(w, Co, Ci, mode, h, &p->ntaps, p->dh, p->dw)) { set_error("pack mode %d", mode); return -21; }
+    return upload_bf16(e, h, &p->w);
+}
+
+static int make_conv3(TmlEncoder* e, const std::string& key, int Ci, int Co, int stride, Conv3* c) {
+    const HostTensor* w = find(e, key + ".weight", (size_t)Co * Ci * 9);
+    const HostTensor* b = find(e, key + ".bias", Co);
+    if (!w || !b) return -20;
+    c->ci = Ci; c->co = Co; c->stride = stride;
+    RC(make_packed(e, w->v.data(), Co, Ci, stride == 1 ? 0 : 2, &c->fwd));
+    if (stride == 1) RC(make_packed(e, w->v.data(), Co, Ci, 1, &c->bwd));
+    else for (int q = 0; q < 4; ++q) RC(make_packed(e, w->v.data(), Co, Ci, 3 + q, &c->bwd_par[q]));
+    RC(upload<float>(e, b->v, &c->bias));
+    return 0;
+}
+
+// W: [co][ci] row-major
+static int make_lin_from(TmlEncoder* e, const std::vector<float>& W, const std::vector<float>& bias, int Ci, int Co,
+                         Lin* l) {
+    l->ci = Ci; l->co = Co;
+    std::vector<uint16_t> f((size_t)Co * Ci), t((size_t)Ci * Co);
+    for (int o = 0; o < Co; ++o)
+        for (int i = 0; i < Ci; ++i) {
+            const uint16_t v = f2bf(W[(size_t)o * Ci + i]);
+            f[(size_t)o * Ci + i] = v;
+            t[(size_t)i * Co + o] = v;
+        }
+    RC(upload_bf16(e, f, &l->fwd));
+    RC(upload_bf16(e, t, &l->bwd));
+    RC(upload<float>(e, bias, &l->bias));
+    return 0;
+}
+
+static int make_resnet(TmlEncoder* e, const std::string& key, int Ci, int Co, Resnet* r) {
+    r->ci = Ci; r->co = Co;
+    RC(make_norm(e, key + ".norm1", Ci, &r->n1));
+    RC(make_conv3(e, key + ".conv1", Ci, Co, 1, &r->c1));
+    RC(make_norm(e, key + ".norm2", Co, &r->n2));
+    RC(make_conv3(e, key + ".conv2", Co, Co, 1, &r->c2));
+    r->has_sc = Ci != Co;
+    if (r->has_sc) {
+        const HostTensor* w = find(e, key + ".conv_shortcut.weight", (size_t)Co * Ci);
+        const HostTensor* b = find(e, key + ".conv_shortcut.bias", Co);
+        if (!w || !b) return -20;
+        RC(make_lin_from(e, w->v, b->v, Ci, Co, &r->sc));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout (what lives where in `saved`; how much scratch the walks need)
+// ------------------------------------------------------------------------------------------------
+static size_t act_bytes(int B, int h, int w, int c) { return (size_t)B * h * w * c * sizeof(bf16); }
+// partial sums written by a GEMM epilogue: one entry per (image, 128-row tile, group)
+static size_t fused_partial_bytes(int B, int h, int w) { return (size_t)B * gemm_gn_tiles_per_image(h, w) * 32 * 2 * sizeof(float); }
+// sized for the smallest channel count (largest chunk count) so one bound covers every layer
+static size_t gn_partial_bytes(int B, int hw) { return (size_t)B * gn_num_chunks(hw, 512) * 32 * 2 * sizeof(float); }
+
+static GnSaved alloc_gn(Arena& a, int B, int C) {
+    GnSaved g;
+    g.ss = a.alloc((size_t)B * C * sizeof(float2));
+    g.mr = a.alloc((size_t)B * 32 * sizeof(float2));
+    return g;
+}
+
+static int build_layout(TmlEncoder* e, int B, int H, int W) {
+    Layout& L = e->lay;
+    if (L.B == B && L.H == H && L.W == W && L.saved_bytes) return 0;
+    const TmlEncoderCfg& c = e->cfg;
+    const int nb = c.num_blocks;
+    const int down_factor = 1 << (nb - 1);
+    if (H % down_factor || W % down_factor) { set_error("H,W must be multiples of %d", down_factor); return -30; }
+    if ((W / down_factor) % 8) { set_error("W/%d must be a multiple of 8 (got W=%d)", down_factor, W); return -30; }
+    L = Layout();
+    L.B = B; L.H = H; L.W = W;
+    Arena S, WS;
+    int h = H, w = W;
+    L.x0 = S.alloc(act_bytes(B, h, w, c.block_out_channels[0]));
+    size_t cur = L.x0;
+    size_t ws_peak = 0;
+    auto resnet_ws = [&](int ci, int co, int hh, int ww) {
+        // forward: partial + a + a2 + sc ; backward: d_a2 + partial + mm + d_h1 + d_a1 + tmp
+        const size_t f = gn_partial_bytes(B, hh * ww) + act_bytes(B, hh, ww, ci) + 2 * act_bytes(B, hh, ww, co) + 4096;
+        const size_t b = 2 * act_bytes(B, hh, ww, co) + 2 * act_bytes(B, hh, ww, ci) + gn_partial_bytes(B, hh * ww) +
+                         (size_t)B * 32 * sizeof(float2) + 8192;
+        return f > b ? f : b;
+    };
+    int cin = c.block_out_channels[0];
+    for (int i = 0; i < nb; ++i) {
+        const int cout = c.block_out_channels[i];
+        for (int j = 0; j < c.layers_per_block; ++j) {
+            ResnetRec r;
+            r.h = h; r.w = w; r.x = cur;
+            r.g1 = alloc_gn(S, B, cin);
+            r.h1 = S.alloc(act_bytes(B, h, w, cout));
+            r.g2 = alloc_gn(S, B, cout);
+            r.out = S.alloc(act_bytes(B, h, w, cout));
+            ws_peak = std::max(ws_peak, resnet_ws(cin, cout, h, w));
+            L.res.push_back(r);
+            cur = r.out;
+            cin = cout;
+        }
+        if (i != nb - 1) {
+            DownRec d;
+            d.h = h; d.w = w; d.x = cur;
+            h /= 2; w /= 2;
+            d.out = S.alloc(act_bytes(B, h, w, cout));
+            L.down.push_back(d);
+            cur = d.out;
+        }
+    }
+    // mid block
+    for (int m = 0; m < 2; ++m) {
+        ResnetRec r;
+        r.h = h; r.w = w; r.x = cur;
+        r.g1 = alloc_gn(S, B, cin);
+        r.h1 = S.alloc(act_bytes(B, h, w, cin));
+        r.g2 = alloc_gn(S, B, cin);
+        r.out = S.alloc(act_bytes(B, h, w, cin));
+        ws_peak = std::max(ws_peak, resnet_ws(cin, cin, h, w));
+        L.res.push_back(r);
+        cur = r.out;
+        if (m == 0 && c.mid_block_add_attention) {
+            AttnRec a;
+            a.h = h; a.w = w; a.x = cur;
+            const size_t tok = (size_t)h * w;
+            a.g = alloc_gn(S, B, cin);
+            a.qkv = S.alloc((size_t)B * tok * 3 * cin * sizeof(bf16));
+            a.P = S.alloc((size_t)B * tok * tok * sizeof(bf16));
+            a.out = S.alloc(act_bytes(B, h, w, cin));
+            const size_t act = act_bytes(B, h, w, cin);
+            const size_t fwd_ws = gn_partial_bytes(B, (int)tok) + act /*t*/ + (size_t)B * tok * tok * 4 /*S*/ + act /*Vt*/ + act /*a*/ + 8192;
+            const size_t bwd_ws = 2 * act /*da, daT*/ + (size_t)B * tok * tok * 4 /*dP*/ + 3 * (size_t)B * tok * tok * 2 /*dS,dST,PT*/ +
+                                  2 * act /*Kt,Qt*/ + 3 * act /*dqkv*/ + act /*dt*/ + gn_partial_bytes(B, (int)tok) + 16384;
+            ws_peak = std::max(ws_peak, std::max(fwd_ws, bwd_ws));
+            L.attn = a;
+            cur = a.out;
+        }
+    }
+    L.gout = alloc_gn(S, B, cin);
+    L.xlast = cur;
+    L.hl = h; L.wl = w;
+    // final: partial + a (fwd); dm64 + d_a + partial + mm (bwd)
+    ws_peak = std::max(ws_peak, gn_partial_bytes(B, h * w) + 2 * act_bytes(B, h, w, cin) + act_bytes(B, h, w, 64) + 16384);
+    // two ping-pong gradient buffers of the largest activation
+    size_t gmax = 0;
+    {
+        int hh = H, ww = W;
+        for (int i = 0; i < nb; ++i) {
+            gmax = std::max(gmax, act_bytes(B, hh, ww, c.block_out_channels[i]));
+            if (i) gmax = std::max(gmax, act_bytes(B, hh, ww, c.block_out_channels[i - 1]));
+            if (i != nb - 1) { hh /= 2; ww /= 2; }
+        }
+    }
+    L.saved_bytes = S.peak + 256;
+    L.ws_bytes = ws_peak + 2 * (gmax + 256) + 3 * (fused_partial_bytes(B, H, W) + 256) + (64 << 10);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// op builders
+// ------------------------------------------------------------------------------------------------
+static GemmOp dense_conv_op(const char* name, const bf16* A, int B, int ih, int iw, int Ci, const Packed& pk, int N,
+                            int stride, int oh, int ow, const float* bias, const bf16* resid, bf16* D) {
+    GemmOp o;
+    o.name = name;
+    o.A = A; o.A_C = Ci; o.A_W = iw; o.A_H = ih; o.A_B = B;
+    o.A_sW = Ci; o.A_sH = (int64_t)iw * Ci; o.A_sB = (int64_t)ih * iw * Ci;
+    o.stride = stride; o.ntaps = pk.ntaps;
+    for (int t = 0; t < pk.ntaps; ++t) { o.dh[t] = pk.dh[t]; o.dw[t] = pk.dw[t]; }
+    o.OW = ow; o.OH = oh;
+    o.Bm = pk.w; o.N = N; o.B_sN = (int64_t)pk.ntaps * Ci; o.B_sBatch = 0;
+    o.bias = bias;
+    o.resid = resid; o.R_sW = N; o.R_sH = (int64_t)ow * N; o.R_sB = (int64_t)oh * ow * N;
+    o.D = D; o.D_sW = N; o.D_sH = (int64_t)ow * N; o.D_sB = (int64_t)oh * ow * N; o.D_sN = 1;
+    return o;
+}
+static GemmOp dense_lin_op(const char* name, const bf16* A, int B, int h, int w, int K, const bf16* Wm, int N,
+                           const float* bias, const bf16* resid, bf16* D) {
+    Packed pk;
+    pk.w = const_cast<bf16*>(Wm);
+    pk.ntaps = 1;
+    return dense_conv_op(name, A, B, h, w, K, pk, N, 1, h, w, bias, resid, D);
+}
+
+// test hook: copy every backward stage's output gradient into consecutive slots of a caller buffer
+inline char* g_dump_base = nullptr;
+inline size_t g_dump_slot = 0;
+inline int g_dump_slots = 0, g_dump_next = 0;
+inline void dump_grad(const void* p, size_t bytes, cudaStream_t st) {
+    if (!g_dump_base || g_dump_next >= g_dump_slots) return;
+    cudaMemcpyAsync(g_dump_base + (size_t)g_dump_next * g_dump_slot, p, bytes < g_dump_slot ? bytes : g_dump_slot,
+                    cudaMemcpyDeviceToDevice, st);
+    ++g_dump_next;
+}
+
+// Partial GroupNorm sums already produced by a GEMM epilogue (null = run the reduction kernel).
+struct Partials {
+    float* p = nullptr;
+    int nchunks = 0;
+};
+
+struct Run {
+    TmlEncoder* e;
+    char* saved;
+    char* ws;
+    Arena wsa;
+    cudaStream_t st;
+    int B;
+    float* statbuf[2] = {nullptr, nullptr};  // forward: ping-pong buffers for epilogue-fused GroupNorm statistics
+    Partials pending;                         // statistics of the current activation, if its producer fused them
+    template <typename T> T* S(size_t off) const { return reinterpret_cast<T*>(saved + off); }
+    template <typename T> T* Walloc(size_t bytes) { return reinterpret_cast<T*>(ws + wsa.alloc(bytes)); }
+};
+
+
+static int gn_forward(Run& r, const bf16* x, const Norm& n, const GnSaved& g, bf16* y, int hw, int silu,
+                      const Partials& pre = Partials()) {
+    const size_t m = r.wsa.mark();
+    const float* part = pre.p;
+    int nchunks = pre.nchunks;
+    if (!part) {
+        float* own = r.Walloc<float>(gn_partial_bytes(r.B, hw));
+        launch_gn_stats(x, own, r.B, hw, n.C, r.st);
+        part = own;
+        nchunks = gn_num_chunks(hw, n.C);
+    }
+    launch_gn_finalize(part, n.gamma, n.beta, r.S<float2>(g.ss), r.S<float2>(g.mr), r.B, hw, n.C, r.e->cfg.norm_eps,
+                       nchunks, r.st);
+    launch_gn_apply(x, r.S<float2>(g.ss), y, r.B, hw, n.C, silu, r.st);
+    r.wsa.reset(m);
+    return 0;
+}
+static int gn_backward(Run& r, const bf16* x, const bf16* dy, const Norm& n, const GnSaved& g, const bf16* resid,
+                       bf16* dx, int hw, int silu, const Partials& pre = Partials()) {
+    const size_t m = r.wsa.mark();
+    const float* part = pre.p;
+    int nchunks = pre.nchunks;
+    if (!part) {
+        float* own = r.Walloc<float>(gn_partial_bytes(r.B, hw));
+        launch_gn_bwd_partial(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), n.gamma, own, r.B, hw, n.C, silu, r.st);
+        part = own;
+        nchunks = gn_num_chunks(hw, n.C);
+    }
+    float2* mm = r.Walloc<float2>((size_t)r.B * 32 * sizeof(float2));
+    launch_gn_bwd_finalize(part, mm, r.B, hw, n.C, nchunks, r.st);
+    launch_gn_bwd_apply(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), mm, n.gamma, resid, dx, r.B, hw, n.C, silu, r.st);
+    r.wsa.reset(m);
+    return 0;
+}
+// Ask a GEMM to also reduce (sum, sumsq) of its output per (image, tile, group).
+static bool env_off(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] == '1';
+}
+static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
+    static const bool off = env_off("TML_NO_FUSE_STATS");     // tuning switch
+    if (off || gemm_get_impl() != 0) return Partials();  // the SIMT debug kernel has no fused reductions
+    o.gn_mode = 1;
+    o.gn_partial = buf;
+    Partials p;
+    p.p = buf;
+    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    return p;
+}
+// Ask a dgrad GEMM to also reduce the GroupNorm-backward sums of the norm whose output it differentiates.
+static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
+                            int oh, int ow) {
+    static const bool off = env_off("TML_NO_FUSE_GNBWD");     // tuning switch
+    // Measured on B200: for K = 9*128 the main loop of a tile is too short to hide this epilogue (exp + rcp per
+    // element and an extra read of x), so 128-channel layers keep the standalone reduction kernel.
+    static const int min_k = getenv("TML_GNBWD_MIN_K") ? atoi(getenv("TML_GNBWD_MIN_K")) : 2000;
+    if (off || gemm_get_impl() != 0 || o.ntaps * o.A_C < min_k) return Partials();
+    o.gn_mode = 2;
+    o.gn_partial = buf;
+    o.gn_x = x;
+    o.gn_ss = r.S<float2>(g.ss);
+    o.gn_mr = r.S<float2>(g.mr);
+    o.gn_gamma = n.gamma;
+    o.gn_silu = silu;
+    Partials p;
+    p.p = buf;
+    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    return p;
+}
+
+static int resnet_forward(Run& r, const Resnet& p, const ResnetRec& rec) {
+    const int B = r.B, h = rec.h, w = rec.w, hw = h * w;
+    const int ns = r.e->num_sms;
+    const bf16* x = r.S<bf16>(rec.x);
+    const size_t m = r.wsa.mark();
+    bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
+    RC(gn_forward(r, x, p.n1, rec.g1, a, hw, 1, r.pending));
+    bf16* h1 = r.S<bf16>(rec.h1);
+    GemmOp c1 = dense_conv_op("resnet.conv1", a, B, h, w, p.ci, p.c1.fwd, p.co, 1, h, w, p.c1.bias, nullptr, h1);
+    const Partials s1 = fuse_stats(c1, r.statbuf[0], h, w);     // statistics of h1 for norm2, from the epilogue
+    RC(gemm_launch(c1, ns, r.st));
+    bf16* a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+    RC(gn_forward(r, h1, p.n2, rec.g2, a2, hw, 1, s1));
+    const bf16* resid = x;
+    if (p.has_sc) {
+        bf16* sc = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+        RC(gemm_launch(dense_lin_op("resnet.shortcut", x, B, h, w, p.ci, p.sc.fwd, p.co, p.sc.bias, nullptr, sc), ns, r.st));
+        resid = sc;
+    }
+    GemmOp c2 = dense_conv_op("resnet.conv2", a2, B, h, w, p.co, p.c2.fwd, p.co, 1, h, w, p.c2.bias, resid, r.S<bf16>(rec.out));
+    r.pending = fuse_stats(c2, r.statbuf[1], h, w);             // statistics of the block output for the next norm
+    RC(gemm_launch(c2, ns, r.st));
+    r.wsa.reset(m);
+    return 0;
+}
+
+// dout -> dx (both dense [B,h,w,*]); dx must not alias dout
+static int resnet_backward(Run& r, const Resnet& p, const ResnetRec& rec, const bf16* dout, bf16* dx) {
+    const int B = r.B, h = rec.h, w = rec.w, hw = h * w;
+    const int ns = r.e->num_sms;
+    const size_t m = r.wsa.mark();
+    float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
+    bf16* d_a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+    GemmOp g2 = dense_conv_op("resnet.conv2.dgrad", dout, B, h, w, p.co, p.c2.bwd, p.co, 1, h, w, nullptr, nullptr, d_a2);
+    const Partials p2 = fuse_gn_bwd(r, g2, r.S<bf16>(rec.h1), p.n2, rec.g2, 1, pbuf, h, w);
+    RC(gemm_launch(g2, ns, r.st));
+    bf16* d_h1 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+    RC(gn_backward(r, r.S<bf16>(rec.h1), d_a2, p.n2, rec.g2, nullptr, d_h1, hw, 1, p2));
+    bf16* d_a1 = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
+    GemmOp g1 = dense_conv_op("resnet.conv1.dgrad", d_h1, B, h, w, p.co, p.c1.bwd, p.ci, 1, h, w, nullptr, nullptr, d_a1);
+    const Partials p1 = fuse_gn_bwd(r, g1, r.S<bf16>(rec.x), p.n1, rec.g1, 1, pbuf, h, w);
+    RC(gemm_launch(g1, ns, r.st));
+    if (p.has_sc) {
+        bf16* tmp = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
+        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, nullptr, tmp, hw, 1, p1));
+        RC(gemm_launch(dense_lin_op("resnet.shortcut.dgrad", dout, B, h, w, p.co, p.sc.bwd, p.ci, nullptr, tmp, dx), ns, r.st));
+    } else {
+        RC(gn_backward(r, r.S<bf16>(rec.x), d_a1, p.n1, rec.g1, dout, dx, hw, 1, p1));
+    }
+    r.wsa.reset(m);
+    return 0;
+}
+
+static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
+    const int B = r.B, h = rec.h, w = rec.w, C = p.C, ns = r.e->num_sms;
+    const int tok = h * w;
+    const bf16* x = r.S<bf16>(rec.x);
+    const size_t m = r.wsa.mark();
+    bf16* t = r.Walloc<bf16>(act_bytes(B, h, w, C));
+    RC(gn_forward(r, x, p.gn, rec.g, t, tok, 0, r.pending));
+    bf16* qkv = r.S<bf16>(rec.qkv);
+    RC(gemm_launch(dense_lin_op("attn.qkv", t, B, h, w, C, p.qkv.fwd, 3 * C, p.qkv.bias, nullptr, qkv), ns, r.st));
+    // S = QK^T / sqrt(C)   (fp32, [B][tok][tok])
+    float* S = r.Walloc<float>((size_t)B * tok * tok * sizeof(float));
+    {
+        GemmOp o;
+        o.name = "attn.qk";
+        o.A = qkv; o.A_C = C; o.A_W = w; o.A_H = h; o.A_B = B;
+        o.A_sW = 3 * C; o.A_sH = (int64_t)w * 3 * C; o.A_sB = (int64_t)tok * 3 * C;
+        o.OW = w; o.OH = h;
+        o.Bm = qkv + C; o.N = tok; o.B_sN = 3 * C; o.B_sBatch = (int64_t)tok * 3 * C;
+        o.alpha = 1.0f / sqrtf((float)C);
+        o.D = S; o.out_fp32 = 1; o.D_sW = tok; o.D_sH = (int64_t)w * tok; o.D_sB = (int64_t)tok * tok; o.D_sN = 1;
+        RC(gemm_launch(o, ns, r.st));
+    }
+    bf16* P = r.S<bf16>(rec.P);
+    launch_softmax_rows(S, P, (long long)B * tok, tok, r.st);
+    bf16* Vt = r.Walloc<bf16>(act_bytes(B, h, w, C));  // [B][C][tok]
+    launch_transpose(qkv + 2 * C, Vt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
+    bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, C));
+    {
+        GemmOp o;
+        o.name = "attn.pv";
+        o.A = P; o.A_C = tok; o.A_W = w; o.A_H = h; o.A_B = B;
+        o.A_sW = tok; o.A_sH = (int64_t)w * tok; o.A_sB = (int64_t)tok * tok;
+        o.OW = w; o.OH = h;
+        o.Bm = Vt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
+        o.D = a; o.D_sW = C; o.D_sH = (int64_t)w * C; o.D_sB = (int64_t)tok * C; o.D_sN = 1;
+        RC(gemm_launch(o, ns, r.st));
+    }
+    GemmOp oo = dense_lin_op("attn.out", a, B, h, w, C, p.out.fwd, C, p.out.bias, x, r.S<bf16>(rec.out));
+    r.pending = fuse_stats(oo, r.statbuf[1], h, w);
+    RC(gemm_launch(oo, ns, r.st));
+    r.wsa.reset(m);
+    return 0;
+}
+
+static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* dout, bf16* dx) {
+    const int B = r.B, h = rec.h, w = rec.w, C = p.C, ns = r.e->num_sms;
+    const int tok = h * w;
+    const float scale = 1.0f / sqrtf((float)C);
+    const bf16* qkv = r.S<bf16>(rec.qkv);
+    const bf16* P = r.S<bf16>(rec.P);
+    const size_t m = r.wsa.mark();
+    const size_t act = act_bytes(B, h, w, C);
+    const size_t tt = (size_t)B * tok * tok;
+    bf16* da = r.Walloc<bf16>(act);
+    RC(gemm_launch(dense_lin_op("attn.out.dgrad", dout, B, h, w, C, p.out.bwd, C, nullptr, nullptr, da), ns, r.st));
+    bf16* daT = r.Walloc<bf16>(act);
+    launch_transpose(da, daT, B, tok, C, C, (long long)tok * C, tok, (long long)C * tok, r.st);
+    float* dP = r.Walloc<float>(tt * sizeof(float));
+    {
+        GemmOp o;  // dP = da V^T
+        o.name = "attn.dP";
+        o.A = da; o.A_C = C; o.A_W = w; o.A_H = h; o.A_B = B;
+        o.A_sW = C; o.A_sH = (int64_t)w * C; o.A_sB = (int64_t)tok * C;
+        o.OW = w; o.OH = h;
+        o.Bm = qkv + 2 * C; o.N = tok; o.B_sN = 3 * C; o.B_sBatch = (int64_t)tok * 3 * C;
+        o.D = dP; o.out_fp32 = 1; o.D_sW = tok; o.D_sH = (int64_t)w * tok; o.D_sB = (int64_t)tok * tok; o.D_sN = 1;
+        RC(gemm_launch(o, ns, r.st));
+    }
+    bf16* dS = r.Walloc<bf16>(tt * 2);
+    launch_softmax_bwd_rows(P, dP, dS, scale, (long long)B * tok, tok, r.st);
+    bf16* dST = r.Walloc<bf16>(tt * 2);
+    launch_transpose(dS, dST, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
+    bf16* PT = r.Walloc<bf16>(tt * 2);
+    launch_transpose(P, PT, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
+    bf16* Kt = r.Walloc<bf16>(act);
+    launch_transpose(qkv + C, Kt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
+    bf16* Qt = r.Walloc<bf16>(act);
+    launch_transpose(qkv, Qt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
+    bf16* dqkv = r.Walloc<bf16>(3 * act);
+    auto tok_gemm = [&](const char* name, const bf16* A, const bf16* Bt, bf16* D) {
+        GemmOp o;  // D[tok, C] (row stride 3C) = A[tok, tok'] * Bt[C, tok']^T
+        o.name = name;
+        o.A = A; o.A_C = tok; o.A_W = w; o.A_H = h; o.A_B = B;
+        o.A_sW = tok; o.A_sH = (int64_t)w * tok; o.A_sB = (int64_t)tok * tok;
+        o.OW = w; o.OH = h;
+        o.Bm = Bt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
+        o.D = D; o.D_sW = 3 * C; o.D_sH = (int64_t)w * 3 * C; o.D_sB = (int64_t)tok * 3 * C; o.D_sN = 1;
+        return gemm_launch(o, ns, r.st);
+    };
+    RC(tok_gemm("attn.dQ", dS, Kt, dqkv));
+    RC(tok_gemm("attn.dK", dST, Qt, dqkv + C));
+    RC(tok_gemm("attn.dV", PT, daT, dqkv + 2 * C));
+    bf16* dt = r.Walloc<bf16>(act);
+    GemmOp gq = dense_lin_op("attn.qkv.dgrad", dqkv, B, h, w, 3 * C, p.qkv.bwd, C, nullptr, nullptr, dt);
+    float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
+    const Partials pq = fuse_gn_bwd(r, gq, r.S<bf16>(rec.x), p.gn, rec.g, 0, pbuf, h, w);
+    RC(gemm_launch(gq, ns, r.st));
+    RC(gn_backward(r, r.S<bf16>(rec.x), dt, p.gn, rec.g, dout, dx, tok, 0, pq));
+    r.wsa.reset(m);
+    return 0;
+}
+

@@ -103,3 +103,45 @@ def universal_step_(delta: torch.Tensor, grad: torch.Tensor, source: Optional[to
                                               source.data_ptr() if source is not None else None, eps, step, lo, hi,
                                               delta.numel(), ws.data_ptr(), _stream()))
     return delta
+
+
+def posterior_sample(moments: torch.Tensor, noise: Optional[torch.Tensor]) -> torch.Tensor:
+    """latent_dist.sample() with explicit noise / .mode() when noise is None (main.py:191)."""
+    _chk(moments, "moments")
+    B, c2, h, w = moments.shape
+    z = torch.empty((B, c2 // 2, h, w), dtype=torch.float32, device=moments.device)
+    if noise is not None:
+        _chk(noise, "noise")
+    _lib.check(_lib.load().tml_posterior_sample(moments.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                                z.data_ptr(), B, h, w, _stream()))
+    return z
+
+
+def posterior_sample_backward(moments: torch.Tensor, noise: Optional[torch.Tensor], dz: torch.Tensor) -> torch.Tensor:
+    _chk(moments, "moments"), _chk(dz, "dz")
+    B, c2, h, w = moments.shape
+    dm = torch.empty_like(moments)
+    _lib.check(_lib.load().tml_posterior_sample_backward(moments.data_ptr(),
+                                                         noise.data_ptr() if noise is not None else None,
+                                                         dz.data_ptr(), dm.data_ptr(), B, h, w, _stream()))
+    return dm
+
+
+def image_loss(out: torch.Tensor, target: torch.Tensor, source: Optional[torch.Tensor], rec_lambda: float = 1.0,
+               pert_lambda: float = 1.0, need_grad: bool = True):
+    """Per-image rec = ||out - target||_2 (main.py:160), pert = mse(out, source) (losses.py:39-41) and the
+    gradient of rec_lambda*rec + pert_lambda*pert w.r.t. out.  Returns (rec [B], pert [B], dout or None)."""
+    _chk(out, "out"), _chk(target, "target")
+    assert out.shape == target.shape
+    if source is not None:
+        _chk(source, "source")
+    B = out.shape[0]
+    rec = torch.empty(B, dtype=torch.float32, device=out.device)
+    pert = torch.zeros(B, dtype=torch.float32, device=out.device)
+    dout = torch.empty_like(out) if need_grad else None
+    lib = _lib.load()
+    ws = torch.empty(lib.tml_image_loss_workspace(B), dtype=torch.uint8, device=out.device)
+    _lib.check(lib.tml_image_loss(out.data_ptr(), target.data_ptr(), source.data_ptr() if source is not None else None,
+                                  B, out[0].numel(), rec_lambda, pert_lambda, rec.data_ptr(), pert.data_ptr(),
+                                  dout.data_ptr() if dout is not None else None, ws.data_ptr(), _stream()))
+    return rec, pert, dout

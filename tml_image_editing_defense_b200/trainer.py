@@ -70,8 +70,10 @@ class Trainer:
     def compute_grad(self, cur_image: torch.Tensor, prompt, source_image: torch.Tensor, target_image,
                      target_latent: torch.Tensor, noise: Optional[List[torch.Tensor]] = None,
                      grad_out: Optional[torch.Tensor] = None, beta: float = 0.0):
-        if not self.cfg.apply_loss_on_latents or self.cfg.apply_loss_on_images:
-            raise NotImplementedError("image-space loss needs vae.decode (SURVEY 8f n1); set apply_loss_on_latents")
+        if self.cfg.apply_loss_on_images:
+            return self._compute_grad_images(cur_image, source_image, target_image, noise, grad_out, beta)
+        if not self.cfg.apply_loss_on_latents:
+            raise ValueError("Please specify whether to apply loss on images or latents")  # main.py:164
         B = cur_image.shape[0]
         lat_shape = (B, 4, cur_image.shape[2] // 8, cur_image.shape[3] // 8)
         eps = self._pick_noise(noise, lat_shape)
@@ -103,6 +105,31 @@ class Trainer:
         loss_dict = {"rec_loss": rec, "pert_loss": 0.0, "per_image": losses}
         return grad, rec * self.cfg.rec_loss_lambda, None, loss_dict
 
+    def _compute_grad_images(self, cur_image, source_image, target_image, noise, grad_out, beta):
+        """The reference's default: rec_loss on decoded images (main.py:156-160) + perturbation_loss (:167-169)."""
+        if target_image is None:
+            raise ValueError("apply_loss_on_images needs target_image")
+        B = cur_image.shape[0]
+        lat_shape = (B, 4, cur_image.shape[2] // 8, cur_image.shape[3] // 8)
+        eps = self._pick_noise(noise, lat_shape)
+        grad = grad_out if grad_out is not None else torch.empty_like(cur_image)
+        rec = torch.empty(B, dtype=torch.float32, device=self.device)
+        pert = torch.empty(B, dtype=torch.float32, device=self.device)
+        outs = []
+        mb = self.micro_batch
+        c = self.cfg
+        for s in range(0, B, mb):
+            e = min(B, s + mb)
+            tgt = target_image[s:e] if target_image.shape[0] == B else target_image.expand(e - s, -1, -1, -1).contiguous()
+            src = source_image[s:e] if c.perturbation_loss_lambda > 0 else None
+            _, r_, p_, img = self.vae.attack_grad_images(cur_image[s:e], tgt, src, eps[s:e], c.rec_loss_lambda,
+                                                         c.perturbation_loss_lambda, grad_out=grad[s:e], beta=beta)
+            rec[s:e] = r_
+            pert[s:e] = p_
+            outs.append(img)
+        loss = c.rec_loss_lambda * rec.mean() + c.perturbation_loss_lambda * pert.mean()
+        return grad, loss, torch.cat(outs), {"rec_loss": rec.mean(), "pert_loss": pert.mean(), "per_image": rec}
+
     # ------------------------------------------------------------------ main.py:248-276
     def perturbation_step(self, X_adv: torch.Tensor, grad: torch.Tensor, X: torch.Tensor,
                           X_mask: Optional[torch.Tensor] = None, grad_scale: float = 1.0) -> torch.Tensor:
@@ -123,6 +150,8 @@ class Trainer:
         c = self.cfg
         source_image = source_image.to(self.device, self.dtype).contiguous()
         B = source_image.shape[0]
+        if target_image is not None:
+            target_image = target_image.to(self.device, self.dtype).contiguous()
         if target_latent is None:
             if target_image is None:
                 raise ValueError("need target_image or target_latent")
@@ -140,7 +169,7 @@ class Trainer:
             step_losses = []
             for i in range(c.grad_reps):  # main.py:88-99; accumulation happens in the dgrad kernel (beta=1)
                 _, loss, _, _ = self.compute_grad(cur_image=X_adv, prompt=None, source_image=source_image,
-                                                  target_image=None, target_latent=target_latent, noise=self.noises,
+                                                  target_image=target_image, target_latent=target_latent, noise=self.noises,
                                                   grad_out=grad, beta=0.0 if i == 0 else 1.0)
                 step_losses.append(loss)
             # main.py:102 takes the mean over reps; sign() and the L2 normalisation are invariant to

@@ -84,6 +84,29 @@ class _EncodeFn(torch.autograd.Function):
         return dx, None
 
 
+class _DecodeFn(torch.autograd.Function):
+    """image = decoder(post_quant_conv(z)); backward = gradient w.r.t. z only."""
+
+    @staticmethod
+    def forward(ctx, z: torch.Tensor, vae: "AutoencoderKL"):
+        image, saved = vae._decode_raw(z, keep=z.requires_grad)
+        ctx.vae = vae
+        ctx.saved_buf = saved
+        ctx.shape = tuple(z.shape)
+        return image
+
+    @staticmethod
+    def backward(ctx, dimage: torch.Tensor):
+        dz = ctx.vae._decode_backward_raw(dimage.contiguous().float(), ctx.saved_buf, ctx.shape)
+        ctx.saved_buf = None
+        return dz, None
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+
 class AutoencoderKL:
     """B200-native encoder behind the reference's ``vae`` interface."""
 
@@ -113,13 +136,16 @@ class AutoencoderKL:
         # streams (Trainer), each with its own workspace / saved-state buffer
         self._ws: Dict[int, torch.Tensor] = {}
         self._scratch_saved: Dict[int, torch.Tensor] = {}
+        self._scratch_saved_dec: Dict[int, torch.Tensor] = {}
         self._finalized = False
+        self.has_decoder = False
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
-        """Accepts a diffusers AutoencoderKL state dict; decoder / post_quant keys are ignored."""
+        """Accepts a diffusers AutoencoderKL state dict.  The decoder ("decoder.*", "post_quant_conv.*") is
+        optional: without it ``decode`` raises."""
         for k, v in sd.items():
-            if not (k.startswith("encoder.") or k.startswith("quant_conv.")):
+            if not k.startswith(("encoder.", "quant_conv.", "decoder.", "post_quant_conv.")):
                 continue
             t = v.detach()
             if t.dtype not in _DTYPES:
@@ -131,6 +157,7 @@ class AutoencoderKL:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.tml_encoder_finalize(self._h, None))
         self._finalized = True
+        self.has_decoder = any(k.startswith("decoder.") for k in sd)
         return self
 
     @classmethod
@@ -156,9 +183,12 @@ class AutoencoderKL:
             pass
 
     # ------------------------------------------------------------------ raw entry points
-    def _buffers(self, B: int, H: int, W: int):
+    def _buffers(self, B: int, H: int, W: int, decoder: bool = False):
+        """(workspace tensor of the current stream, bytes of saved state).  H, W: image size (encoder) or
+        latent size (decoder).  Encoder and decoder share the per-stream workspace (stream-ordered use)."""
         ws_b, sv_b = C.c_size_t(), C.c_size_t()
-        _lib.check(self._lib.tml_encoder_query(self._h, B, H, W, C.byref(ws_b), C.byref(sv_b)))
+        q = self._lib.tml_decoder_query if decoder else self._lib.tml_encoder_query
+        _lib.check(q(self._h, B, H, W, C.byref(ws_b), C.byref(sv_b)))
         key = torch.cuda.current_stream().cuda_stream
         ws = self._ws.get(key)
         if ws is None or ws.numel() < ws_b.value:
@@ -217,9 +247,62 @@ class AutoencoderKL:
         out = AutoencoderKLOutput(DiagonalGaussianDistribution(self.moments(x)))
         return out if return_dict else (out.latent_dist,)
 
-    def decode(self, z, *a, **k):
-        raise NotImplementedError(
-            "vae.decode is outside the B200 hot path of this round (SURVEY 8f n1); use apply_loss_on_latents")
+    # ------------------------------------------------------------------ decoder (main.py:156)
+    def _decode_raw(self, z: torch.Tensor, keep: bool):
+        if not self.has_decoder:
+            raise _lib.TmlError("decoder weights were not loaded (state dict had no 'decoder.*' keys)")
+        if not z.is_cuda:
+            raise _lib.TmlError("decode() needs a CUDA tensor; the B200 path has no CPU fallback")
+        z = z.detach().to(torch.float32).contiguous()
+        B, Cz, h, w = z.shape
+        ws, sv_bytes = self._buffers(B, h, w, decoder=True)
+        if keep:
+            saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
+        else:
+            key = torch.cuda.current_stream().cuda_stream
+            saved = self._scratch_saved_dec.get(key)
+            if saved is None or saved.numel() < sv_bytes:
+                self._scratch_saved_dec.pop(key, None)
+                saved = None
+                saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
+                self._scratch_saved_dec[key] = saved
+        f = 2 ** (len(self.config.block_out_channels) - 1)
+        image = torch.empty((B, 3, h * f, w * f), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.tml_decoder_forward(self._h, z.data_ptr(), B, h, w, image.data_ptr(), saved.data_ptr(),
+                                                 ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return image, saved
+
+    def _decode_backward_raw(self, dimage: torch.Tensor, saved: torch.Tensor, zshape) -> torch.Tensor:
+        B, Cz, h, w = zshape
+        ws, _ = self._buffers(B, h, w, decoder=True)
+        dz = torch.empty(zshape, dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.tml_decoder_backward(self._h, dimage.data_ptr(), B, h, w, saved.data_ptr(), dz.data_ptr(),
+                                                  ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return dz
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
+        """``vae.decode(z).sample`` (main.py:156), differentiable w.r.t. z."""
+        if torch.is_grad_enabled() and z.requires_grad:
+            img = _DecodeFn.apply(z, self)
+        else:
+            img = self._decode_raw(z, keep=False)[0]
+        return DecoderOutput(sample=img) if return_dict else (img,)
+
+    def attack_grad_images(self, x_adv: torch.Tensor, target_image: torch.Tensor, source_image: Optional[torch.Tensor],
+                           noise: Optional[torch.Tensor], rec_lambda: float = 1.0, pert_lambda: float = 1.0,
+                           grad_out: Optional[torch.Tensor] = None, beta: float = 0.0):
+        """compute_grad of the reference with its default image-space losses (main.py:144-177, UNet removed):
+        encode -> sample -> decode -> rec_lambda*||out-target||_2 + pert_lambda*mse(out, source) -> backward
+        through decoder and encoder.  Returns (grad, rec [B], pert [B], output_image)."""
+        from . import ops
+        moments, saved_e = self._forward_raw(x_adv, keep=False)
+        z = ops.posterior_sample(moments, noise)
+        img, saved_d = self._decode_raw(z, keep=False)
+        rec, pert, dimg = ops.image_loss(img, target_image, source_image, rec_lambda, pert_lambda)
+        dz = self._decode_backward_raw(dimg, saved_d, tuple(z.shape))
+        dm = ops.posterior_sample_backward(moments, noise, dz)
+        g = self._backward_raw(dm, saved_e, tuple(x_adv.shape), out=grad_out, beta=beta)
+        return g, rec, pert, img
 
     # ------------------------------------------------------------------ fused attack gradient (no autograd)
     def attack_grad(self, x_adv: torch.Tensor, target: torch.Tensor, noise: Optional[torch.Tensor], kind: int = 0,

@@ -11,7 +11,7 @@ import torch
 from .vae import EncoderConfig
 
 
-def encoder_param_shapes(cfg: EncoderConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+def encoder_param_shapes(cfg: EncoderConfig, include_decoder: bool = False) -> List[Tuple[str, Tuple[int, ...]]]:
     ch = cfg.block_out_channels
     out: List[Tuple[str, Tuple[int, ...]]] = []
 
@@ -53,16 +53,36 @@ def encoder_param_shapes(cfg: EncoderConfig) -> List[Tuple[str, Tuple[int, ...]]
     norm("encoder.conv_norm_out", cin)
     conv("encoder.conv_out", 2 * cfg.latent_channels, cin, 3)
     conv("quant_conv", 2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+    if include_decoder:
+        rev = list(reversed(ch))
+        conv("post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+        conv("decoder.conv_in", rev[0], cfg.latent_channels, 3)
+        resnet("decoder.mid_block.resnets.0", rev[0], rev[0])
+        if cfg.mid_block_add_attention:
+            a = "decoder.mid_block.attentions.0"
+            norm(a + ".group_norm", rev[0])
+            for n in ("to_q", "to_k", "to_v", "to_out.0"):
+                lin(f"{a}.{n}", rev[0], rev[0])
+        resnet("decoder.mid_block.resnets.1", rev[0], rev[0])
+        cin = rev[0]
+        for i, cout in enumerate(rev):
+            for j in range(cfg.layers_per_block + 1):
+                resnet(f"decoder.up_blocks.{i}.resnets.{j}", cin, cout)
+                cin = cout
+            if i != len(rev) - 1:
+                conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
+        norm("decoder.conv_norm_out", cin)
+        conv("decoder.conv_out", cfg.out_channels, cin, 3)
     return out
 
 
-def random_init_state_dict(cfg: EncoderConfig = None, seed: int = 0) -> Dict[str, torch.Tensor]:
+def random_init_state_dict(cfg: EncoderConfig = None, seed: int = 0, include_decoder: bool = False) -> Dict[str, torch.Tensor]:
     """torch.nn default initialisation (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for conv / linear weights
     and biases, GroupNorm gamma = 1, beta = 0), reproducible from `seed`."""
     cfg = cfg or EncoderConfig()
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    shapes = encoder_param_shapes(cfg)
+    shapes = encoder_param_shapes(cfg, include_decoder)
     fan_in = {}
     for name, shape in shapes:
         if name.endswith(".weight") and len(shape) > 1:
