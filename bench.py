@@ -176,11 +176,13 @@ def run_ours(args):
     lib = _lib.load()
 
     res, B, mb = args.res, args.batch, args.micro_batch
-    weights = random_init_state_dict(seed=0)
+    weights = random_init_state_dict(seed=0, include_decoder=args.loss == "images")
     vae = AutoencoderKL(device=str(dev)).load_state_dict(weights)
     del weights
     cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
-                      n_optimization_steps=1, device=str(dev))
+                      n_optimization_steps=1, device=str(dev), apply_loss_on_images=args.loss == "images",
+                      apply_loss_on_latents=args.loss != "images",
+                      perturbation_loss_lambda=1.0 if args.loss == "images" else 0.0)
     tr = Trainer(cfg, vae, micro_batch=mb, num_streams=args.streams)
 
     xh, th, nh = synth_inputs(B, res, 1000 + rank, pin=True)
@@ -190,8 +192,12 @@ def run_ours(args):
     grad = torch.empty_like(x)
     tr.noises = [noise]
 
+    tgt_img = None
+    if args.loss == "images":   # the reference's default losses on decoded images (main.py:156-171), UNet removed
+        tgt_img = (torch.rand((B, 3, res, res), generator=torch.Generator().manual_seed(7)) * 2 - 1).to(dev)
+
     def step_device():
-        tr.compute_grad(x_adv, None, x, None, tgt, tr.noises, grad_out=grad, beta=0.0)
+        tr.compute_grad(x_adv, None, x, tgt_img, tgt, tr.noises, grad_out=grad, beta=0.0)
         tr.perturbation_step(x_adv, grad, x, None)
 
     def barrier():
@@ -384,10 +390,14 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (configs[1]: 64)")
     ap.add_argument("--micro_batch", type=int, default=16, help="images per encoder pass")
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the micro-batches alternate on")
+    ap.add_argument("--loss", default="latents", choices=["latents", "images"],
+                    help="latents: the BASELINE encoder attack; images: + decoder and image-space losses (needs --quick)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--gemm_table", action="store_true", help="print per-shape GEMM times (stderr)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()
+    if args.loss == "images" and not args.quick:
+        raise SystemExit("--loss images is an informational mode: use it with --quick")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
