@@ -195,6 +195,21 @@ def main():
             out_d[f"loss_kind{kind}"] = ls.numpy()
             out_d["z"] = z.numpy()
         np.savez_compressed(out / f"encoder_{res}.npz", **out_d)
+    # ---------------------------------------------------------------- decoder regression fixture
+    from oracle.decoder_oracle import make_vae_oracle, autoencoder_attack_grad
+    vae = make_vae_oracle(0)
+    perturb_affine_params(vae, 1234)
+    assert sum(p.numel() for p in vae.parameters()) == 83_653_863
+    g = torch.Generator().manual_seed(300)
+    x = torch.rand((1, 3, 64, 64), generator=g) * 2 - 1
+    tgt_img = torch.rand((1, 3, 64, 64), generator=g) * 2 - 1
+    noise = torch.randn((1, 4, 8, 8), generator=g)
+    z = torch.randn((1, 4, 8, 8), generator=g)
+    with torch.no_grad():
+        img = vae.decode(z)
+    gr, ls, outimg = autoencoder_attack_grad(vae, x, tgt_img, x, noise, 1.0, 1.0)
+    np.savez_compressed(out / "decoder_64.npz", z=z.numpy(), image=img.numpy(), x=x.numpy(), target_image=tgt_img.numpy(),
+                        noise=noise.numpy(), grad=gr.numpy(), loss=ls.numpy(), output_image=outimg.numpy())
     print("golden fixtures written to", out)
 
 

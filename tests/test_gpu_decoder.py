@@ -104,3 +104,15 @@ def test_trainer_image_loss_mode(dev, models):
     xa = tr.run(x, target_image=tgt)
     assert float((xa - x).abs().max()) <= 0.1 + 1e-6
     assert tr.loss_history[-1] < tr.loss_history[0]
+
+
+def test_decoder_vs_golden_fixture(golden_dir, dev, models):
+    _, vae = models
+    d = np.load(golden_dir / "decoder_64.npz")
+    img = vae.decode(torch.from_numpy(d["z"]).to(dev)).sample
+    assert rel_err(img.cpu(), torch.from_numpy(d["image"])) < 4e-2
+    x = torch.from_numpy(d["x"]).to(dev)
+    gg, rec, pert, out = vae.attack_grad_images(x, torch.from_numpy(d["target_image"]).to(dev), x,
+                                                torch.from_numpy(d["noise"]).to(dev), 1.0, 1.0)
+    assert cosine(gg.cpu(), torch.from_numpy(d["grad"])) >= 0.998
+    np.testing.assert_allclose((rec + pert).cpu().numpy(), d["loss"], rtol=3e-2)

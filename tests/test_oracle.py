@@ -108,3 +108,28 @@ def test_encoder_attack_loss_decreases():
     po.encoder_attack(m, x, tgt, noise, 6, 32 / 255, 4 / 255, -1, 1, kind=0,
                       record=lambda xa, gr, ls: rec.append(float(ls.sum())))
     assert rec[-1] < rec[0]
+
+
+def test_decoder_param_count_and_keys():
+    from oracle.decoder_oracle import OracleVAE
+    m = OracleVAE(EncoderConfig())
+    assert sum(p.numel() for p in m.parameters()) == 83_653_863          # the known SD VAE size
+    assert sum(p.numel() for p in m.decoder.parameters()) + sum(p.numel() for p in m.post_quant_conv.parameters()) == 49_490_199
+    keys = set(m.state_dict().keys())
+    for k in ["post_quant_conv.weight", "decoder.conv_in.weight", "decoder.mid_block.attentions.0.to_out.0.bias",
+              "decoder.up_blocks.0.resnets.2.conv2.weight", "decoder.up_blocks.0.upsamplers.0.conv.weight",
+              "decoder.up_blocks.2.resnets.0.conv_shortcut.weight", "decoder.up_blocks.3.resnets.2.norm2.bias",
+              "decoder.conv_norm_out.weight", "decoder.conv_out.bias"]:
+        assert k in keys, k
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in keys
+
+
+def test_decoder_oracle_regression_64(golden_dir):
+    from oracle.decoder_oracle import make_vae_oracle
+    from oracle.encoder_oracle import perturb_affine_params
+    d = np.load(golden_dir / "decoder_64.npz")
+    m = make_vae_oracle(0)
+    perturb_affine_params(m, 1234)
+    with torch.no_grad():
+        img = m.decode(torch.from_numpy(d["z"]))
+    np.testing.assert_allclose(img.numpy(), d["image"], rtol=1e-4, atol=1e-5)
