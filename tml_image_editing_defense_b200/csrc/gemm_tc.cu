@@ -469,7 +469,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // broadcast through a shuffle so the compiler knows the value is warp-uniform (keeps it in a uniform register)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     uint32_t crank = 0u;
     if constexpr (PAIR) crank = cluster_ctarank();
     volatile int* hw = p.hang_where;
@@ -584,7 +585,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0 && crank == 0) {   // pair mode: only the leader CTA issues
+        // The whole warp runs this loop convergently with warp-uniform values (descriptors, stage indices live in
+        // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.  Issuing
+        // from a divergent `if (lane == 0)` region costs ~16 instructions of R2UR/ELECT shuffling per MMA, which
+        // made the N = 128 layers issue-bound (64 tensor cycles per MMA).
+        if (crank == 0) {   // pair mode: only the leader CTA issues
             const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kUmmaM : kUmmaM, p.BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -603,54 +608,68 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             mbar_wait(&full_bar[stage], phase, hw, htag + 5);
                             tc_fence_after();
                             const uint64_t b_desc = umma_desc_sw128(smem_u32(ring + size_t(stage) * p.stage_bytes));
-                            for (int sub = 0; sub < p.mt; ++sub) {
-                                // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
-                                const uint32_t row0 = uint32_t((sub + p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
-                                const uint64_t a_desc = umma_desc_sw128(h_addr + row0 * 128u);
-                                if constexpr (PAIR) {
-#pragma unroll
-                                    for (int k = 0; k < kBlockK / 16; ++k)
-                                        umma_bf16_2sm(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k),
-                                                      b_desc + uint64_t(2 * k), idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < kBlockK / 16; ++k)
-                                        umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
-                                                  idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                            // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
+                            const uint32_t row0 = uint32_t((p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
+                            const uint64_t a_desc0 = umma_desc_sw128(h_addr + row0 * 128u);
+                            const uint32_t first = (ch | tap) != 0 ? 1u : 0u;
+                            if (elect_one()) {
+                                for (int sub = 0; sub < p.mt; ++sub) {
+                                    // next output row = next halo row: +kHaloW rows of 128 B = +kHaloW*8 in the addr>>4 field
+                                    const uint64_t a_desc = a_desc0 + uint64_t(sub * kHaloW * 8);
+                                    const uint32_t d = d_tmem + uint32_t(sub * p.BN);
+                                    if constexpr (PAIR) {
+                                        umma_bf16_2sm(d, a_desc, b_desc, idesc, first);
+                                        umma_bf16_2sm(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                        umma_bf16_2sm(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                        umma_bf16_2sm(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                    } else {
+                                        umma_bf16(d, a_desc, b_desc, idesc, first);
+                                        umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                        umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                        umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                    }
+                                }
+                                if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                                // halo tile free once its nine taps have retired
+                                if (tap == p.ntaps - 1) {
+                                    if constexpr (PAIR) umma_commit_2sm(&hempty_bar[hs], 3); else umma_commit(&hempty_bar[hs]);
                                 }
                             }
-                            if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                            __syncwarp();
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
-                        // halo tile free once its nine taps have retired
-                        if constexpr (PAIR) umma_commit_2sm(&hempty_bar[hs], 3); else umma_commit(&hempty_bar[hs]);
                         hs ^= 1;
                         if (hs == 0) hphase ^= 1u;
                     }
-                    if constexpr (PAIR) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
-                    continue;
-                }
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + size_t(stage) * p.stage_bytes);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
-                    for (int sub = 0; sub < p.mt; ++sub) {
-                        uint64_t a_desc = umma_desc_sw128(a_addr + sub * kATileBytes + uint32_t(p.dbg_shift) * 128u);
-                        if (p.dbg_bo) a_desc |= uint64_t(((a_addr + sub * kATileBytes + uint32_t(p.dbg_shift) * 128u) >> 7) & 7u) << 49;
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
-                            umma_bf16(d_tmem + uint32_t(sub * p.BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                } else {
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase, hw, htag + 5);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + size_t(stage) * p.stage_bytes);
+                        const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
+                        uint64_t a_desc0 = umma_desc_sw128(a_addr + uint32_t(p.dbg_shift) * 128u);
+                        if (p.dbg_bo) a_desc0 |= uint64_t(((a_addr + uint32_t(p.dbg_shift) * 128u) >> 7) & 7u) << 49;
+                        const uint32_t first = kb != 0 ? 1u : 0u;
+                        if (elect_one()) {
+                            for (int sub = 0; sub < p.mt; ++sub) {
+                                const uint64_t a_desc = a_desc0 + uint64_t(sub * (kATileBytes >> 4));
+                                const uint32_t d = d_tmem + uint32_t(sub * p.BN);
+                                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
+                                umma_bf16(d, a_desc, b_desc, idesc, first);
+                                umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                            }
+                            umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
                         }
+                        __syncwarp();
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+                if (elect_one()) {   // accumulator complete -> epilogue
+                    if constexpr (PAIR) umma_commit_2sm(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
