@@ -287,6 +287,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// 256-bit global accesses (sm_100: LDG/STG.256): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
 // Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel): alpha, bias,
@@ -315,19 +326,25 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
     if (p.dbg_no_epi == 2) return;
     if (p.D_sN == 1 && n0 + NC <= p.n_store && p.beta == 0.f) {
         if (p.out_fp32) {
-            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n0);
+            float* dp = reinterpret_cast<float*>(p.D) + d_off + n0;
 #pragma unroll
-            for (int j = 0; j < NC / 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < NC / 8; ++j)
+                st_global_256(dp + 8 * j,
+                              make_uint4(__float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]), __float_as_uint(f[8 * j + 3])),
+                              make_uint4(__float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]), __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7])));
         } else {
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n0);
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n0;
+            uint4 o[NC / 8];
 #pragma unroll
             for (int j = 0; j < NC / 8; ++j) {
-                const uint4 o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                dp[j] = o;
-                f[8 * j + 0] = bf16_lo(o.x); f[8 * j + 1] = bf16_hi(o.x); f[8 * j + 2] = bf16_lo(o.y); f[8 * j + 3] = bf16_hi(o.y);
-                f[8 * j + 4] = bf16_lo(o.z); f[8 * j + 5] = bf16_hi(o.z); f[8 * j + 6] = bf16_lo(o.w); f[8 * j + 7] = bf16_hi(o.w);
+                o[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                  pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                f[8 * j + 0] = bf16_lo(o[j].x); f[8 * j + 1] = bf16_hi(o[j].x); f[8 * j + 2] = bf16_lo(o[j].y); f[8 * j + 3] = bf16_hi(o[j].y);
+                f[8 * j + 4] = bf16_lo(o[j].z); f[8 * j + 5] = bf16_hi(o[j].z); f[8 * j + 6] = bf16_lo(o[j].w); f[8 * j + 7] = bf16_hi(o[j].w);
             }
+            // full 32-byte sectors per lane (a 16-byte store would leave every sector half written)
+#pragma unroll
+            for (int j = 0; j < NC / 16; ++j) st_global_256(dp + 16 * j, o[2 * j], o[2 * j + 1]);
         }
     } else {
         // strided / partially stored columns (e.g. fp32 NCHW moments, transposed operands)
@@ -713,12 +730,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 if (valid && ch_lo < ch_hi) {
                     const int n0 = nt * p.BN + ch_lo * 32;
                     if (ld_res) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(p.resid + r_off + n0) + j);
+                        ld_global_nc_256(p.resid + r_off + n0, rres[0], rres[1]);
+                        ld_global_nc_256(p.resid + r_off + n0 + 16, rres[2], rres[3]);
                     }
                     if (ld_x) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xreg[j] = __ldg(reinterpret_cast<const uint4*>(p.gn_x + d_off + n0) + j);
+                        ld_global_nc_256(p.gn_x + d_off + n0, xreg[0], xreg[1]);
+                        ld_global_nc_256(p.gn_x + d_off + n0 + 16, xreg[2], xreg[3]);
                     }
                 }
                 if (p.gn_mode != 0) named_bar_sync(1, kEpiThreads);  // previous readers of the scratch are done
@@ -751,12 +768,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     if (valid && ch + 1 < ch_hi) {
                         const int n1 = nt * p.BN + c + 32;
                         if (ld_res) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.resid + r_off + n1) + j);
+                            ld_global_nc_256(p.resid + r_off + n1, rnext[0], rnext[1]);
+                            ld_global_nc_256(p.resid + r_off + n1 + 16, rnext[2], rnext[3]);
                         }
                         if (ld_x) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) xnext[j] = __ldg(reinterpret_cast<const uint4*>(p.gn_x + d_off + n1) + j);
+                            ld_global_nc_256(p.gn_x + d_off + n1, xnext[0], xnext[1]);
+                            ld_global_nc_256(p.gn_x + d_off + n1 + 16, xnext[2], xnext[3]);
                         }
                     }
                     tmem_ld_wait();
