@@ -380,6 +380,63 @@ def run_ours(args):
     return 0
 
 
+def run_diffusion(args):
+    """BASELINE configs[4], informational: backprop through the img2img DDIM steps of the SD-1.5 UNet at 512^2 with
+    activation checkpointing.  Encoder / decoder / PGD update are this repo's kernels; the UNet is the PyTorch
+    library module (unet_torch.py) with random-init weights."""
+    from tml_image_editing_defense_b200 import _lib, ops
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.diffusion import DiffusionAttack
+    from tml_image_editing_defense_b200.schedulers import DDIMScheduler
+    from tml_image_editing_defense_b200.unet_torch import UNet2DConditionModel
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    from tml_image_editing_defense_b200.weights import random_init_state_dict
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    B, res = args.batch, args.res
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(random_init_state_dict(seed=0, include_decoder=True))
+    with torch.device(dev):
+        torch.manual_seed(0)
+        unet = UNet2DConditionModel().to(torch.bfloat16).requires_grad_(False)
+    cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
+                      device=str(dev), apply_loss_on_images=True, apply_loss_on_latents=False,
+                      perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=4, limit_timesteps=False)
+    da = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=True, unet_dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
+    tgt = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
+    pe = torch.randn((2, 77, 768), generator=g).to(dev)
+    nz = [torch.randn((B, 4, res // 8, res // 8), generator=g).to(dev)]
+    x_adv = x.clone()
+
+    def step():
+        grad, loss, _, _ = da.compute_grad(x_adv, pe, x, tgt, None, nz)
+        ops.pgd_step_linf_(x_adv, grad.contiguous(), x, EPS, STEP, LO, HI)
+        return loss
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    c0 = _lib.launch_counts()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    c1 = _lib.launch_counts()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"mode": "diffusion", "metric": "image-PGD-iters/sec", "value": B * args.steps / (ms / 1e3),
+                      "ms_per_step": ms / args.steps, "steps": args.steps, "loss": float(loss),
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                      "gpu_launches": (c1[0] - c0[0]) + (c1[1] - c0[1]),
+                      "config": {"workload": f"BASELINE configs[4]: diffusion attack, 4 DDIM steps of the SD-1.5 UNet (PyTorch "
+                                             f"library module, bf16, checkpointed) + encoder/decoder/update on this repo's "
+                                             f"kernels, batch {B} x {res}^2, CFG, image-space losses, random-init weights"}}),
+          flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -392,10 +449,14 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the micro-batches alternate on")
     ap.add_argument("--loss", default="latents", choices=["latents", "images"],
                     help="latents: the BASELINE encoder attack; images: + decoder and image-space losses (needs --quick)")
+    ap.add_argument("--mode", default="encoder", choices=["encoder", "diffusion"],
+                    help="diffusion: BASELINE configs[4] (4 DDIM steps of the SD-1.5 UNet, checkpointed; informational)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--gemm_table", action="store_true", help="print per-shape GEMM times (stderr)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()
+    if args.mode == "diffusion":
+        return run_diffusion(args)
     if args.loss == "images" and not args.quick:
         raise SystemExit("--loss images is an informational mode: use it with --quick")
     if args.impl == "reference":

@@ -116,3 +116,33 @@ def test_decoder_vs_golden_fixture(golden_dir, dev, models):
                                                 torch.from_numpy(d["noise"]).to(dev), 1.0, 1.0)
     assert cosine(gg.cpu(), torch.from_numpy(d["grad"])) >= 0.998
     np.testing.assert_allclose((rec + pert).cpu().numpy(), d["loss"], rtol=3e-2)
+
+
+def test_diffusion_attack_hybrid_vs_oracle(dev, models):
+    """encode (our kernels) -> add_noise -> UNet steps with CFG (PyTorch library module, bf16,
+    checkpointed) -> decode (our kernels) -> image losses -> gradient, against the all-fp32 oracle pipeline."""
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.diffusion import DiffusionAttack
+    from tml_image_editing_defense_b200.schedulers import DDIMScheduler
+    from tml_image_editing_defense_b200.unet_torch import UNet2DConditionModel, tiny_unet_config
+    oracle, vae = models
+    torch.manual_seed(11)
+    unet = UNet2DConditionModel(tiny_unet_config()).requires_grad_(False).to(dev)
+    cfg = TrainConfig(norm_type="linf", override_from_norm_type=False, device=str(dev), apply_loss_on_images=True,
+                      apply_loss_on_latents=False, perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=4)
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).to(dev)
+    tgt = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).to(dev)
+    pe = torch.randn(2, 7, 32, generator=g).to(dev)
+    nz = [torch.randn(2, 4, 8, 8, generator=g).to(dev)]
+    od = oracle.to(dev)
+    ref = DiffusionAttack(cfg, od, unet, DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+    g_ref, l_ref, img_ref, _ = ref.compute_grad(x, pe, x, tgt, None, nz)
+    oracle.to("cpu")
+    ours = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=True, unet_dtype=torch.bfloat16)
+    gg, l, img, _ = ours.compute_grad(x, pe, x, tgt, None, nz)
+    c = cosine(gg, g_ref)
+    print("diffusion attack gradient cosine", c)
+    assert c >= 0.99
+    assert abs(float(l) - float(l_ref)) / float(l_ref) < 0.03
+    assert rel_err(img, img_ref) < 0.08

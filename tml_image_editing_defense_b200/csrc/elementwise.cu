@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restr
     const float2 m_hi = __ldg(&mr[(size_t)b * 32 + (oct * 8 + 4) / cpg]);
     float a_lo = 0.f, b_lo = 0.f, a_hi = 0.f, b_hi = 0.f;
     const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
-    constexpr int U = 2;  // pixels per iteration: 4 independent 16-byte loads in flight per thread
+    constexpr int U = 4;  // pixels per iteration: 8 independent 16-byte loads in flight per thread
     for (int p = p0 + pl; p < p1; p += PL * U) {
         uint4 ux[U], ud[U];
 #pragma unroll
