@@ -1,6 +1,6 @@
 """GPU diagnostic: layer-by-layer comparison of the CUDA path against the oracle (run on a B200).
 
-    python tools/gpu_check.py [--res 64] [--batch 2] [--impl tc|simt|both]
+    python tests/gpu_check.py [--res 64] [--batch 2] [--impl tc|simt|both]
 
 Prints one line per check and never stops at the first failure; meant for gpurun round trips where
 one call must localise a bug.  Not part of the product path."""

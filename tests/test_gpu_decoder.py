@@ -31,7 +31,7 @@ def models(dev):
 
 
 def test_decoder_layerwise_parity_64(dev):
-    from tools.gpu_check_decoder import run_decoder
+    from tests.gpu_check_decoder import run_decoder
     assert run_decoder(dev, 64, 2)
 
 

@@ -30,7 +30,7 @@ def models(dev):
 
 
 def test_layerwise_parity_64(dev):
-    from tools.gpu_check import run_encoder
+    from tests.gpu_check import run_encoder
     from tml_image_editing_defense_b200 import _lib
     _lib.load().tml_debug_set_gemm_impl(0)
     assert run_encoder(dev, 64, 2, 0, "tc")

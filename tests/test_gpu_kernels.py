@@ -130,7 +130,7 @@ def test_latent_loss_vs_autograd(dev, kind, use_noise):
 
 # ------------------------------------------------------------------ K1-K5: tcgen05 implicit GEMM
 def test_tcgen05_gemm_suite(dev, lib):
-    from tools.gpu_check import run_gemm_suite
+    from tests.gpu_check import run_gemm_suite
     lib.tml_debug_set_gemm_impl(0)
     before = np.zeros(2, np.int64)
     lib.tml_launch_counts(before.ctypes.data_as(C.POINTER(C.c_int64)))
@@ -179,7 +179,7 @@ def test_tcgen05_gemm_suite_cta_pairs(dev):
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
     env = dict(os.environ, TML_PAIR="1")
-    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_check.py"), "--gemm-only", "--impl", "tc"], env=env, capture_output=True,
+    r = subprocess.run([sys.executable, str(root / "tests" / "gpu_check.py"), "--gemm-only", "--impl", "tc"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "ALL OK" in r.stdout
