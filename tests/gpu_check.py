@@ -160,6 +160,12 @@ def run_gemm_suite(lib, dev):
         ("halo pair 512->512 4x128 2 n-tiles", dict(B=2, H=4, W=128, Cin=512, N=512, mode=0, resid=True, bias=True, gn=1)),
         ("halo pair N=16 dgrad 8x256", dict(B=2, H=8, W=256, Cin=128, N=16, mode=1)),
         ("halo multi-wave 128->128 128x128 B=4", dict(B=4, H=128, W=128, Cin=128, N=128, mode=0, resid=True)),
+        # operand-swapped kernel (N = 128 output channels, rows of 256 pixels)
+        ("swap 128->128 4x256 bias +stats", dict(B=2, H=4, W=256, Cin=128, N=128, mode=0, bias=True, gn=1)),
+        ("swap dgrad 128->128 3x512 resid", dict(B=1, H=3, W=512, Cin=128, N=128, mode=1, resid=True)),
+        ("swap dgrad 256->128 2x256", dict(B=2, H=2, W=256, Cin=256, N=128, mode=1)),
+        ("swap 64->128 1x256", dict(B=1, H=1, W=256, Cin=64, N=128, mode=0, bias=True)),
+        ("swap multi-wave 128->128 64x256 B=4 all", dict(B=4, H=64, W=256, Cin=128, N=128, mode=0, bias=True, resid=True, gn=1)),
     ]
     for name, kw in cases:
         try:

@@ -1,4 +1,4 @@
-// Bandwidth-bound kernels of the PGD hot path: conv_in (K=27) forward / input gradient, GroupNorm
+// Bandwidth-bound kernels of the PGD hot path: conv_in im2col (hi/lo bf16 split of the fp32 image), GroupNorm
 // (+SiLU) forward / backward, softmax forward / backward, transposes, posterior sample + latent loss
 // gradient, and the fused PGD updates.  All reductions are two-stage with a fixed order, so results
 // are bitwise reproducible run to run and independent of how images are sharded over GPUs.
@@ -94,66 +94,47 @@ __device__ __forceinline__ float block_max(float v, float* red /*[33]*/) {
 }
 
 // ================================================================================================
-// conv_in forward: fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,C0]      (diffusers
-// encoder.conv_in, reached from main.py:191).  K = 27 is far too thin for tensor cores: this is a
-// direct convolution whose cost is writing the bf16 output once.
-// Block: 256 threads = 16 channel octets x 16 pixel groups of 4 -> 64 pixels of one image row.
+// conv_in forward, step 1: fp32 NCHW [B,3,H,W] -> im2col rows bf16 [B*H*W][64]   (diffusers
+// encoder.conv_in, reached from main.py:191).  Row layout, k = ci*9 + r*3 + s:
+//   [0,27)  hi = bf16(x)          [27,54)  lo = bf16(x - hi)          [54,64)  zero
+// The tensor-core GEMM that follows multiplies both halves by the same bf16 weights, so the image enters with
+// ~16 mantissa bits: a PGD step of 2/255 on a pixel near 1.0 is one bf16 ulp and would vanish with hi alone.
+// One row is one 128-byte swizzle row of the GEMM's A operand (K = 64).
+// Block: 64 pixels of one image row; 4 threads per pixel, 32 bytes each.
 // ================================================================================================
-template <int C0>
-__global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_kc,
-                                                          const float* __restrict__ bias, bf16* __restrict__ y, int H,
-                                                          int W) {
-    static_assert(C0 == 128, "conv_in kernel is specialised for 128 output channels");
-    __shared__ __align__(16) float sw[27 * C0];
-    __shared__ float sb[C0];
-    __shared__ float sx[3][3][66];
+__global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H,
+                                                             int W) {
+    __shared__ uint16_t sp[2][9][66];  // [hi|lo][ci*3 + r][column]
     const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < 27 * C0; i += 256) sw[i] = w_kc[i];
-    for (int i = threadIdx.x; i < C0; i += 256) sb[i] = bias[i];
-    for (int i = threadIdx.x; i < 3 * 3 * 66; i += 256) {
-        const int col = i % 66, r = (i / 66) % 3, ci = i / (66 * 3);
+    for (int i = threadIdx.x; i < 9 * 66; i += 256) {
+        const int col = i % 66, cr = i / 66, ci = cr / 3, r = cr % 3;
         const int ih = h + r - 1, iw = w0 + col - 1;
         float v = 0.f;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((size_t)(b * 3 + ci) * H + ih) * W + iw];
-        sx[ci][r][col] = v;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(&x[((size_t)(b * 3 + ci) * H + ih) * W + iw]);
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        sp[0][cr][col] = __bfloat16_as_ushort(hi);
+        sp[1][cr][col] = __bfloat16_as_ushort(lo);
     }
     __syncthreads();
-    const int oct = threadIdx.x & 15, pg = threadIdx.x >> 4;
-    const int co0 = oct * 8;
-    float acc[4][8];
+    const int p = threadIdx.x >> 2, q = threadIdx.x & 3;
+    if (w0 + p >= W) return;
+    auto elem = [&](int k) -> uint32_t {
+        if (k >= 54) return 0u;
+        const int part = k >= 27 ? 1 : 0, kk = k - 27 * part;
+        return sp[part][kk / 3][p + kk % 3];
+    };
+    uint32_t o[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[p][j] = sb[co0 + j];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int k = ci * 9 + r * 3 + s;
-                const float4 wa = *reinterpret_cast<const float4*>(&sw[k * C0 + co0]);
-                const float4 wb = *reinterpret_cast<const float4*>(&sw[k * C0 + co0 + 4]);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const float xv = sx[ci][r][pg * 4 + p + s];
-                    acc[p][0] = fmaf(xv, wa.x, acc[p][0]); acc[p][1] = fmaf(xv, wa.y, acc[p][1]);
-                    acc[p][2] = fmaf(xv, wa.z, acc[p][2]); acc[p][3] = fmaf(xv, wa.w, acc[p][3]);
-                    acc[p][4] = fmaf(xv, wb.x, acc[p][4]); acc[p][5] = fmaf(xv, wb.y, acc[p][5]);
-                    acc[p][6] = fmaf(xv, wb.z, acc[p][6]); acc[p][7] = fmaf(xv, wb.w, acc[p][7]);
-                }
-            }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int w = w0 + pg * 4 + p;
-        if (w < W) *reinterpret_cast<uint4*>(y + (((size_t)b * H + h) * W + w) * C0 + co0) = pack8(acc[p]);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = elem(q * 16 + 2 * j) | (elem(q * 16 + 2 * j + 1) << 16);
+    uint4* dst = reinterpret_cast<uint4*>(a + (((size_t)b * H + h) * W + w0 + p) * 64 + q * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf16* y, int B, int H, int W, int C0,
-                        cudaStream_t s) {
+void launch_conv_in_im2col(const float* x, bf16* a, int B, int H, int W, cudaStream_t s) {
     dim3 grid((W + 63) / 64, H, B);
-    conv_in_fwd_kernel<128><<<grid, 256, 0, s>>>(x, w_kc, bias, y, H, W);
+    conv_in_im2col_kernel<<<grid, 256, 0, s>>>(x, a, H, W);
     COUNT_LAUNCH();
 }
 

@@ -95,15 +95,15 @@ int tml_encoder_finalize(TmlEncoder* e, void* stream) {
     CUDA_OK(cudaSetDevice(e->device));
     const TmlEncoderCfg& c = e->cfg;
     const int C0 = c.block_out_channels[0];
-    {   // conv_in: [C0][3][3][3] -> [27][C0] fp32
+    {   // conv_in forward as a K=64 GEMM over im2col rows [hi(27) | lo(27) | 0(10)]: both halves see the same weights
+        if (c.in_channels != 3) { set_error("in_channels must be 3 (got %d)", c.in_channels); return -22; }
         const HostTensor* w = find(e, "encoder.conv_in.weight", (size_t)C0 * 27);
         const HostTensor* b = find(e, "encoder.conv_in.bias", C0);
         if (!w || !b) return -20;
-        std::vector<float> kc((size_t)27 * C0);
+        std::vector<float> w64((size_t)C0 * 64, 0.f);
         for (int co = 0; co < C0; ++co)
-            for (int k = 0; k < 27; ++k) kc[(size_t)k * C0 + co] = w->v[(size_t)co * 27 + k];
-        RC(upload<float>(e, kc, &e->conv_in_w));
-        RC(upload<float>(e, b->v, &e->conv_in_b));
+            for (int k = 0; k < 27; ++k) w64[(size_t)co * 64 + k] = w64[(size_t)co * 64 + 27 + k] = w->v[(size_t)co * 27 + k];
+        RC(make_lin_from(e, w64, b->v, 64, C0, &e->conv_in_fwd));
         // input gradient runs on the tensor cores: N = 3 padded to 16 (UMMA needs N % 16 == 0 at M = 128)
         std::vector<float> w16((size_t)C0 * 16 * 9, 0.f);
         for (int co = 0; co < C0; ++co)
@@ -212,7 +212,16 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
     const int C0 = e->cfg.block_out_channels[0];
     r.statbuf[0] = r.Walloc<float>(fused_partial_bytes(B, H, W));
     r.statbuf[1] = r.Walloc<float>(fused_partial_bytes(B, H, W));
-    launch_conv_in_fwd(x, e->conv_in_w, e->conv_in_b, r.S<bf16>(L.x0), B, H, W, C0, r.st);
+    {   // conv_in: im2col (hi/lo bf16 split of the fp32 image) + K=64 GEMM with the GroupNorm statistics fused
+        const size_t m = r.wsa.mark();
+        bf16* cols = r.Walloc<bf16>(act_bytes(B, H, W, 64));
+        launch_conv_in_im2col(x, cols, B, H, W, r.st);
+        GemmOp ci = dense_lin_op("conv_in", cols, B, H, W, 64, e->conv_in_fwd.fwd, C0, e->conv_in_fwd.bias, nullptr,
+                                 r.S<bf16>(L.x0));
+        r.pending = fuse_stats(ci, r.statbuf[1], H, W);
+        RC(gemm_launch(ci, e->num_sms, r.st));
+        r.wsa.reset(m);
+    }
     size_t ri = 0, di = 0;
     for (int i = 0; i < e->cfg.num_blocks; ++i) {
         for (int j = 0; j < e->cfg.layers_per_block; ++j, ++ri) RC(resnet_forward(r, e->resnets[ri], L.res[ri]));

@@ -837,6 +837,239 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// "Swapped" 3x3 stride-1 convolution for exactly 128 output channels on wide rows (OW % 256 == 0).
+//
+// tcgen05.mma at N = 128 tops out ~27 % below N = 256 (measured MMA-only ceilings 1160 vs 1590 TFLOP/s), and the
+// 128-channel layers at full resolution are a third of all GEMM time.  N is the weight dimension in the kernel
+// above, so here the operands trade places:  D^T[channel][pixel] = W[channel][k] * X[pixel][k]^T  with
+//   A (M = 128)  = one (tap, 64-channel chunk) slice of the packed weights          -- a ring of 16 KB stages
+//   B (N = 256)  = 256 consecutive pixels of ONE input row, 64 channels              -- a ring of 258-pixel rows
+// A tile is 256 pixels of one output row.  Each input row (y-1, y, y+1) x chunk is one ring slot of 258 pixels
+// (the tile plus one halo pixel each side, zero-filled by TMA outside the image); the three horizontal taps read
+// it through descriptors whose start is shifted by 0 / 128 / 256 bytes (same mechanism as halo mode above).
+// The accumulator is [128 lanes = channels][256 columns = pixels], double buffered (2 x 256 TMEM columns).
+// Epilogue: thread = channel, registers = 32 consecutive pixels; a warp's store of one pixel is 32 channels =
+// 64 contiguous bytes (two full sectors).  GroupNorm statistics are per channel = per thread, so the fused
+// reduction is a private accumulation plus two shuffles per group: no shared memory, no named barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSwRowPx = 258;
+constexpr int kSwRowBytes = 33 * 1024;        // 258 * 128 B = 33024, rounded up to the 1 KB swizzle atom
+constexpr int kSwRowSlots = 4;
+constexpr int kSwWStages = 5;
+constexpr int kSwWBytes = 128 * kBlockK * 2;  // 16 KB: 128 output channels x 64 input channels
+constexpr int kSwSmem = 1024 + kSwRowSlots * kSwRowBytes + kSwWStages * kSwWBytes + 256;
+static_assert(kSwSmem <= kMaxSmem, "swapped-conv shared memory");
+
+struct SwParams {
+    int H, W, nimg, kchunks;
+    int tap_of[3][3];            // packed-weight tap index of (row dh + 1, column dw + 1)
+    const float* bias;           // [128] or null
+    const __nv_bfloat16* resid;  // dense NHWC [nimg][H][W][128] or null
+    __nv_bfloat16* D;            // dense NHWC [nimg][H][W][128]
+    int gn_mode;                 // 0 or 1
+    float* gn_partial;           // [nimg][H * W/128][32][2]
+    volatile int* hang_where;
+    int dbg_no_epi, dbg_mma_only;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapRow,
+                       const __grid_constant__ CUtensorMap mapTail, const SwParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* rows = smem;
+    uint8_t* wring = rows + size_t(kSwRowSlots) * kSwRowBytes;
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + size_t(kSwWStages) * kSwWBytes);   // [8]
+    uint64_t* wempty = wfull + 8;     // [8]
+    uint64_t* rfull = wempty + 8;     // [4]
+    uint64_t* rempty = rfull + 4;     // [4]
+    uint64_t* tfull = rempty + 4;     // [2]
+    uint64_t* tempty = tfull + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapRow);
+        tma_prefetch_desc(&mapTail);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kSwWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < kSwRowSlots; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiThreads); }
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    volatile int* hw = p.hang_where;
+
+    const int tiles_x = p.W >> 8;
+    const int total_tiles = p.nimg * p.H * tiles_x;
+
+    if (warp == 0) {
+        // ===================================================================== weight producer
+        if (lane == 0) {
+            int ws = 0;
+            uint32_t wphase = 0;
+            bool first_pass = true;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+                for (int ch = 0; ch < p.kchunks; ++ch)
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) {
+                            mbar_wait(&wempty[ws], wphase ^ 1u, hw, 201);
+                            if (p.dbg_mma_only && !first_pass) {
+                                mbar_arrive(&wfull[ws]);
+                            } else {
+                                mbar_arrive_expect_tx(&wfull[ws], uint32_t(kSwWBytes));
+                                tma_load_3d(wring + size_t(ws) * kSwWBytes, &mapW, &wfull[ws],
+                                            (p.tap_of[r][c] * p.kchunks + ch) * kBlockK, 0, 0);
+                            }
+                            if (++ws == kSwWStages) { ws = 0; wphase ^= 1u; first_pass = false; }
+                        }
+        }
+    } else if (warp == 3) {
+        // ===================================================================== input-row producer
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t rphase = 0;
+            bool first_pass = true;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int xh = tile % tiles_x;
+                const int rem = tile / tiles_x;
+                const int y = rem % p.H, img = rem / p.H;
+                const int x0 = xh << 8;
+                for (int ch = 0; ch < p.kchunks; ++ch)
+                    for (int r = 0; r < 3; ++r) {
+                        mbar_wait(&rempty[rs], rphase ^ 1u, hw, 202);
+                        if (p.dbg_mma_only && !first_pass) {
+                            mbar_arrive(&rfull[rs]);
+                        } else {
+                            uint8_t* dst = rows + size_t(rs) * kSwRowBytes;
+                            mbar_arrive_expect_tx(&rfull[rs], uint32_t(kSwRowPx) * 128u);
+                            // pixels x0-1 .. x0+254, then x0+255 .. x0+256 (a TMA box is at most 256 wide); rows or
+                            // pixels outside the image arrive as zeros (= the convolution padding)
+                            tma_load_4d(dst, &mapRow, &rfull[rs], ch * kBlockK, x0 - 1, y + r - 1, img);
+                            tma_load_4d(dst + 256 * 128, &mapTail, &rfull[rs], ch * kBlockK, x0 + 255, y + r - 1, img);
+                        }
+                        if (++rs == kSwRowSlots) { rs = 0; rphase ^= 1u; first_pass = false; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (convergent warp)
+        const uint32_t idesc = umma_idesc_bf16(kUmmaM, 256);
+        int ws = 0, rs = 0, acc = 0;
+        uint32_t wphase = 0, rphase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u, hw, 203);
+            tc_fence_after();
+            const uint32_t d = tmem_base + uint32_t(acc * 256);
+            for (int ch = 0; ch < p.kchunks; ++ch)
+                for (int r = 0; r < 3; ++r) {
+                    mbar_wait(&rfull[rs], rphase, hw, 204);
+                    tc_fence_after();
+                    const uint32_t raddr = smem_u32(rows + size_t(rs) * kSwRowBytes);
+                    for (int c = 0; c < 3; ++c) {
+                        mbar_wait(&wfull[ws], wphase, hw, 205);
+                        tc_fence_after();
+                        const uint64_t a_desc = umma_desc_sw128(smem_u32(wring + size_t(ws) * kSwWBytes));
+                        // operand rows = 256 consecutive pixels of the slot starting at pixel c (= dw + 1)
+                        const uint64_t b_desc = umma_desc_sw128(raddr + uint32_t(c) * 128u);
+                        const uint32_t first = (ch | r | c) != 0 ? 1u : 0u;
+                        if (elect_one()) {
+                            umma_bf16(d, a_desc, b_desc, idesc, first);
+                            umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                            umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                            umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                            umma_commit(&wempty[ws]);
+                            if (c == 2) umma_commit(&rempty[rs]);
+                        }
+                        __syncwarp();
+                        if (++ws == kSwWStages) { ws = 0; wphase ^= 1u; }
+                    }
+                    if (++rs == kSwRowSlots) { rs = 0; rphase ^= 1u; }
+                }
+            if (elect_one()) umma_commit(&tfull[acc]);
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (8 warps)
+        // warp e: TMEM lane quadrant e % 4 (output channels 32q .. 32q+31), pixel half e / 4 (128 of the 256 pixels)
+        const int e = warp - 4;
+        const int q = e & 3, half = e >> 2;
+        const int chn = q * 32 + lane;
+        const float bias_c = p.bias != nullptr ? __ldg(p.bias + chn) : 0.f;
+        const int tiles128 = p.W >> 7;   // 128-pixel segments per row: the granularity of the GroupNorm partials
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int xh = tile % tiles_x;
+            const int rem = tile / tiles_x;
+            const int y = rem % p.H, img = rem / p.H;
+            const size_t off = (((size_t)img * p.H + y) * p.W + (xh << 8) + (half << 7)) * 128 + chn;
+            mbar_wait(&tfull[acc], acc_phase, hw, 206);
+            tc_fence_after();
+            if (p.dbg_no_epi != 1) {
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + half * 128);
+                __nv_bfloat16* dp = p.D + off;
+                const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.resid) + off;
+                float s = 0.f, ss = 0.f;
+                for (int ck = 0; ck < 4; ++ck) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + uint32_t(ck * 32), v);
+                    unsigned short rr[32];
+                    if (p.resid != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rr[j] = __ldg(rp + (size_t)(ck * 32 + j) * 128);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = __uint_as_float(v[j]) + bias_c;
+                        if (p.resid != nullptr) f += __uint_as_float(uint32_t(rr[j]) << 16);
+                        const __nv_bfloat16 b = __float2bfloat16_rn(f);
+                        dp[(size_t)(ck * 32 + j) * 128] = b;
+                        const float fr = __bfloat162float(b);   // statistics of the values as stored
+                        s += fr;
+                        ss = fmaf(fr, fr, ss);
+                    }
+                }
+                if (p.gn_mode == 1) {
+                    // group = 4 consecutive channels = 4 consecutive lanes; fixed order -> reproducible
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                    if ((lane & 3) == 0) {
+                        const size_t seg = (size_t)y * tiles128 + (xh << 1) + half;
+                        float2* out = reinterpret_cast<float2*>(p.gn_partial) +
+                                      (((size_t)img * p.H * tiles128 + seg) * 32 + q * 8 + (lane >> 2));
+                        *out = make_float2(s, ss);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -893,7 +1126,87 @@ static volatile int* hang_word_device() {
 }
 int gemm_last_hang() { return g_hang_host ? *g_hang_host : 0; }
 
+// Is this op a dense 3x3 stride-1 convolution to exactly 128 channels on rows that split into 256-pixel tiles?
+static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
+    static const bool off = getenv("TML_NO_SWAP") && getenv("TML_NO_SWAP")[0] == '1';   // tuning switch
+    if (off || op.stride != 1 || op.ntaps != 9 || op.N != 128 || op.OW % 256 != 0 || op.OW != op.A_W || op.OH != op.A_H ||
+        op.B_sBatch != 0 || op.dbg_shift != 0 || op.alpha != 1.0f || op.out_fp32 || op.D_sN != 1 || op.A_C % kBlockK != 0 ||
+        (op.n_store != 0 && op.n_store != 128) || (op.gn_mode != 0 && op.gn_mode != 1))
+        return false;
+    const int64_t sW = 128, sH = (int64_t)op.OW * 128, sB = (int64_t)op.OH * op.OW * 128;
+    if (op.D_sW != sW || op.D_sH != sH || op.D_sB != sB) return false;
+    if (op.resid && (op.R_sW != sW || op.R_sH != sH || op.R_sB != sB)) return false;
+    if (op.gn_mode == 1 && !op.gn_partial) return false;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) tap_of[r][c] = -1;
+    for (int i = 0; i < 9; ++i) {
+        if (op.dh[i] < -1 || op.dh[i] > 1 || op.dw[i] < -1 || op.dw[i] > 1) return false;
+        tap_of[op.dh[i] + 1][op.dw[i] + 1] = i;
+    }
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) if (tap_of[r][c] < 0) return false;
+    return true;
+}
+
+static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num_sms, cudaStream_t stream) {
+    int rc;
+    CUtensorMap mapW, mapRow, mapTail;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)op.ntaps * op.A_C, (cuuint64_t)op.N, 1};
+        cuuint64_t str[2] = {(cuuint64_t)op.B_sN * 2, (cuuint64_t)op.B_sN * 2 * (cuuint64_t)op.N};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, 128, 1};
+        if ((rc = encode_map(&mapW, op.Bm, 3, dims, str, box, op.name))) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)op.A_C, (cuuint64_t)op.A_W, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
+        cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, 256, 1, 1};
+        if ((rc = encode_map(&mapRow, op.A, 4, dims, str, box, op.name))) return rc;
+        box[1] = 2;
+        if ((rc = encode_map(&mapTail, op.A, 4, dims, str, box, op.name))) return rc;
+    }
+    SwParams p;
+    memset(&p, 0, sizeof(p));
+    p.H = op.OH; p.W = op.OW; p.nimg = op.A_B; p.kchunks = op.A_C / kBlockK;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) p.tap_of[r][c] = tap_of[r][c];
+    p.bias = op.bias;
+    p.resid = reinterpret_cast<const __nv_bfloat16*>(op.resid);
+    p.D = reinterpret_cast<__nv_bfloat16*>(op.D);
+    p.gn_mode = op.gn_mode;
+    p.gn_partial = op.gn_partial;
+    p.hang_where = hang_word_device();
+    { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
+      static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne == 1 ? 1 : 0; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+        attr_set = true;
+    }
+    const int total_tiles = op.A_B * op.OH * (op.OW / 256);
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    const bool timed = g_timing && g_timed.size() < g_timing_cap;
+    TimedLaunch tl;
+    if (timed) {
+        tl.a = take_event(); tl.b = take_event();
+        tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * 128.0 * (double)op.ntaps * op.A_C;
+        snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
+                 op.ntaps * op.A_C, 2000 + op.gn_mode * 10);
+        cudaEventRecord(tl.a, stream);
+    } else if (g_timing) {
+        ++g_timing_dropped;
+    }
+    conv3x3_swapped_kernel<<<grid, kThreads, kSwSmem, stream>>>(mapW, mapRow, mapTail, p);
+    if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s: launch failed: %s", op.name, cudaGetErrorString(e)); return -5; }
+    g_tc_launches.fetch_add(1);
+    return 0;
+}
+
 int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
+    {
+        int tap_of[3][3];
+        if (swap_eligible(op, tap_of)) return gemm_launch_swapped(op, tap_of, num_sms, stream);
+    }
     GemmTiling t;
     int rc = gemm_plan(op, &t);
     if (rc) return rc;

@@ -8,9 +8,9 @@ namespace tml {
 
 typedef __nv_bfloat16 bf16;
 
-// conv_in (3 -> C0, 3x3 s1 p1): fp32 NCHW image -> bf16 NHWC.  w_kc: [27][C0] fp32 (k = ci*9+r*3+s).
-void launch_conv_in_fwd(const float* x, const float* w_kc, const float* bias, bf16* y, int B, int H, int W, int C0,
-                        cudaStream_t s);
+// conv_in (3 -> C0, 3x3 s1 p1), step 1: fp32 NCHW image -> im2col rows bf16 [B*H*W][64]
+// (k = ci*9+r*3+s: [0,27) hi = bf16(x), [27,54) lo = bf16(x - hi), rest 0); step 2 is a K=64 GEMM.
+void launch_conv_in_im2col(const float* x, bf16* a, int B, int H, int W, cudaStream_t s);
 
 // GroupNorm(32 groups) over bf16 [B, HW, C].
 //   partial: [B][chunks][32][2] fp32 scratch;  ss: [B][C] float2 (scale, shift);  mr: [B][32] float2 (mean, rstd)

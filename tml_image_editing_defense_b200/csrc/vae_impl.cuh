@@ -211,8 +211,7 @@ struct TmlEncoder {
     std::map<std::string, HostTensor> host;
     std::vector<void*> dev_allocs;
     // parameters
-    float* conv_in_w = nullptr;  // [27][C0] fp32
-    float* conv_in_b = nullptr;
+    Lin conv_in_fwd;             // forward as a GEMM over im2col rows: [C0][64] = [w(27) | w(27) | 0]
     Packed conv_in_bwd;          // dgrad as a GEMM: B[ci (3, padded to 16)][t*C0 + co]
     std::vector<Resnet> resnets;          // in forward order (down blocks then mid[0], mid[1])
     std::vector<Conv3> downs;
