@@ -135,6 +135,8 @@ typedef struct TmlGemmDesc {
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 /* entries per image of the partial buffer a gn_mode GEMM writes: [B][tiles][32][2] floats */
 int tml_debug_gn_tiles_per_image(int OH, int OW);
+/* the same for one specific op (the operand-swapped 3x3 kernel reduces gn_mode 2 per 64-pixel segment) */
+int tml_debug_gn_chunks_per_image(const TmlGemmDesc* d);
 /* Offsets (bytes into `saved`) and [B,H,W,C] dims of the bf16 NHWC activations the forward keeps:
  * "conv_in", "resnet_h1"/"resnet_out" (index = resnet in forward order), "down_out", "attn_qkv",
  * "attn_P" ([B,tok,tok,1]), "attn_out". */

@@ -68,9 +68,7 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     if gn and IMPL["simt"]:
         gn = 0   # the SIMT debug kernel has no fused reductions
     if gn:
-        ntile = lib.tml_debug_gn_tiles_per_image(OH, OW)
-        part = torch.full((B, ntile, 32, 2), float("nan"), dtype=torch.float32, device=dev)
-        d.gn_mode = gn; d.gn_partial = part.data_ptr()
+        d.gn_mode = gn
         if gn == 2:
             xg = torch.randn(B, OH, OW, N, generator=g).to(torch.bfloat16)
             ss = torch.stack([torch.rand(B, N, generator=g) + 0.5, torch.randn(B, N, generator=g) * 0.3], dim=-1)
@@ -79,6 +77,9 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
             keep = [xg.to(dev), ss.contiguous().to(dev), mr.contiguous().to(dev), gam.to(dev)]
             d.gn_x, d.gn_ss, d.gn_mr, d.gn_gamma = [t.data_ptr() for t in keep]
             d.gn_silu = 1
+        ntile = lib.tml_debug_gn_chunks_per_image(C.byref(d))
+        part = torch.full((B, ntile, 32, 2), float("nan"), dtype=torch.float32, device=dev)
+        d.gn_partial = part.data_ptr()
     rc = lib.tml_debug_gemm(C.byref(d), torch.cuda.current_stream().cuda_stream)
     if rc:
         print(f"[gemm] {name}: launch error {lib.tml_last_error().decode()}")
@@ -165,6 +166,12 @@ def run_gemm_suite(lib, dev):
         ("swap dgrad 128->128 3x512 resid", dict(B=1, H=3, W=512, Cin=128, N=128, mode=1, resid=True)),
         ("swap dgrad 256->128 2x256", dict(B=2, H=2, W=256, Cin=256, N=128, mode=1)),
         ("swap 64->128 1x256", dict(B=1, H=1, W=256, Cin=64, N=128, mode=0, bias=True)),
+        ("swap 128->256 3x256 bias +stats", dict(B=2, H=3, W=256, Cin=128, N=256, mode=0, bias=True, gn=1)),
+        ("swap 256->256 2x256 resid +stats", dict(B=1, H=2, W=256, Cin=256, N=256, mode=0, resid=True, gn=1)),
+        ("swap dgrad 256->256 2x512 +gnbwd", dict(B=2, H=2, W=512, Cin=256, N=256, mode=1, gn=2)),
+        ("swap dgrad 128->128 4x256 +gnbwd", dict(B=2, H=4, W=256, Cin=128, N=128, mode=1, gn=2)),
+        ("swap 128->512 2x256 +stats", dict(B=1, H=2, W=256, Cin=128, N=512, mode=0, bias=True, gn=1)),
+        ("swap dgrad 512->512 1x256 +gnbwd", dict(B=2, H=1, W=256, Cin=512, N=512, mode=1, gn=2)),
         ("swap multi-wave 128->128 64x256 B=4 all", dict(B=4, H=64, W=256, Cin=128, N=128, mode=0, bias=True, resid=True, gn=1)),
     ]
     for name, kw in cases:

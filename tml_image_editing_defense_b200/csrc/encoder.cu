@@ -389,9 +389,8 @@ void tml_launch_counts(int64_t out[2]) {
 }
 void tml_debug_set_gemm_impl(int impl) { gemm_set_impl(impl); }
 
-int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
+static int desc_to_op(const TmlGemmDesc* d, GemmOp& o) {
     if (!d) { set_error("null desc"); return -1; }
-    GemmOp o;
     o.name = "debug_gemm";
     o.A = d->A; o.A_C = d->A_C; o.A_W = d->A_W; o.A_H = d->A_H; o.A_B = d->A_B;
     o.A_sW = d->A_sW; o.A_sH = d->A_sH; o.A_sB = d->A_sB;
@@ -409,6 +408,18 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
     o.gn_ss = reinterpret_cast<const float2*>(d->gn_ss); o.gn_mr = reinterpret_cast<const float2*>(d->gn_mr);
     o.gn_gamma = d->gn_gamma; o.gn_silu = d->gn_silu;
     o.dbg_shift = d->dbg_shift; o.dbg_bo = d->dbg_bo;
+    return 0;
+}
+
+int tml_debug_gn_chunks_per_image(const TmlGemmDesc* d) {
+    GemmOp o;
+    if (desc_to_op(d, o)) return -1;
+    return gemm_gn_chunks_per_image(o);
+}
+
+int tml_debug_gemm(const TmlGemmDesc* d, void* stream) {
+    GemmOp o;
+    RC(desc_to_op(d, o));
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return gemm_launch(o, sms, reinterpret_cast<cudaStream_t>(stream));

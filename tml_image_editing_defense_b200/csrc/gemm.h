@@ -61,8 +61,14 @@ struct GemmTiling {
 
 // Returns 0 and fills `t`, or a negative value and sets the thread-local error message.
 int gemm_plan(const GemmOp& op, GemmTiling* t);
-// number of 128-row tiles per image (= chunk count of the fused GroupNorm partial buffer)
+// number of 128-row tiles per image (= chunk count of the fused GroupNorm partial buffer, gn_mode 1)
 int gemm_gn_tiles_per_image(int OH, int OW);
+// partial-sum entries per image this op's fused reduction writes (gn_mode set); at most 2 x tiles per image
+int gemm_gn_chunks_per_image(const GemmOp& op);
+
+// true when gemm_launch_tc runs this op on the operand-swapped 3x3 kernel (channels as M, 256 pixels of a row as N),
+// whose fused GroupNorm reductions are cheap enough to use at any K
+bool gemm_swapped_shape(const GemmOp& op);
 
 // tcgen05/TMEM/TMA implicit-GEMM kernel (the product path).
 int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream);

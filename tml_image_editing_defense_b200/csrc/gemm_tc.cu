@@ -133,6 +133,13 @@ int gemm_gn_tiles_per_image(int OH, int OW) {
     return TW ? (OH / TH) * (OW / TW) : 0;
 }
 
+bool gemm_swapped_shape(const GemmOp& op);
+// Partial-sum entries per image written by the fused GroupNorm reduction of this op.
+int gemm_gn_chunks_per_image(const GemmOp& op) {
+    if (op.gn_mode == 2 && gemm_swapped_shape(op)) return op.OH * op.OW / 64;   // 16-warp epilogue: 64-pixel segments
+    return gemm_gn_tiles_per_image(op.OH, op.OW);
+}
+
 int gemm_plan(const GemmOp& op, GemmTiling* t) {
     if (op.A_C % kBlockK != 0) { set_error("%s: A_C=%d is not a multiple of 64", op.name, op.A_C); return -1; }
     if (op.N % 16 != 0) { set_error("%s: N=%d is not a multiple of 16", op.name, op.N); return -1; }
@@ -863,16 +870,33 @@ static_assert(kSwSmem <= kMaxSmem, "swapped-conv shared memory");
 struct SwParams {
     int H, W, nimg, kchunks;
     int tap_of[3][3];            // packed-weight tap index of (row dh + 1, column dw + 1)
-    const float* bias;           // [128] or null
-    const __nv_bfloat16* resid;  // dense NHWC [nimg][H][W][128] or null
-    __nv_bfloat16* D;            // dense NHWC [nimg][H][W][128]
-    int gn_mode;                 // 0 or 1
+    const float* bias;           // [N] or null
+    const __nv_bfloat16* resid;  // dense NHWC [nimg][H][W][N] or null
+    __nv_bfloat16* D;            // dense NHWC [nimg][H][W][N]
+    int gn_mode;                 // 0 none, 1 (sum, sumsq) of the output, 2 GroupNorm-backward sums (see GemmOp)
     float* gn_partial;           // [nimg][H * W/128][32][2]
+    const __nv_bfloat16* gn_x;   // mode 2: the GroupNorm input, same layout as D
+    const float2* gn_ss;         // mode 2: [nimg][N] (scale, shift)
+    const float2* gn_mr;         // mode 2: [nimg][32] (mean, rstd)
+    const float* gn_gamma;       // mode 2: [N]
+    int gn_silu;
     volatile int* hang_where;
     int dbg_no_epi, dbg_mma_only;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+// NC: output channels = 128 * NC (NC channel tiles of M = 128 per pixel tile); RES: residual add; GNB: fused
+// GroupNorm-backward reductions (gn_mode 2).  Template parameters so the common instantiations stay lean.
+// The GNB instantiations run 16 epilogue warps (64 pixels each, 8-pixel steps, <= 102 registers) because their
+// epilogue is instruction-bound (exp + rcp + ~18 ALU ops per element): four warps per SM sub-partition instead of two
+// is what lets it finish inside the main loop of the next tile.  Their partial sums are per 64-pixel segment.
+template <bool GNB> struct SwCfg {
+    static constexpr int kEpiWarps = GNB ? 16 : 8;
+    static constexpr int kThreadsSw = 128 + 32 * kEpiWarps;
+    static constexpr int kPx = 256 / (kEpiWarps / 4);   // pixels per epilogue warp
+    static constexpr int kStep = kPx / 8;               // pixels per tcgen05.ld
+};
+template <int NC, bool RES, bool GNB>
+__global__ void __launch_bounds__(SwCfg<GNB>::kThreadsSw, 1)
 conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapRow,
                        const __grid_constant__ CUtensorMap mapTail, const SwParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -897,7 +921,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kSwWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < kSwRowSlots; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiThreads); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * SwCfg<GNB>::kEpiWarps); }
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -907,8 +931,10 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     volatile int* hw = p.hang_where;
 
+    // tile = (pixel tile, channel tile), channel tile fastest: CTAs that run side by side share their input rows in L2
+    constexpr int N = 128 * NC;
     const int tiles_x = p.W >> 8;
-    const int total_tiles = p.nimg * p.H * tiles_x;
+    const int total_tiles = p.nimg * p.H * tiles_x * NC;
 
     if (warp == 0) {
         // ===================================================================== weight producer
@@ -916,7 +942,8 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             int ws = 0;
             uint32_t wphase = 0;
             bool first_pass = true;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ct = tile % NC;
                 for (int ch = 0; ch < p.kchunks; ++ch)
                     for (int r = 0; r < 3; ++r)
                         for (int c = 0; c < 3; ++c) {
@@ -926,10 +953,11 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                             } else {
                                 mbar_arrive_expect_tx(&wfull[ws], uint32_t(kSwWBytes));
                                 tma_load_3d(wring + size_t(ws) * kSwWBytes, &mapW, &wfull[ws],
-                                            (p.tap_of[r][c] * p.kchunks + ch) * kBlockK, 0, 0);
+                                            (p.tap_of[r][c] * p.kchunks + ch) * kBlockK, ct * 128, 0);
                             }
                             if (++ws == kSwWStages) { ws = 0; wphase ^= 1u; first_pass = false; }
                         }
+            }
         }
     } else if (warp == 3) {
         // ===================================================================== input-row producer
@@ -938,8 +966,9 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             uint32_t rphase = 0;
             bool first_pass = true;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int xh = tile % tiles_x;
-                const int rem = tile / tiles_x;
+                const int pt = tile / NC;
+                const int xh = pt % tiles_x;
+                const int rem = pt / tiles_x;
                 const int y = rem % p.H, img = rem / p.H;
                 const int x0 = xh << 8;
                 for (int ch = 0; ch < p.kchunks; ++ch)
@@ -999,57 +1028,123 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             if (acc == 0) acc_phase ^= 1u;
         }
     } else if (warp >= 4) {
-        // ===================================================================== epilogue (8 warps)
-        // warp e: TMEM lane quadrant e % 4 (output channels 32q .. 32q+31), pixel half e / 4 (128 of the 256 pixels)
+        // ===================================================================== epilogue (8 or 16 warps)
+        // warp e: TMEM lane quadrant e % 4 (output channels 32q .. 32q+31 of the channel tile), pixel part e / 4
+        constexpr int PX = SwCfg<GNB>::kPx, STEP = SwCfg<GNB>::kStep;
         const int e = warp - 4;
-        const int q = e & 3, half = e >> 2;
-        const int chn = q * 32 + lane;
-        const float bias_c = p.bias != nullptr ? __ldg(p.bias + chn) : 0.f;
-        const int tiles128 = p.W >> 7;   // 128-pixel segments per row: the granularity of the GroupNorm partials
+        const int q = e & 3, part = e >> 2;
+        constexpr int CPG = N / 32;      // channels per GroupNorm group = consecutive lanes per group (4, 8 or 16)
+        const int segs_row = p.W / PX;   // partial-sum segments per image row
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int xh = tile % tiles_x;
-            const int rem = tile / tiles_x;
+            const int ct = tile % NC, pt = tile / NC;
+            const int xh = pt % tiles_x;
+            const int rem = pt / tiles_x;
             const int y = rem % p.H, img = rem / p.H;
-            const size_t off = (((size_t)img * p.H + y) * p.W + (xh << 8) + (half << 7)) * 128 + chn;
-            mbar_wait(&tfull[acc], acc_phase, hw, 206);
-            tc_fence_after();
-            if (p.dbg_no_epi != 1) {
-                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + half * 128);
-                __nv_bfloat16* dp = p.D + off;
-                const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.resid) + off;
-                float s = 0.f, ss = 0.f;
-                for (int ck = 0; ck < 4; ++ck) {
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + uint32_t(ck * 32), v);
-                    unsigned short rr[32];
-                    if (p.resid != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) rr[j] = __ldg(rp + (size_t)(ck * 32 + j) * 128);
+            const int chn = ct * 128 + q * 32 + lane;
+            const size_t off = (((size_t)img * p.H + y) * p.W + (xh << 8) + part * PX) * N + chn;
+            if constexpr (RES || GNB) {
+                // Pull the NEXT tile's residual / GroupNorm-input slice (256 pixels x 256 bytes) into L2 a whole tile
+                // ahead: epilogue thread t < 256 takes pixel t (two 128-byte lines).
+                const int nxt = tile + int(gridDim.x);
+                const int et = int(threadIdx.x) - 128;
+                if (nxt < total_tiles && et < 256) {
+                    const int nct = nxt % NC, npt = nxt / NC;
+                    const int nxh = npt % tiles_x, nrem = npt / tiles_x;
+                    const size_t noff = (((size_t)(nrem / p.H) * p.H + (nrem % p.H)) * p.W + (nxh << 8) + et) * N + nct * 128;
+                    if constexpr (RES) {
+                        prefetch_l2(p.resid + noff);
+                        prefetch_l2(p.resid + noff + 64);
                     }
-                    tmem_ld_wait();
+                    if constexpr (GNB) {
+                        prefetch_l2(p.gn_x + noff);
+                        prefetch_l2(p.gn_x + noff + 64);
+                    }
+                }
+            }
+            // per-thread constants (thread = channel): requested before waiting for the accumulator
+            const float bias_c = p.bias != nullptr ? __ldg(p.bias + chn) : 0.f;
+            float sc = 0.f, sh = 0.f, gm = 0.f, mean = 0.f, rstd = 0.f;
+            if constexpr (GNB) {
+                const float2 s2 = __ldg(&p.gn_ss[(size_t)img * N + chn]);
+                const float2 m2 = __ldg(&p.gn_mr[(size_t)img * 32 + chn / CPG]);
+                sc = s2.x; sh = s2.y; mean = m2.x; rstd = m2.y;
+                gm = __ldg(p.gn_gamma + chn);
+            }
+            __nv_bfloat16* dp = p.D + off;
+            const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.resid) + off;
+            const unsigned short* xp = reinterpret_cast<const unsigned short*>(p.gn_x) + off;
+            // Residual / GroupNorm-input values are gathered per thread (thread = channel, one 2-byte load per
+            // pixel; a warp's load of one pixel is 64 contiguous bytes).  They are fetched one step ahead of their
+            // use, the first step before the accumulator is even complete.
+            unsigned short ra[STEP], rb[STEP], xa[STEP], xb[STEP];
+            auto fetch = [&](int k, unsigned short (&r)[STEP], unsigned short (&x)[STEP]) {
+                if constexpr (RES) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = __uint_as_float(v[j]) + bias_c;
-                        if (p.resid != nullptr) f += __uint_as_float(uint32_t(rr[j]) << 16);
-                        const __nv_bfloat16 b = __float2bfloat16_rn(f);
-                        dp[(size_t)(ck * 32 + j) * 128] = b;
-                        const float fr = __bfloat162float(b);   // statistics of the values as stored
+                    for (int j = 0; j < STEP; ++j) r[j] = __ldg(rp + (size_t)(k * STEP + j) * N);
+                }
+                if constexpr (GNB) {
+#pragma unroll
+                    for (int j = 0; j < STEP; ++j) x[j] = __ldg(xp + (size_t)(k * STEP + j) * N);
+                }
+            };
+            float s = 0.f, ss = 0.f;
+            auto process = [&](int k, const uint32_t (&v)[STEP], const unsigned short (&r)[STEP], const unsigned short (&x)[STEP]) {
+#pragma unroll
+                for (int j = 0; j < STEP; ++j) {
+                    float f = __uint_as_float(v[j]) + bias_c;
+                    if constexpr (RES) f += __uint_as_float(uint32_t(r[j]) << 16);
+                    const __nv_bfloat16 b = __float2bfloat16_rn(f);
+                    dp[(size_t)(k * STEP + j) * N] = b;
+                    const float fr = __bfloat162float(b);   // reductions see the values as stored
+                    if constexpr (GNB) {
+                        // GroupNorm backward: dxh = dy * act'(x*sc+sh) * gamma; sums of dxh and dxh*x
+                        const float xv = __uint_as_float(uint32_t(x[j]) << 16);
+                        float dxh = fr * gm;
+                        if (p.gn_silu) {
+                            const float u = fmaf(xv, sc, sh);
+                            const float sg = __fdividef(1.f, 1.f + __expf(-u));
+                            dxh *= sg * fmaf(u, 1.f - sg, 1.f);
+                        }
+                        s += dxh;
+                        ss = fmaf(dxh, xv, ss);
+                    } else {
                         s += fr;
                         ss = fmaf(fr, fr, ss);
                     }
                 }
-                if (p.gn_mode == 1) {
-                    // group = 4 consecutive channels = 4 consecutive lanes; fixed order -> reproducible
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-                    if ((lane & 3) == 0) {
-                        const size_t seg = (size_t)y * tiles128 + (xh << 1) + half;
+            };
+            if (p.dbg_no_epi != 1) fetch(0, ra, xa);
+            mbar_wait(&tfull[acc], acc_phase, hw, 206);
+            tc_fence_after();
+            if (p.dbg_no_epi != 1) {
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + part * PX);
+#pragma unroll 1
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    uint32_t v[STEP];
+                    tmem_ld_n(t_addr + uint32_t(2 * k2 * STEP), v);
+                    fetch(2 * k2 + 1, rb, xb);
+                    tmem_ld_wait();
+                    process(2 * k2, v, ra, xa);
+                    tmem_ld_n(t_addr + uint32_t((2 * k2 + 1) * STEP), v);
+                    if (k2 < 3) fetch(2 * k2 + 2, ra, xa);
+                    tmem_ld_wait();
+                    process(2 * k2 + 1, v, rb, xb);
+                }
+                if (p.gn_mode != 0) {
+                    // sum(dxh*xh) = rstd * (sum(dxh*x) - mean * sum(dxh)); linear, so applied per thread
+                    if constexpr (GNB) ss = rstd * fmaf(-mean, s, ss);
+                    // group = CPG consecutive channels = CPG consecutive lanes; fixed order -> reproducible
+#pragma unroll
+                    for (int m = 1; m < CPG; m <<= 1) {
+                        s += __shfl_xor_sync(0xffffffffu, s, m);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, m);
+                    }
+                    if ((lane & (CPG - 1)) == 0) {
+                        const size_t seg = (size_t)y * segs_row + xh * (256 / PX) + part;
                         float2* out = reinterpret_cast<float2*>(p.gn_partial) +
-                                      (((size_t)img * p.H * tiles128 + seg) * 32 + q * 8 + (lane >> 2));
+                                      (((size_t)img * p.H * segs_row + seg) * 32 + chn / CPG);
                         *out = make_float2(s, ss);
                     }
                 }
@@ -1126,17 +1221,24 @@ static volatile int* hang_word_device() {
 }
 int gemm_last_hang() { return g_hang_host ? *g_hang_host : 0; }
 
-// Is this op a dense 3x3 stride-1 convolution to exactly 128 channels on rows that split into 256-pixel tiles?
-static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
+// Is this op a dense 3x3 stride-1 convolution to 128 / 256 / 512 channels on rows that split into 256-pixel tiles?
+// (shape only: the fused-reduction fields are checked at launch)
+bool gemm_swapped_shape(const GemmOp& op) {
     static const bool off = getenv("TML_NO_SWAP") && getenv("TML_NO_SWAP")[0] == '1';   // tuning switch
-    if (off || op.stride != 1 || op.ntaps != 9 || op.N != 128 || op.OW % 256 != 0 || op.OW != op.A_W || op.OH != op.A_H ||
-        op.B_sBatch != 0 || op.dbg_shift != 0 || op.alpha != 1.0f || op.out_fp32 || op.D_sN != 1 || op.A_C % kBlockK != 0 ||
-        (op.n_store != 0 && op.n_store != 128) || (op.gn_mode != 0 && op.gn_mode != 1))
+    static const int max_n = getenv("TML_SWAP_MAX_N") ? atoi(getenv("TML_SWAP_MAX_N")) : 512;   // tuning switch
+    if (off || op.stride != 1 || op.ntaps != 9 || (op.N != 128 && op.N != 256 && op.N != 512) || op.N > max_n ||
+        op.OW % 256 != 0 || op.OW != op.A_W || op.OH != op.A_H || op.B_sBatch != 0 || op.dbg_shift != 0 ||
+        op.alpha != 1.0f || op.out_fp32 || op.D_sN != 1 || op.A_C % kBlockK != 0 || (op.n_store != 0 && op.n_store != op.N))
         return false;
-    const int64_t sW = 128, sH = (int64_t)op.OW * 128, sB = (int64_t)op.OH * op.OW * 128;
+    const int64_t sW = op.N, sH = (int64_t)op.OW * op.N, sB = (int64_t)op.OH * op.OW * op.N;
     if (op.D_sW != sW || op.D_sH != sH || op.D_sB != sB) return false;
     if (op.resid && (op.R_sW != sW || op.R_sH != sH || op.R_sB != sB)) return false;
-    if (op.gn_mode == 1 && !op.gn_partial) return false;
+    return true;
+}
+static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
+    if (!gemm_swapped_shape(op) || op.gn_mode < 0 || op.gn_mode > 2) return false;
+    if (op.gn_mode != 0 && !op.gn_partial) return false;
+    if (op.gn_mode == 2 && (!op.gn_x || !op.gn_ss || !op.gn_mr || !op.gn_gamma)) return false;
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) tap_of[r][c] = -1;
     for (int i = 0; i < 9; ++i) {
         if (op.dh[i] < -1 || op.dh[i] > 1 || op.dw[i] < -1 || op.dw[i] > 1) return false;
@@ -1172,29 +1274,47 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     p.D = reinterpret_cast<__nv_bfloat16*>(op.D);
     p.gn_mode = op.gn_mode;
     p.gn_partial = op.gn_partial;
+    p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
+    p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.hang_where = hang_word_device();
     { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne == 1 ? 1 : 0; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
-        attr_set = true;
-    }
-    const int total_tiles = op.A_B * op.OH * (op.OW / 256);
+    const int nc = op.N / 128;
+    const int total_tiles = op.A_B * op.OH * (op.OW / 256) * nc;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     const bool timed = g_timing && g_timed.size() < g_timing_cap;
     TimedLaunch tl;
     if (timed) {
         tl.a = take_event(); tl.b = take_event();
-        tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * 128.0 * (double)op.ntaps * op.A_C;
+        tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)op.N * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
                  op.ntaps * op.A_C, 2000 + op.gn_mode * 10);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;
     }
-    conv3x3_swapped_kernel<<<grid, kThreads, kSwSmem, stream>>>(mapW, mapRow, mapTail, p);
+    {
+        typedef void (*SwKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const SwParams);
+        static const SwKernel table[3][2][2] = {
+            {{conv3x3_swapped_kernel<1, false, false>, conv3x3_swapped_kernel<1, false, true>},
+             {conv3x3_swapped_kernel<1, true, false>, conv3x3_swapped_kernel<1, true, true>}},
+            {{conv3x3_swapped_kernel<2, false, false>, conv3x3_swapped_kernel<2, false, true>},
+             {conv3x3_swapped_kernel<2, true, false>, conv3x3_swapped_kernel<2, true, true>}},
+            {{conv3x3_swapped_kernel<4, false, false>, conv3x3_swapped_kernel<4, false, true>},
+             {conv3x3_swapped_kernel<4, true, false>, conv3x3_swapped_kernel<4, true, true>}}};
+        static bool attr_set = false;
+        if (!attr_set) {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 2; ++b)
+                    for (int c = 0; c < 2; ++c) {
+                        cudaError_t e = cudaFuncSetAttribute(table[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem);
+                        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+                    }
+            attr_set = true;
+        }
+        const SwKernel k = table[nc == 1 ? 0 : nc == 2 ? 1 : 2][op.resid ? 1 : 0][op.gn_mode == 2 ? 1 : 0];
+        k<<<grid, op.gn_mode == 2 ? SwCfg<true>::kThreadsSw : SwCfg<false>::kThreadsSw, kSwSmem, stream>>>(mapW, mapRow, mapTail, p);
+    }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("%s: launch failed: %s", op.name, cudaGetErrorString(e)); return -5; }

@@ -328,8 +328,8 @@ static int make_resnet(TmlEncoder* e, const std::string& key, int Ci, int Co, Re
 // layout (what lives where in `saved`; how much scratch the walks need)
 // ------------------------------------------------------------------------------------------------
 static size_t act_bytes(int B, int h, int w, int c) { return (size_t)B * h * w * c * sizeof(bf16); }
-// partial sums written by a GEMM epilogue: one entry per (image, 128-row tile, group)
-static size_t fused_partial_bytes(int B, int h, int w) { return (size_t)B * gemm_gn_tiles_per_image(h, w) * 32 * 2 * sizeof(float); }
+// partial sums written by a GEMM epilogue: one entry per (image, 128-row tile or 64-pixel segment, group)
+static size_t fused_partial_bytes(int B, int h, int w) { return (size_t)B * 2 * gemm_gn_tiles_per_image(h, w) * 32 * 2 * sizeof(float); }
 // sized for the smallest channel count (largest chunk count) so one bound covers every layer
 static size_t gn_partial_bytes(int B, int hw) { return (size_t)B * gn_num_chunks(hw, 512) * 32 * 2 * sizeof(float); }
 
@@ -544,10 +544,12 @@ static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
 static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, const GnSaved& g, int silu, float* buf,
                             int oh, int ow) {
     static const bool off = env_off("TML_NO_FUSE_GNBWD");     // tuning switch
-    // Measured on B200: for K = 9*128 the main loop of a tile is too short to hide this epilogue (exp + rcp per
-    // element and an extra read of x), so 128-channel layers keep the standalone reduction kernel.
+    // Measured on B200: in the pixel-major kernel a K = 9*128 main loop is too short to hide this epilogue (exp + rcp
+    // per element, an extra read of x, cross-lane sums), so short-K layers keep the standalone reduction kernel there.
+    // The operand-swapped kernel (thread = channel, 16 epilogue warps) hides it at any K: 128-channel dgrads go
+    // 7.1 -> 8.0 ms per 64 images and the 2.2 ms/16-image reduction kernel disappears.
     static const int min_k = getenv("TML_GNBWD_MIN_K") ? atoi(getenv("TML_GNBWD_MIN_K")) : 2000;
-    if (off || gemm_get_impl() != 0 || o.ntaps * o.A_C < min_k) return Partials();
+    if (off || gemm_get_impl() != 0 || (o.ntaps * o.A_C < min_k && !gemm_swapped_shape(o))) return Partials();
     o.gn_mode = 2;
     o.gn_partial = buf;
     o.gn_x = x;
@@ -557,7 +559,7 @@ static Partials fuse_gn_bwd(Run& r, GemmOp& o, const bf16* x, const Norm& n, con
     o.gn_silu = silu;
     Partials p;
     p.p = buf;
-    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    p.nchunks = gemm_gn_chunks_per_image(o);
     return p;
 }
 
