@@ -172,6 +172,12 @@ def run_gemm_suite(lib, dev):
         ("swap dgrad 128->128 4x256 +gnbwd", dict(B=2, H=4, W=256, Cin=128, N=128, mode=1, gn=2)),
         ("swap 128->512 2x256 +stats", dict(B=1, H=2, W=256, Cin=128, N=512, mode=0, bias=True, gn=1)),
         ("swap dgrad 512->512 1x256 +gnbwd", dict(B=2, H=1, W=256, Cin=512, N=512, mode=1, gn=2)),
+        # the same kernel on CTA pairs (rows of 128 pixels: M = 256 channels, N = 2 rows x 128 pixels)
+        ("swpair 256->256 4x128 bias +stats", dict(B=2, H=4, W=128, Cin=256, N=256, mode=0, bias=True, gn=1)),
+        ("swpair 512->512 2x128 resid", dict(B=1, H=2, W=128, Cin=512, N=512, mode=0, resid=True)),
+        ("swpair dgrad 512->512 4x128 +gnbwd", dict(B=2, H=4, W=128, Cin=512, N=512, mode=1, gn=2)),
+        ("swpair dgrad 512->256 2x128", dict(B=2, H=2, W=128, Cin=512, N=256, mode=1)),
+        ("swpair multi-wave 256->512 64x128 B=4 all", dict(B=4, H=64, W=128, Cin=256, N=512, mode=0, bias=True, resid=True, gn=1)),
         ("swap multi-wave 128->128 64x256 B=4 all", dict(B=4, H=64, W=256, Cin=128, N=128, mode=0, bias=True, resid=True, gn=1)),
     ]
     for name, kw in cases:

@@ -859,13 +859,21 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 // 64 contiguous bytes (two full sectors).  GroupNorm statistics are per channel = per thread, so the fused
 // reduction is a private accumulation plus two shuffles per group: no shared memory, no named barriers.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSwRowPx = 258;
-constexpr int kSwRowBytes = 33 * 1024;        // 258 * 128 B = 33024, rounded up to the 1 KB swizzle atom
-constexpr int kSwRowSlots = 4;
-constexpr int kSwWStages = 5;
+// Geometry of the two instantiations.  Single CTA: a tile is 256 pixels of one row (a 258-pixel slot per input row).
+// CTA pair (cta_group::2, for rows of only 128 pixels): the pair computes 256 channels x (2 rows x 128 pixels) with
+// one M = 256, N = 256 MMA stream issued by the leader; CTA r stages channels [128r, 128r+128) of the weight slice
+// (its half of A) and input row 2*yp + r (+ halo, a 130-pixel slot: its half of B).  The two 128-pixel halves of the
+// N operand live in DIFFERENT shared memories, which is what makes a two-row tile expressible at all: inside one
+// CTA, rows of 128+2 pixels cannot be 128 pixels apart.
+template <bool PAIR> struct SwGeo {
+    static constexpr int kRowPx = PAIR ? 130 : 258;
+    static constexpr int kRowBytes = PAIR ? 17 * 1024 : 33 * 1024;   // kRowPx * 128 B rounded up to the 1 KB swizzle atom
+    static constexpr int kRowSlots = 4;
+    static constexpr int kWStages = PAIR ? 8 : 5;
+    static constexpr int kSmem = 1024 + kRowSlots * kRowBytes + kWStages * (128 * kBlockK * 2) + 256;
+};
 constexpr int kSwWBytes = 128 * kBlockK * 2;  // 16 KB: 128 output channels x 64 input channels
-constexpr int kSwSmem = 1024 + kSwRowSlots * kSwRowBytes + kSwWStages * kSwWBytes + 256;
-static_assert(kSwSmem <= kMaxSmem, "swapped-conv shared memory");
+static_assert(SwGeo<false>::kSmem <= kMaxSmem && SwGeo<true>::kSmem <= kMaxSmem, "swapped-conv shared memory");
 
 struct SwParams {
     int H, W, nimg, kchunks;
@@ -874,7 +882,7 @@ struct SwParams {
     const __nv_bfloat16* resid;  // dense NHWC [nimg][H][W][N] or null
     __nv_bfloat16* D;            // dense NHWC [nimg][H][W][N]
     int gn_mode;                 // 0 none, 1 (sum, sumsq) of the output, 2 GroupNorm-backward sums (see GemmOp)
-    float* gn_partial;           // [nimg][H * W/128][32][2]
+    float* gn_partial;           // [nimg][H * W/128 (mode 1) or H * W/64 (mode 2)][32][2]
     const __nv_bfloat16* gn_x;   // mode 2: the GroupNorm input, same layout as D
     const float2* gn_ss;         // mode 2: [nimg][N] (scale, shift)
     const float2* gn_mr;         // mode 2: [nimg][32] (mean, rstd)
@@ -884,8 +892,6 @@ struct SwParams {
     int dbg_no_epi, dbg_mma_only;
 };
 
-// NC: output channels = 128 * NC (NC channel tiles of M = 128 per pixel tile); RES: residual add; GNB: fused
-// GroupNorm-backward reductions (gn_mode 2).  Template parameters so the common instantiations stay lean.
 // The GNB instantiations run 16 epilogue warps (64 pixels each, 8-pixel steps, <= 102 registers) because their
 // epilogue is instruction-bound (exp + rcp + ~18 ALU ops per element): four warps per SM sub-partition instead of two
 // is what lets it finish inside the main loop of the next tile.  Their partial sums are per 64-pixel segment.
@@ -895,15 +901,53 @@ template <bool GNB> struct SwCfg {
     static constexpr int kPx = 256 / (kEpiWarps / 4);   // pixels per epilogue warp
     static constexpr int kStep = kPx / 8;               // pixels per tcgen05.ld
 };
-template <int NC, bool RES, bool GNB>
+
+// What one CTA does for tile number `tile`.
+struct SwTile {
+    int img;
+    int chan0;        // first of this CTA's 128 output channels
+    int brow, bx0;    // the input row / first pixel behind this CTA's half of the N operand
+    int orow, ox0;    // output row / pixel of accumulator column 0; column c is pixel (orow + c / cols_row, ox0 + c % cols_row)
+};
+template <int NC, bool PAIR>
+__device__ __forceinline__ SwTile sw_decode(const SwParams& p, int tile, int crank) {
+    SwTile t;
+    if constexpr (PAIR) {
+        constexpr int NCP = NC / 2;
+        const int cp = tile % NCP, pt = tile / NCP;
+        const int segs = p.W >> 7;
+        const int xs = pt % segs, rem = pt / segs;
+        const int hp = p.H >> 1;
+        const int yp = rem % hp;
+        t.img = rem / hp;
+        t.chan0 = cp * 256 + crank * 128;
+        t.brow = 2 * yp + crank; t.bx0 = xs << 7;
+        t.orow = 2 * yp; t.ox0 = xs << 7;
+    } else {
+        const int ct = tile % NC, pt = tile / NC;
+        const int tiles_x = p.W >> 8;
+        const int xh = pt % tiles_x, rem = pt / tiles_x;
+        t.img = rem / p.H;
+        t.chan0 = ct * 128;
+        t.brow = rem % p.H; t.bx0 = xh << 8;
+        t.orow = t.brow; t.ox0 = t.bx0;
+    }
+    return t;
+}
+
+// NC: output channels = 128 * NC; RES: residual add; GNB: fused GroupNorm-backward reductions (gn_mode 2);
+// PAIR: the cta_group::2 instantiation (launched as clusters of two CTAs; the others contain no cluster instruction).
+template <int NC, bool RES, bool GNB, bool PAIR>
 __global__ void __launch_bounds__(SwCfg<GNB>::kThreadsSw, 1)
 conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapRow,
                        const __grid_constant__ CUtensorMap mapTail, const SwParams p) {
+    using G = SwGeo<PAIR>;
+    constexpr int kRowSlots = G::kRowSlots, kWStages = G::kWStages, kRowBytes = G::kRowBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* rows = smem;
-    uint8_t* wring = rows + size_t(kSwRowSlots) * kSwRowBytes;
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + size_t(kSwWStages) * kSwWBytes);   // [8]
+    uint8_t* wring = rows + size_t(kRowSlots) * kRowBytes;
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + size_t(kWStages) * kSwWBytes);   // [8]
     uint64_t* wempty = wfull + 8;     // [8]
     uint64_t* rfull = wempty + 8;     // [4]
     uint64_t* rempty = rfull + 4;     // [4]
@@ -916,25 +960,39 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapRow);
-        tma_prefetch_desc(&mapTail);
+        if constexpr (!PAIR) tma_prefetch_desc(&mapTail);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kSwWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < kSwRowSlots; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * SwCfg<GNB>::kEpiWarps); }
+        // pair mode: the "full" barriers live in the leader CTA: ONE arrival (the leader's, which also announces the
+        // transaction bytes of both CTAs' loads); the follower only issues its TMA, whose bytes are counted on the
+        // leader's barrier (a complete_tx may precede the expect_tx of its phase).  A per-stage remote arrive by the
+        // follower's producer throttled it to one stage per cross-SM round trip (measured: 855 vs 1800 TFLOP/s
+        // without loads).  The accumulator-empty barrier collects both epilogues.
+        const uint32_t nprod = PAIR ? 2u : 1u;
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < kRowSlots; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], nprod * 32 * SwCfg<GNB>::kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 2) {
+        if constexpr (PAIR) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     volatile int* hw = p.hang_where;
+    uint32_t crank = 0u;
+    if constexpr (PAIR) crank = cluster_ctarank();
+    const int htag = int(crank) * 100 + 200;
 
     // tile = (pixel tile, channel tile), channel tile fastest: CTAs that run side by side share their input rows in L2
     constexpr int N = 128 * NC;
-    const int tiles_x = p.W >> 8;
-    const int total_tiles = p.nimg * p.H * tiles_x * NC;
+    const int total_tiles = PAIR ? p.nimg * (p.H >> 1) * (p.W >> 7) * (NC / 2) : p.nimg * p.H * (p.W >> 8) * NC;
+    const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int tstep = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
     if (warp == 0) {
         // ===================================================================== weight producer
@@ -942,20 +1000,31 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             int ws = 0;
             uint32_t wphase = 0;
             bool first_pass = true;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ct = tile % NC;
+            for (int tile = tile0; tile < total_tiles; tile += tstep) {
+                const SwTile t = sw_decode<NC, PAIR>(p, tile, int(crank));
                 for (int ch = 0; ch < p.kchunks; ++ch)
                     for (int r = 0; r < 3; ++r)
                         for (int c = 0; c < 3; ++c) {
-                            mbar_wait(&wempty[ws], wphase ^ 1u, hw, 201);
-                            if (p.dbg_mma_only && !first_pass) {
-                                mbar_arrive(&wfull[ws]);
+                            mbar_wait(&wempty[ws], wphase ^ 1u, hw, htag + 1);
+                            uint8_t* dst = wring + size_t(ws) * kSwWBytes;
+                            const int k0 = (p.tap_of[r][c] * p.kchunks + ch) * kBlockK;
+                            if constexpr (PAIR) {
+                                // each CTA stages its 128 channels; bytes are counted on the leader's barrier
+                                if ((p.dbg_mma_only == 1 || p.dbg_mma_only == 2) && !first_pass) {
+                                    if (crank == 0) mbar_arrive(&wfull[ws]);
+                                } else {
+                                    if (crank == 0) mbar_arrive_expect_tx(&wfull[ws], 2u * uint32_t(kSwWBytes));
+                                    tma_load_3d_2sm(dst, &mapW, &wfull[ws], k0, t.chan0, 0);
+                                }
                             } else {
-                                mbar_arrive_expect_tx(&wfull[ws], uint32_t(kSwWBytes));
-                                tma_load_3d(wring + size_t(ws) * kSwWBytes, &mapW, &wfull[ws],
-                                            (p.tap_of[r][c] * p.kchunks + ch) * kBlockK, ct * 128, 0);
+                                if ((p.dbg_mma_only == 1 || p.dbg_mma_only == 2) && !first_pass) {
+                                    mbar_arrive(&wfull[ws]);
+                                } else {
+                                    mbar_arrive_expect_tx(&wfull[ws], uint32_t(kSwWBytes));
+                                    tma_load_3d(dst, &mapW, &wfull[ws], k0, t.chan0, 0);
+                                }
                             }
-                            if (++ws == kSwWStages) { ws = 0; wphase ^= 1u; first_pass = false; }
+                            if (++ws == kWStages) { ws = 0; wphase ^= 1u; first_pass = false; }
                         }
             }
         }
@@ -965,94 +1034,111 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             int rs = 0;
             uint32_t rphase = 0;
             bool first_pass = true;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int pt = tile / NC;
-                const int xh = pt % tiles_x;
-                const int rem = pt / tiles_x;
-                const int y = rem % p.H, img = rem / p.H;
-                const int x0 = xh << 8;
+            for (int tile = tile0; tile < total_tiles; tile += tstep) {
+                const SwTile t = sw_decode<NC, PAIR>(p, tile, int(crank));
                 for (int ch = 0; ch < p.kchunks; ++ch)
                     for (int r = 0; r < 3; ++r) {
-                        mbar_wait(&rempty[rs], rphase ^ 1u, hw, 202);
-                        if (p.dbg_mma_only && !first_pass) {
-                            mbar_arrive(&rfull[rs]);
+                        mbar_wait(&rempty[rs], rphase ^ 1u, hw, htag + 2);
+                        uint8_t* dst = rows + size_t(rs) * kRowBytes;
+                        // rows or pixels outside the image arrive as zeros (= the convolution padding)
+                        if constexpr (PAIR) {
+                            if ((p.dbg_mma_only == 1 || p.dbg_mma_only == 3) && !first_pass) {
+                                if (crank == 0) mbar_arrive(&rfull[rs]);
+                            } else {
+                                if (crank == 0) mbar_arrive_expect_tx(&rfull[rs], 2u * uint32_t(G::kRowPx) * 128u);
+                                tma_load_4d_2sm(dst, &mapRow, &rfull[rs], ch * kBlockK, t.bx0 - 1, t.brow + r - 1, t.img);
+                            }
                         } else {
-                            uint8_t* dst = rows + size_t(rs) * kSwRowBytes;
-                            mbar_arrive_expect_tx(&rfull[rs], uint32_t(kSwRowPx) * 128u);
-                            // pixels x0-1 .. x0+254, then x0+255 .. x0+256 (a TMA box is at most 256 wide); rows or
-                            // pixels outside the image arrive as zeros (= the convolution padding)
-                            tma_load_4d(dst, &mapRow, &rfull[rs], ch * kBlockK, x0 - 1, y + r - 1, img);
-                            tma_load_4d(dst + 256 * 128, &mapTail, &rfull[rs], ch * kBlockK, x0 + 255, y + r - 1, img);
+                            if ((p.dbg_mma_only == 1 || p.dbg_mma_only == 3) && !first_pass) {
+                                mbar_arrive(&rfull[rs]);
+                            } else {
+                                mbar_arrive_expect_tx(&rfull[rs], uint32_t(G::kRowPx) * 128u);
+                                // pixels x0-1 .. x0+254, then x0+255 .. x0+256 (a TMA box is at most 256 wide)
+                                tma_load_4d(dst, &mapRow, &rfull[rs], ch * kBlockK, t.bx0 - 1, t.brow + r - 1, t.img);
+                                tma_load_4d(dst + 256 * 128, &mapTail, &rfull[rs], ch * kBlockK, t.bx0 + 255, t.brow + r - 1, t.img);
+                            }
                         }
-                        if (++rs == kSwRowSlots) { rs = 0; rphase ^= 1u; first_pass = false; }
+                        if (++rs == kRowSlots) { rs = 0; rphase ^= 1u; first_pass = false; }
                     }
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (convergent warp)
-        const uint32_t idesc = umma_idesc_bf16(kUmmaM, 256);
-        int ws = 0, rs = 0, acc = 0;
-        uint32_t wphase = 0, rphase = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1u, hw, 203);
-            tc_fence_after();
-            const uint32_t d = tmem_base + uint32_t(acc * 256);
-            for (int ch = 0; ch < p.kchunks; ++ch)
-                for (int r = 0; r < 3; ++r) {
-                    mbar_wait(&rfull[rs], rphase, hw, 204);
-                    tc_fence_after();
-                    const uint32_t raddr = smem_u32(rows + size_t(rs) * kSwRowBytes);
-                    for (int c = 0; c < 3; ++c) {
-                        mbar_wait(&wfull[ws], wphase, hw, 205);
+        if (crank == 0) {   // pair mode: only the leader CTA issues
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kUmmaM : kUmmaM, 256);
+            int ws = 0, rs = 0, acc = 0;
+            uint32_t wphase = 0, rphase = 0, acc_phase = 0;
+            for (int tile = tile0; tile < total_tiles; tile += tstep) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u, hw, htag + 3);
+                tc_fence_after();
+                const uint32_t d = tmem_base + uint32_t(acc * 256);
+                for (int ch = 0; ch < p.kchunks; ++ch)
+                    for (int r = 0; r < 3; ++r) {
+                        mbar_wait(&rfull[rs], rphase, hw, htag + 4);
                         tc_fence_after();
-                        const uint64_t a_desc = umma_desc_sw128(smem_u32(wring + size_t(ws) * kSwWBytes));
-                        // operand rows = 256 consecutive pixels of the slot starting at pixel c (= dw + 1)
-                        const uint64_t b_desc = umma_desc_sw128(raddr + uint32_t(c) * 128u);
-                        const uint32_t first = (ch | r | c) != 0 ? 1u : 0u;
-                        if (elect_one()) {
-                            umma_bf16(d, a_desc, b_desc, idesc, first);
-                            umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
-                            umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
-                            umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
-                            umma_commit(&wempty[ws]);
-                            if (c == 2) umma_commit(&rempty[rs]);
+                        const uint32_t raddr = smem_u32(rows + size_t(rs) * kRowBytes);
+                        for (int c = 0; c < 3; ++c) {
+                            mbar_wait(&wfull[ws], wphase, hw, htag + 5);
+                            tc_fence_after();
+                            const uint64_t a_desc = umma_desc_sw128(smem_u32(wring + size_t(ws) * kSwWBytes));
+                            // operand rows = consecutive pixels of the slot starting at pixel c (= dw + 1)
+                            const uint64_t b_desc = umma_desc_sw128(raddr + uint32_t(c) * 128u);
+                            const uint32_t first = (ch | r | c) != 0 ? 1u : 0u;
+                            if (elect_one()) {
+                                if constexpr (PAIR) {
+                                    umma_bf16_2sm(d, a_desc, b_desc, idesc, first);
+                                    umma_bf16_2sm(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                    umma_bf16_2sm(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                    umma_bf16_2sm(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                    umma_commit_2sm(&wempty[ws], 3);
+                                    if (c == 2) umma_commit_2sm(&rempty[rs], 3);
+                                } else {
+                                    umma_bf16(d, a_desc, b_desc, idesc, first);
+                                    umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                    umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                    umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                    umma_commit(&wempty[ws]);
+                                    if (c == 2) umma_commit(&rempty[rs]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++ws == kWStages) { ws = 0; wphase ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++ws == kSwWStages) { ws = 0; wphase ^= 1u; }
+                        if (++rs == kRowSlots) { rs = 0; rphase ^= 1u; }
                     }
-                    if (++rs == kSwRowSlots) { rs = 0; rphase ^= 1u; }
+                if (elect_one()) {
+                    if constexpr (PAIR) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
                 }
-            if (elect_one()) umma_commit(&tfull[acc]);
-            __syncwarp();
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+                __syncwarp();
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
         }
     } else if (warp >= 4) {
         // ===================================================================== epilogue (8 or 16 warps)
-        // warp e: TMEM lane quadrant e % 4 (output channels 32q .. 32q+31 of the channel tile), pixel part e / 4
+        // warp e: TMEM lane quadrant e % 4 (output channels 32q .. 32q+31 of this CTA's 128), pixel part e / 4
         constexpr int PX = SwCfg<GNB>::kPx, STEP = SwCfg<GNB>::kStep;
+        constexpr int COLS_ROW = PAIR ? 128 : 256;   // accumulator columns per output row
         const int e = warp - 4;
         const int q = e & 3, part = e >> 2;
         constexpr int CPG = N / 32;      // channels per GroupNorm group = consecutive lanes per group (4, 8 or 16)
         const int segs_row = p.W / PX;   // partial-sum segments per image row
+        const int et = int(threadIdx.x) - 128;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ct = tile % NC, pt = tile / NC;
-            const int xh = pt % tiles_x;
-            const int rem = pt / tiles_x;
-            const int y = rem % p.H, img = rem / p.H;
-            const int chn = ct * 128 + q * 32 + lane;
-            const size_t off = (((size_t)img * p.H + y) * p.W + (xh << 8) + part * PX) * N + chn;
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
+            const SwTile t = sw_decode<NC, PAIR>(p, tile, int(crank));
+            const int img = t.img;
+            const int chn = t.chan0 + q * 32 + lane;
+            const int wrow = t.orow + (part * PX) / COLS_ROW, wx = t.ox0 + (part * PX) % COLS_ROW;   // this warp's first pixel
+            const size_t off = (((size_t)img * p.H + wrow) * p.W + wx) * N + chn;
             if constexpr (RES || GNB) {
                 // Pull the NEXT tile's residual / GroupNorm-input slice (256 pixels x 256 bytes) into L2 a whole tile
-                // ahead: epilogue thread t < 256 takes pixel t (two 128-byte lines).
-                const int nxt = tile + int(gridDim.x);
-                const int et = int(threadIdx.x) - 128;
+                // ahead: epilogue thread t < 256 takes the pixel of accumulator column t (two 128-byte lines).
+                const int nxt = tile + tstep;
                 if (nxt < total_tiles && et < 256) {
-                    const int nct = nxt % NC, npt = nxt / NC;
-                    const int nxh = npt % tiles_x, nrem = npt / tiles_x;
-                    const size_t noff = (((size_t)(nrem / p.H) * p.H + (nrem % p.H)) * p.W + (nxh << 8) + et) * N + nct * 128;
+                    const SwTile n = sw_decode<NC, PAIR>(p, nxt, int(crank));
+                    const size_t noff = (((size_t)n.img * p.H + n.orow + et / COLS_ROW) * p.W + n.ox0 + et % COLS_ROW) * N + n.chan0;
                     if constexpr (RES) {
                         prefetch_l2(p.resid + noff);
                         prefetch_l2(p.resid + noff + 64);
@@ -1116,7 +1202,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                 }
             };
             if (p.dbg_no_epi != 1) fetch(0, ra, xa);
-            mbar_wait(&tfull[acc], acc_phase, hw, 206);
+            mbar_wait(&tfull[acc], acc_phase, hw, htag + 6);
             tc_fence_after();
             if (p.dbg_no_epi != 1) {
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + part * PX);
@@ -1142,7 +1228,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                         ss += __shfl_xor_sync(0xffffffffu, ss, m);
                     }
                     if ((lane & (CPG - 1)) == 0) {
-                        const size_t seg = (size_t)y * segs_row + xh * (256 / PX) + part;
+                        const size_t seg = (size_t)wrow * segs_row + wx / PX;
                         float2* out = reinterpret_cast<float2*>(p.gn_partial) +
                                       (((size_t)img * p.H * segs_row + seg) * 32 + chn / CPG);
                         *out = make_float2(s, ss);
@@ -1150,7 +1236,12 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            if constexpr (PAIR) {
+                if (crank != 0) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns both accumulators
+                else mbar_arrive(&tempty[acc]);
+            } else {
+                mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -1158,9 +1249,11 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -1221,20 +1314,28 @@ static volatile int* hang_word_device() {
 }
 int gemm_last_hang() { return g_hang_host ? *g_hang_host : 0; }
 
-// Is this op a dense 3x3 stride-1 convolution to 128 / 256 / 512 channels on rows that split into 256-pixel tiles?
-// (shape only: the fused-reduction fields are checked at launch)
-bool gemm_swapped_shape(const GemmOp& op) {
-    static const bool off = getenv("TML_NO_SWAP") && getenv("TML_NO_SWAP")[0] == '1';   // tuning switch
+// Is this op a dense 3x3 stride-1 convolution to 128 / 256 / 512 channels that the operand-swapped kernel tiles?
+// Returns 0 (no), 1 (rows split into 256-pixel tiles: one CTA per tile) or 2 (rows of 128-pixel segments, an even
+// number of rows, >= 256 channels: CTA pairs).  Shape only: the fused-reduction fields are checked at launch.
+static int swapped_kind(const GemmOp& op) {
+    static const bool off = getenv("TML_NO_SWAP") && getenv("TML_NO_SWAP")[0] == '1';            // tuning switch
+    static const bool no_pair = getenv("TML_NO_SWAP_PAIR") && getenv("TML_NO_SWAP_PAIR")[0] == '1';   // tuning switch
     static const int max_n = getenv("TML_SWAP_MAX_N") ? atoi(getenv("TML_SWAP_MAX_N")) : 512;   // tuning switch
     if (off || op.stride != 1 || op.ntaps != 9 || (op.N != 128 && op.N != 256 && op.N != 512) || op.N > max_n ||
-        op.OW % 256 != 0 || op.OW != op.A_W || op.OH != op.A_H || op.B_sBatch != 0 || op.dbg_shift != 0 ||
+        op.OW % 128 != 0 || op.OW != op.A_W || op.OH != op.A_H || op.B_sBatch != 0 || op.dbg_shift != 0 ||
         op.alpha != 1.0f || op.out_fp32 || op.D_sN != 1 || op.A_C % kBlockK != 0 || (op.n_store != 0 && op.n_store != op.N))
-        return false;
+        return 0;
     const int64_t sW = op.N, sH = (int64_t)op.OW * op.N, sB = (int64_t)op.OH * op.OW * op.N;
-    if (op.D_sW != sW || op.D_sH != sH || op.D_sB != sB) return false;
-    if (op.resid && (op.R_sW != sW || op.R_sH != sH || op.R_sB != sB)) return false;
-    return true;
+    if (op.D_sW != sW || op.D_sH != sH || op.D_sB != sB) return 0;
+    if (op.resid && (op.R_sW != sW || op.R_sH != sH || op.R_sB != sB)) return 0;
+    // measured in situ: pairs 1520-1610 TFLOP/s vs 1390-1500 for single CTAs on the 256-channel layers (a pair stages
+    // each input row once for 256 channels), so pairs are used wherever they apply
+    static const bool prefer_pair = !(getenv("TML_SWAP_PREFER_PAIR") && getenv("TML_SWAP_PREFER_PAIR")[0] == '0');   // tuning switch
+    const bool pair_ok = !no_pair && op.OH % 2 == 0 && op.N >= 256 && (long)op.A_B * (op.OH / 2) * (op.OW / 128) * (op.N / 256) >= 2;
+    if (op.OW % 256 == 0 && !(prefer_pair && pair_ok)) return 1;
+    return pair_ok ? 2 : 0;
 }
+bool gemm_swapped_shape(const GemmOp& op) { return swapped_kind(op) != 0; }
 static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
     if (!gemm_swapped_shape(op) || op.gn_mode < 0 || op.gn_mode > 2) return false;
     if (op.gn_mode != 0 && !op.gn_partial) return false;
@@ -1250,6 +1351,7 @@ static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
 
 static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num_sms, cudaStream_t stream) {
     int rc;
+    const bool pair = swapped_kind(op) == 2;
     CUtensorMap mapW, mapRow, mapTail;
     {
         cuuint64_t dims[3] = {(cuuint64_t)op.ntaps * op.A_C, (cuuint64_t)op.N, 1};
@@ -1260,7 +1362,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     {
         cuuint64_t dims[4] = {(cuuint64_t)op.A_C, (cuuint64_t)op.A_W, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
         cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, 256, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, pair ? 130u : 256u, 1, 1};
         if ((rc = encode_map(&mapRow, op.A, 4, dims, str, box, op.name))) return rc;
         box[1] = 2;
         if ((rc = encode_map(&mapTail, op.A, 4, dims, str, box, op.name))) return rc;
@@ -1277,43 +1379,62 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.hang_where = hang_word_device();
-    { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
+    { static const int mo = getenv("TML_DBG_MMA_ONLY") ? atoi(getenv("TML_DBG_MMA_ONLY")) : 0; p.dbg_mma_only = mo;   // 1 none, 2 no weights, 3 no rows
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne == 1 ? 1 : 0; }
     const int nc = op.N / 128;
-    const int total_tiles = op.A_B * op.OH * (op.OW / 256) * nc;
-    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    const int total_tiles = pair ? op.A_B * (op.OH / 2) * (op.OW / 128) * (nc / 2) : op.A_B * op.OH * (op.OW / 256) * nc;
+    int grid = pair ? (2 * total_tiles < num_sms ? 2 * total_tiles : (num_sms & ~1)) : (total_tiles < num_sms ? total_tiles : num_sms);
     const bool timed = g_timing && g_timed.size() < g_timing_cap;
     TimedLaunch tl;
     if (timed) {
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)op.N * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
-                 op.ntaps * op.A_C, 2000 + op.gn_mode * 10);
+                 op.ntaps * op.A_C, (pair ? 3000 : 2000) + op.gn_mode * 10);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;
     }
     {
         typedef void (*SwKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const SwParams);
-        static const SwKernel table[3][2][2] = {
-            {{conv3x3_swapped_kernel<1, false, false>, conv3x3_swapped_kernel<1, false, true>},
-             {conv3x3_swapped_kernel<1, true, false>, conv3x3_swapped_kernel<1, true, true>}},
-            {{conv3x3_swapped_kernel<2, false, false>, conv3x3_swapped_kernel<2, false, true>},
-             {conv3x3_swapped_kernel<2, true, false>, conv3x3_swapped_kernel<2, true, true>}},
-            {{conv3x3_swapped_kernel<4, false, false>, conv3x3_swapped_kernel<4, false, true>},
-             {conv3x3_swapped_kernel<4, true, false>, conv3x3_swapped_kernel<4, true, true>}}};
+#define SW_ROW(NC_, PAIR_)                                                                                   \
+    {{conv3x3_swapped_kernel<NC_, false, false, PAIR_>, conv3x3_swapped_kernel<NC_, false, true, PAIR_>},    \
+     {conv3x3_swapped_kernel<NC_, true, false, PAIR_>, conv3x3_swapped_kernel<NC_, true, true, PAIR_>}}
+        static const SwKernel table[3][2][2] = {SW_ROW(1, false), SW_ROW(2, false), SW_ROW(4, false)};
+        static const SwKernel ptable[2][2][2] = {SW_ROW(2, true), SW_ROW(4, true)};
+#undef SW_ROW
         static bool attr_set = false;
         if (!attr_set) {
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 2; ++b)
-                    for (int c = 0; c < 2; ++c) {
-                        cudaError_t e = cudaFuncSetAttribute(table[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem);
-                        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
-                    }
+            for (int b = 0; b < 2; ++b)
+                for (int c = 0; c < 2; ++c) {
+                    cudaError_t e = cudaSuccess;
+                    for (int a = 0; a < 3 && e == cudaSuccess; ++a)
+                        e = cudaFuncSetAttribute(table[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SwGeo<false>::kSmem);
+                    for (int a = 0; a < 2 && e == cudaSuccess; ++a)
+                        e = cudaFuncSetAttribute(ptable[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SwGeo<true>::kSmem);
+                    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+                }
             attr_set = true;
         }
-        const SwKernel k = table[nc == 1 ? 0 : nc == 2 ? 1 : 2][op.resid ? 1 : 0][op.gn_mode == 2 ? 1 : 0];
-        k<<<grid, op.gn_mode == 2 ? SwCfg<true>::kThreadsSw : SwCfg<false>::kThreadsSw, kSwSmem, stream>>>(mapW, mapRow, mapTail, p);
+        const int threads = op.gn_mode == 2 ? SwCfg<true>::kThreadsSw : SwCfg<false>::kThreadsSw;
+        const int ri = op.resid ? 1 : 0, gi = op.gn_mode == 2 ? 1 : 0;
+        if (pair) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = SwGeo<true>::kSmem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, ptable[nc == 2 ? 0 : 1][ri][gi], mapW, mapRow, mapTail, p);
+            if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
+        } else {
+            table[nc == 1 ? 0 : nc == 2 ? 1 : 2][ri][gi]<<<grid, threads, SwGeo<false>::kSmem, stream>>>(mapW, mapRow, mapTail, p);
+        }
     }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
