@@ -202,54 +202,53 @@ void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaSt
     COUNT_LAUNCH();
 }
 
-// per image: group mean / rstd, then per channel scale = rstd*gamma, shift = beta - mean*scale
+// per (image, group): mean / rstd, then per channel scale = rstd*gamma, shift = beta - mean*scale.
+// One block per (group, image): the partial list (up to 4096 entries per image for 512^2 layers) is summed by 256
+// threads in double precision and a fixed order (thread t takes entries t, t+256, ...; then a fixed tree).
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float2* __restrict__ ss,
                                                           float2* __restrict__ mr, int nchunks, int HW, int C,
                                                           float eps) {
-    __shared__ double red[8][32][2];
-    __shared__ float2 smr[32];
-    const int b = blockIdx.x;
-    {   // thread = (group, slice): 8 slices of the chunk list per group, combined in fixed order
-        const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
-        double s = 0.0, q = 0.0;
-        for (int c = sl; c < nchunks; c += 8) {
-            const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2);
-            s += (double)v.x;
-            q += (double)v.y;
-        }
-        red[sl][g][0] = s;
-        red[sl][g][1] = q;
+    __shared__ double red[33];
+    __shared__ float2 smr;
+    const int g = blockIdx.x, b = blockIdx.y;
+    double s = 0.0, q = 0.0;
+    for (int c = threadIdx.x; c < nchunks; c += 256) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2));
+        s += (double)v.x;
+        q += (double)v.y;
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int g = threadIdx.x;
-        double s = 0.0, q = 0.0;
-        for (int sl = 0; sl < 8; ++sl) { s += red[sl][g][0]; q += red[sl][g][1]; }
-        const double n = (double)HW * (C / 32);
+    s = block_sum_d(s, red);
+    q = block_sum_d(q, red);
+    const int cpg = C / 32;
+    if (threadIdx.x == 0) {
+        const double n = (double)HW * cpg;
         const double mean = s / n;
         double var = q / n - mean * mean;
         if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        smr[g] = make_float2((float)mean, rstd);
-        mr[(size_t)b * 32 + g] = smr[g];
+        smr = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        mr[(size_t)b * 32 + g] = smr;
     }
     __syncthreads();
-    const int cpg = C / 32;
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const float2 m = smr[c / cpg];
-        const float sc = m.y * gamma[c];
-        ss[(size_t)b * C + c] = make_float2(sc, beta[c] - m.x * sc);
+    if (threadIdx.x < cpg) {
+        const int c = g * cpg + threadIdx.x;
+        const float sc = smr.y * gamma[c];
+        ss[(size_t)b * C + c] = make_float2(sc, beta[c] - smr.x * sc);
     }
 }
 
 void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
                         int HW, int C, float eps, int nchunks, cudaStream_t s) {
-    gn_finalize_kernel<<<B, 256, 0, s>>>(partial, gamma, beta, ss, mr, nchunks, HW, C, eps);
+    gn_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partial, gamma, beta, ss, mr, nchunks, HW, C, eps);
     COUNT_LAUNCH();
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ss,
@@ -374,32 +373,33 @@ void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, cons
 
 __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial,
                                                               float2* __restrict__ mm, int nchunks, int HW, int C) {
-    __shared__ double red[8][32][2];
-    const int b = blockIdx.x;
-    const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    __shared__ double red[33];
+    const int g = blockIdx.x, b = blockIdx.y;   // one block per (group, image), same scheme as gn_finalize_kernel
     double s = 0.0, q = 0.0;
-    for (int c = sl; c < nchunks; c += 8) {
-        const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2);
+    for (int c = threadIdx.x; c < nchunks; c += 256) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((size_t)b * nchunks + c) * 32 + g) * 2));
         s += (double)v.x;
         q += (double)v.y;
     }
-    red[sl][g][0] = s;
-    red[sl][g][1] = q;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        s = 0.0; q = 0.0;
-        for (int k = 0; k < 8; ++k) { s += red[k][g][0]; q += red[k][g][1]; }
+    s = block_sum_d(s, red);
+    q = block_sum_d(q, red);
+    if (threadIdx.x == 0) {
         const double n = (double)HW * (C / 32);
         mm[(size_t)b * 32 + g] = make_float2((float)(s / n), (float)(q / n));
     }
 }
 
 void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, int nchunks, cudaStream_t s) {
-    gn_bwd_finalize_kernel<<<B, 256, 0, s>>>(partial, mm, nchunks, HW, C);
+    gn_bwd_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partial, mm, nchunks, HW, C);
     COUNT_LAUNCH();
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+// dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh)) [+ resid],  dxh = dy * act'(u) * gamma,  u = x*sc + sh,
+// xh = (x - mean) * rstd.  The kernel is instruction-bound before it is bandwidth-bound (3-4 streams of 2 B per
+// element), so the affine parts are folded into per-thread constants:
+//   dx = (rstd*gamma) * (dy * act'(u)) + (cx * x + c0),   cx = -rstd^2 * k.y,   c0 = rstd * (rstd*mean*k.y - k.x)
+// and the SiLU derivative is sg + u * sg * (1 - sg) with exp2 taking a pre-scaled argument.
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                            const float2* __restrict__ ss,
                                                            const float2* __restrict__ mr,
                                                            const float2* __restrict__ mm,
@@ -410,16 +410,19 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
     const int oct = threadIdx.x % C8, pl = threadIdx.x / C8;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * gn_pix_per_chunk(C), p1 = min(HW, p0 + gn_pix_per_chunk(C));
-    float sc[8], sh[8], gm[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float2 v = __ldg(&ss[(size_t)b * C + oct * 8 + j]);
-        sc[j] = v.x; sh[j] = v.y;
-        gm[j] = __ldg(&gamma[oct * 8 + j]);
-    }
     const int g_lo = (oct * 8) / cpg, g_hi = (oct * 8 + 4) / cpg;
     const float2 m_lo = __ldg(&mr[(size_t)b * 32 + g_lo]), m_hi = __ldg(&mr[(size_t)b * 32 + g_hi]);
     const float2 k_lo = __ldg(&mm[(size_t)b * 32 + g_lo]), k_hi = __ldg(&mm[(size_t)b * 32 + g_hi]);
+    float sc2[8], sh2[8], ag[8];
+    constexpr float kNegLog2e = -1.4426950408889634f, kNegLn2 = -0.6931471805599453f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 v = __ldg(&ss[(size_t)b * C + oct * 8 + j]);
+        sc2[j] = v.x * kNegLog2e; sh2[j] = v.y * kNegLog2e;   // t = -u*log2(e): exp(-u) = exp2(t), u = -ln2 * t
+        ag[j] = (j < 4 ? m_lo.y : m_hi.y) * __ldg(&gamma[oct * 8 + j]);
+    }
+    const float cx_lo = -m_lo.y * m_lo.y * k_lo.y, c0_lo = m_lo.y * (m_lo.y * m_lo.x * k_lo.y - k_lo.x);
+    const float cx_hi = -m_hi.y * m_hi.y * k_hi.y, c0_hi = m_hi.y * (m_hi.y * m_hi.x * k_hi.y - k_hi.x);
     const size_t base = (size_t)b * HW * C + (size_t)oct * 8;
     constexpr int U = 2;
     for (int p = p0 + pl; p < p1; p += PL * U) {
@@ -440,12 +443,13 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
             if (resid != nullptr) unpack8(ur[q], fr);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float u = fmaf(fx[j], sc[j], sh[j]);
-                const float dxh = fd[j] * dact(u, silu) * gm[j];
-                const float2 m = j < 4 ? m_lo : m_hi;
-                const float2 k = j < 4 ? k_lo : k_hi;
-                const float xh = (fx[j] - m.x) * m.y;
-                float v = m.y * (dxh - k.x - xh * k.y);
+                float d = fd[j];
+                if (silu) {
+                    const float t = fmaf(fx[j], sc2[j], sh2[j]);
+                    const float sg = __fdividef(1.f, 1.f + ex2_approx(t));
+                    d *= fmaf(t * kNegLn2, fmaf(-sg, sg, sg), sg);   // sg + u*sg*(1-sg)
+                }
+                float v = fmaf(ag[j], d, fmaf(j < 4 ? cx_lo : cx_hi, fx[j], j < 4 ? c0_lo : c0_hi));
                 if (resid != nullptr) v += fr[j];
                 o[j] = v;
             }
