@@ -336,7 +336,7 @@ def run_ours(args):
     achieved_tf = algo_flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else None
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel",
+        "bound": "tensor", "kernel": "conv3x3_swapped_kernel + conv_gemm_tcgen05_kernel (all tcgen05 GEMM launches)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",

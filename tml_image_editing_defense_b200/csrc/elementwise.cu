@@ -138,6 +138,40 @@ void launch_conv_in_im2col(const float* x, bf16* a, int B, int H, int W, cudaStr
     COUNT_LAUNCH();
 }
 
+// conv_in input gradient, step 2: gather the 9 shifted tap planes of each input channel (col2im).
+// Thread = one pixel (consecutive threads = consecutive w: every plane read is coalesced).
+__global__ void __launch_bounds__(256) conv_in_col2im_kernel(const float* __restrict__ y, float* __restrict__ dx, int H,
+                                                             int W, float beta) {
+    const int w = blockIdx.x * 256 + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+    if (w >= W) return;
+    const size_t plane = (size_t)H * W;
+    const float* yb = y + (size_t)b * 27 * plane;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hh = h - r + 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int ww = w - s + 1;
+            if (ww < 0 || ww >= W) continue;
+            const float* src = yb + (size_t)((r * 3 + s) * 3) * plane + (size_t)hh * W + ww;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) acc[ci] += __ldg(src + (size_t)ci * plane);
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        float* d = dx + ((size_t)(b * 3 + ci) * H + h) * W + w;
+        *d = beta != 0.f ? fmaf(beta, *d, acc[ci]) : acc[ci];
+    }
+}
+
+void launch_conv_in_col2im(const float* y, float* dx, int B, int H, int W, float beta, cudaStream_t s) {
+    conv_in_col2im_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, s>>>(y, dx, H, W, beta);
+    COUNT_LAUNCH();
+}
+
 // ================================================================================================
 // GroupNorm (32 groups, affine) [+ SiLU] over bf16 NHWC.   diffusers ResnetBlock2D.norm1/norm2,
 // Attention.group_norm, Encoder.conv_norm_out.

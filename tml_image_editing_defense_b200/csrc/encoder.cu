@@ -104,12 +104,15 @@ int tml_encoder_finalize(TmlEncoder* e, void* stream) {
         for (int co = 0; co < C0; ++co)
             for (int k = 0; k < 27; ++k) w64[(size_t)co * 64 + k] = w64[(size_t)co * 64 + 27 + k] = w->v[(size_t)co * 27 + k];
         RC(make_lin_from(e, w64, b->v, 64, C0, &e->conv_in_fwd));
-        // input gradient runs on the tensor cores: N = 3 padded to 16 (UMMA needs N % 16 == 0 at M = 128)
-        std::vector<float> w16((size_t)C0 * 16 * 9, 0.f);
+        // Input gradient: the output is only 3 channels wide, so the 3x3 dgrad as a K = 9*C0 GEMM with N padded to 16
+        // spends 144 tiny MMAs per 256 pixels.  Instead ONE K = C0 GEMM produces, per pixel, the 27 products
+        // Y[p][(r,s,ci)] = sum_co dy[p][co] * W[co][ci][r][s]  (N = 27 padded to 32, 8 MMAs per 128 pixels) into fp32
+        // planes, and a col2im kernel gathers dx[ci][h][w] = sum_{r,s} Y[(h-r+1, w-s+1)][(r,s,ci)].
+        std::vector<float> wt((size_t)32 * C0, 0.f), zb(32, 0.f);
         for (int co = 0; co < C0; ++co)
             for (int ci = 0; ci < 3; ++ci)
-                for (int k = 0; k < 9; ++k) w16[((size_t)co * 16 + ci) * 9 + k] = w->v[((size_t)co * 3 + ci) * 9 + k];
-        RC(make_packed(e, w16.data(), C0, 16, 1, &e->conv_in_bwd));
+                for (int k = 0; k < 9; ++k) wt[(size_t)(k * 3 + ci) * C0 + co] = w->v[((size_t)co * 3 + ci) * 9 + k];
+        RC(make_lin_from(e, wt, zb, C0, 32, &e->conv_in_bwd));
     }
     e->resnets.clear();
     e->downs.clear();
@@ -321,10 +324,14 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
     {   // conv_in input gradient -> fp32 NCHW image gradient (the tensor PGD consumes, main.py:176);
         // beta = 1 accumulates the grad_reps of main.py:88-102 in place.
         const int C0 = e->cfg.block_out_channels[0];
-        GemmOp o = dense_conv_op("conv_in.dgrad", G[cur], B, H, W, C0, e->conv_in_bwd, 16, 1, H, W, nullptr, nullptr, nullptr);
-        o.D = dx; o.out_fp32 = 1; o.n_store = 3; o.beta = beta;
-        o.D_sB = (int64_t)3 * H * W; o.D_sH = W; o.D_sW = 1; o.D_sN = (int64_t)H * W;
+        const size_t m = r.wsa.mark();
+        float* Y = r.Walloc<float>((size_t)B * 27 * H * W * sizeof(float));   // [B][27][H][W] tap products
+        GemmOp o = dense_lin_op("conv_in.dgrad", G[cur], B, H, W, C0, e->conv_in_bwd.fwd, 32, nullptr, nullptr, nullptr);
+        o.D = Y; o.out_fp32 = 1; o.n_store = 27;
+        o.D_sB = (int64_t)27 * H * W; o.D_sH = W; o.D_sW = 1; o.D_sN = (int64_t)H * W;
         RC(gemm_launch(o, e->num_sms, r.st));
+        launch_conv_in_col2im(Y, dx, B, H, W, beta, r.st);
+        r.wsa.reset(m);
     }
     if (r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     CUDA_OK(cudaGetLastError());

@@ -134,9 +134,11 @@ int gemm_gn_tiles_per_image(int OH, int OW) {
 }
 
 bool gemm_swapped_shape(const GemmOp& op);
+int sw_px_per_warp(bool gnb);
 // Partial-sum entries per image written by the fused GroupNorm reduction of this op.
 int gemm_gn_chunks_per_image(const GemmOp& op) {
-    if (op.gn_mode == 2 && gemm_swapped_shape(op)) return op.OH * op.OW / 64;   // 16-warp epilogue: 64-pixel segments
+    if (op.gn_mode != 0 && gemm_swapped_shape(op))   // one entry per epilogue warp's pixel range (64 or 128 pixels)
+        return op.OH * op.OW / (op.gn_mode == 2 ? sw_px_per_warp(true) : sw_px_per_warp(false));
     return gemm_gn_tiles_per_image(op.OH, op.OW);
 }
 
@@ -213,8 +215,8 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     int stage_bytes = t->mt * kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
     if (stages > 8) stages = 8;
-    int kblocks = op.ntaps * t->kchunks;
-    if (stages > kblocks && kblocks >= 2) stages = kblocks;
+    // (the ring runs across tiles: with short K it holds several tiles' operands, which is what hides the load latency
+    // of the memory-bound 1x1 / thin GEMMs -- capping it at one tile's k-blocks left them latency-bound)
     if (stages < 2) stages = 2;
     t->stages = stages;
     t->stage_bytes = stage_bytes;
@@ -895,12 +897,17 @@ struct SwParams {
 // The GNB instantiations run 16 epilogue warps (64 pixels each, 8-pixel steps, <= 102 registers) because their
 // epilogue is instruction-bound (exp + rcp + ~18 ALU ops per element): four warps per SM sub-partition instead of two
 // is what lets it finish inside the main loop of the next tile.  Their partial sums are per 64-pixel segment.
+#ifndef TML_SW_EPI16
+#define TML_SW_EPI16 0
+#endif
 template <bool GNB> struct SwCfg {
-    static constexpr int kEpiWarps = GNB ? 16 : 8;
+    static constexpr int kEpiWarps = (GNB || TML_SW_EPI16) ? 16 : 8;
     static constexpr int kThreadsSw = 128 + 32 * kEpiWarps;
     static constexpr int kPx = 256 / (kEpiWarps / 4);   // pixels per epilogue warp
     static constexpr int kStep = kPx / 8;               // pixels per tcgen05.ld
 };
+
+int sw_px_per_warp(bool gnb) { return gnb ? SwCfg<true>::kPx : SwCfg<false>::kPx; }
 
 // What one CTA does for tile number `tile`.
 struct SwTile {

@@ -212,7 +212,7 @@ struct TmlEncoder {
     std::vector<void*> dev_allocs;
     // parameters
     Lin conv_in_fwd;             // forward as a GEMM over im2col rows: [C0][64] = [w(27) | w(27) | 0]
-    Packed conv_in_bwd;          // dgrad as a GEMM: B[ci (3, padded to 16)][t*C0 + co]
+    Lin conv_in_bwd;             // input gradient, step 1: [32][C0], row (r*3+s)*3+ci = W[:, ci, r, s] (27 used)
     std::vector<Resnet> resnets;          // in forward order (down blocks then mid[0], mid[1])
     std::vector<Conv3> downs;
     bool has_attn = false;
@@ -537,7 +537,7 @@ static Partials fuse_stats(GemmOp& o, float* buf, int oh, int ow) {
     o.gn_partial = buf;
     Partials p;
     p.p = buf;
-    p.nchunks = gemm_gn_tiles_per_image(oh, ow);
+    p.nchunks = gemm_gn_chunks_per_image(o);
     return p;
 }
 // Ask a dgrad GEMM to also reduce the GroupNorm-backward sums of the norm whose output it differentiates.

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     for k, v in dict(B=16, H=128, W=128, Cin=512, N=512, iters=20, gn=0).items():
         ap.add_argument(f"--{k}", type=int, default=v)
+    ap.add_argument("--k1", action="store_true", help="1x1 convolution instead of 3x3")
     ap.add_argument("--resid", action="store_true")
     ap.add_argument("--bias", action="store_true")
     ap.add_argument("--tag", default="")
@@ -28,16 +29,17 @@ def main():
     lib = _lib.load()
     B, H, W, Cin, N = a.B, a.H, a.W, a.Cin, a.N
     A = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
-    Wm = (torch.randn(N, 9 * Cin, device=dev) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    T = 1 if a.k1 else 9
+    Wm = (torch.randn(N, T * Cin, device=dev) / (T * Cin) ** 0.5).to(torch.bfloat16)
     D = torch.empty(B, H, W, N, dtype=torch.bfloat16, device=dev)
     d = _lib.TmlGemmDesc()
     d.A = A.data_ptr(); d.A_C = Cin; d.A_W = W; d.A_H = H; d.A_B = B
     d.A_sW = Cin; d.A_sH = W * Cin; d.A_sB = H * W * Cin
-    d.stride = 1; d.ntaps = 9
-    for t in range(9):
-        d.dh[t] = t // 3 - 1; d.dw[t] = t % 3 - 1
+    d.stride = 1; d.ntaps = T
+    for t in range(T):
+        d.dh[t] = (t // 3 - 1) if T == 9 else 0; d.dw[t] = (t % 3 - 1) if T == 9 else 0
     d.OW = W; d.OH = H
-    d.Bm = Wm.data_ptr(); d.N = N; d.B_sN = 9 * Cin; d.B_sBatch = 0; d.alpha = 1.0
+    d.Bm = Wm.data_ptr(); d.N = N; d.B_sN = T * Cin; d.B_sBatch = 0; d.alpha = 1.0
     keep = []
     if a.bias:
         keep.append(torch.randn(N, device=dev)); d.bias = keep[-1].data_ptr()
@@ -67,8 +69,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
-    fl = 2.0 * B * H * W * N * 9 * Cin
-    print(f"{a.tag:28s} B={B} {H}x{W} {Cin}->{N} res={int(a.resid)} gn={a.gn}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    fl = 2.0 * B * H * W * N * T * Cin
+    print(f"{a.tag:28s} B={B} {H}x{W} {Cin}->{N} res={int(a.resid)} gn={a.gn}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  out {B * H * W * N * 2 / ms / 1e6:.0f} GB/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,7 @@
-M="python tools/gemm_micro.py --B 16 --H 128 --W 128 --Cin 512 --N 512 --bias"
-timeout 60 $M --tag pair_full
-TML_DBG_NO_EPI=1 timeout 60 $M --tag pair_noepi
-TML_DBG_MMA_ONLY=1 timeout 60 $M --tag pair_noloads
-TML_NO_SWAP_PAIR=1 timeout 60 $M --tag old_full
-timeout 60 $M --resid --gn 1 --tag pair_res_stats
-timeout 60 $M --gn 2 --tag pair_gnbwd
+M="python tools/gemm_micro.py --B 16 --H 512 --W 512 --Cin 64 --N 128 --bias"
+timeout 60 $M --tag sw_k576_bias
+timeout 60 $M --gn 1 --tag sw_k576_bias_stats
+timeout 60 $M --gn 1 --resid --tag sw_k576_res_stats
+M="python tools/gemm_micro.py --B 16 --H 512 --W 512 --Cin 128 --N 128 --bias"
+timeout 60 $M --gn 1 --tag sw_k1152_bias_stats
+timeout 60 $M --gn 1 --resid --tag sw_k1152_res_stats
