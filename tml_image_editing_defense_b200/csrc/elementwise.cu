@@ -1,4 +1,4 @@
-// Bandwidth-bound kernels of the PGD hot path: conv_in im2col (hi/lo bf16 split of the fp32 image), GroupNorm
+// Bandwidth-bound kernels of the PGD hot path: conv_in pack (hi/lo bf16 split of the fp32 image) / col2im, GroupNorm
 // (+SiLU) forward / backward, softmax forward / backward, transposes, posterior sample + latent loss
 // gradient, and the fused PGD updates.  All reductions are two-stage with a fixed order, so results
 // are bitwise reproducible run to run and independent of how images are sharded over GPUs.
@@ -94,47 +94,39 @@ __device__ __forceinline__ float block_max(float v, float* red /*[33]*/) {
 }
 
 // ================================================================================================
-// conv_in forward, step 1: fp32 NCHW [B,3,H,W] -> im2col rows bf16 [B*H*W][64]   (diffusers
-// encoder.conv_in, reached from main.py:191).  Row layout, k = ci*9 + r*3 + s:
-//   [0,27)  hi = bf16(x)          [27,54)  lo = bf16(x - hi)          [54,64)  zero
-// The tensor-core GEMM that follows multiplies both halves by the same bf16 weights, so the image enters with
-// ~16 mantissa bits: a PGD step of 2/255 on a pixel near 1.0 is one bf16 ulp and would vanish with hi alone.
-// One row is one 128-byte swizzle row of the GEMM's A operand (K = 64).
-// Block: 64 pixels of one image row; 4 threads per pixel, 32 bytes each.
+// conv_in forward, step 1: fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64]   (diffusers encoder.conv_in,
+// reached from main.py:191).  Channels: [0,3) hi = bf16(x), [3,6) lo = bf16(x - hi), [6,64) zero.
+// The 3x3 tensor-core convolution that follows carries the same bf16 weights on channels c and c+3, so the image
+// enters with ~16 mantissa bits: a PGD step of 2/255 on a pixel near 1.0 is one bf16 ulp and would vanish with hi
+// alone.  64 channels = one 128-byte swizzle row = the minimum K chunk of the GEMM kernels.
+// Thread = (pixel, 16-byte octet): octet 0 carries the data, octets 1..7 are zeros; a warp writes 512 contiguous bytes.
 // ================================================================================================
-__global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H,
-                                                             int W) {
-    __shared__ uint16_t sp[2][9][66];  // [hi|lo][ci*3 + r][column]
-    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < 9 * 66; i += 256) {
-        const int col = i % 66, cr = i / 66, ci = cr / 3, r = cr % 3;
-        const int ih = h + r - 1, iw = w0 + col - 1;
-        float v = 0.f;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(&x[((size_t)(b * 3 + ci) * H + ih) * W + iw]);
-        const bf16 hi = __float2bfloat16_rn(v);
-        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        sp[0][cr][col] = __bfloat16_as_ushort(hi);
-        sp[1][cr][col] = __bfloat16_as_ushort(lo);
-    }
-    __syncthreads();
-    const int p = threadIdx.x >> 2, q = threadIdx.x & 3;
-    if (w0 + p >= W) return;
-    auto elem = [&](int k) -> uint32_t {
-        if (k >= 54) return 0u;
-        const int part = k >= 27 ? 1 : 0, kk = k - 27 * part;
-        return sp[part][kk / 3][p + kk % 3];
-    };
-    uint32_t o[8];
+__global__ void __launch_bounds__(256) conv_in_pack_kernel(const float* __restrict__ x, bf16* __restrict__ a, int HW,
+                                                           long long total_px) {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long px = t >> 3;
+    if (px >= total_px) return;
+    const int oct = (int)(t & 7);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (oct == 0) {
+        const long long b = px / HW, p = px - b * HW;
+        const float* src = x + (size_t)b * 3 * HW + p;
+        uint32_t hi[3], lo[3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = elem(q * 16 + 2 * j) | (elem(q * 16 + 2 * j + 1) << 16);
-    uint4* dst = reinterpret_cast<uint4*>(a + (((size_t)b * H + h) * W + w0 + p) * 64 + q * 16);
-    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(src + (size_t)c * HW);
+            const bf16 h = __float2bfloat16_rn(v);
+            hi[c] = __bfloat16_as_ushort(h);
+            lo[c] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+        }
+        o = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (lo[0] << 16), lo[1] | (lo[2] << 16), 0u);
+    }
+    *reinterpret_cast<uint4*>(a + (size_t)px * 64 + oct * 8) = o;
 }
 
-void launch_conv_in_im2col(const float* x, bf16* a, int B, int H, int W, cudaStream_t s) {
-    dim3 grid((W + 63) / 64, H, B);
-    conv_in_im2col_kernel<<<grid, 256, 0, s>>>(x, a, H, W);
+void launch_conv_in_pack(const float* x, bf16* a, int B, int H, int W, cudaStream_t s) {
+    const long long total_px = (long long)B * H * W;
+    conv_in_pack_kernel<<<(unsigned)((total_px * 8 + 255) / 256), 256, 0, s>>>(x, a, H * W, total_px);
     COUNT_LAUNCH();
 }
 

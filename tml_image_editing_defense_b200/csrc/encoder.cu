@@ -95,15 +95,20 @@ int tml_encoder_finalize(TmlEncoder* e, void* stream) {
     CUDA_OK(cudaSetDevice(e->device));
     const TmlEncoderCfg& c = e->cfg;
     const int C0 = c.block_out_channels[0];
-    {   // conv_in forward as a K=64 GEMM over im2col rows [hi(27) | lo(27) | 0(10)]: both halves see the same weights
+    {   // conv_in forward as a 3x3 convolution over a 64-channel image [hi(3) | lo(3) | 0(58)]: both halves see the same weights
         if (c.in_channels != 3) { set_error("in_channels must be 3 (got %d)", c.in_channels); return -22; }
         const HostTensor* w = find(e, "encoder.conv_in.weight", (size_t)C0 * 27);
         const HostTensor* b = find(e, "encoder.conv_in.bias", C0);
         if (!w || !b) return -20;
-        std::vector<float> w64((size_t)C0 * 64, 0.f);
+        std::vector<float> w64((size_t)C0 * 64 * 9, 0.f);
         for (int co = 0; co < C0; ++co)
-            for (int k = 0; k < 27; ++k) w64[(size_t)co * 64 + k] = w64[(size_t)co * 64 + 27 + k] = w->v[(size_t)co * 27 + k];
-        RC(make_lin_from(e, w64, b->v, 64, C0, &e->conv_in_fwd));
+            for (int ci = 0; ci < 3; ++ci)
+                for (int k = 0; k < 9; ++k)
+                    w64[((size_t)co * 64 + ci) * 9 + k] = w64[((size_t)co * 64 + ci + 3) * 9 + k] = w->v[((size_t)co * 3 + ci) * 9 + k];
+        Conv3& ci3 = e->conv_in_fwd;
+        ci3.ci = 64; ci3.co = C0; ci3.stride = 1;
+        RC(make_packed(e, w64.data(), C0, 64, 0, &ci3.fwd));
+        RC(upload<float>(e, b->v, &ci3.bias));
         // Input gradient: the output is only 3 channels wide, so the 3x3 dgrad as a K = 9*C0 GEMM with N padded to 16
         // spends 144 tiny MMAs per 256 pixels.  Instead ONE K = C0 GEMM produces, per pixel, the 27 products
         // Y[p][(r,s,ci)] = sum_co dy[p][co] * W[co][ci][r][s]  (N = 27 padded to 32, 8 MMAs per 128 pixels) into fp32
@@ -215,12 +220,12 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
     const int C0 = e->cfg.block_out_channels[0];
     r.statbuf[0] = r.Walloc<float>(fused_partial_bytes(B, H, W));
     r.statbuf[1] = r.Walloc<float>(fused_partial_bytes(B, H, W));
-    {   // conv_in: im2col (hi/lo bf16 split of the fp32 image) + K=64 GEMM with the GroupNorm statistics fused
+    {   // conv_in: pack (hi/lo bf16 split of the fp32 image, 64 channels) + 3x3 convolution with the statistics fused
         const size_t m = r.wsa.mark();
-        bf16* cols = r.Walloc<bf16>(act_bytes(B, H, W, 64));
-        launch_conv_in_im2col(x, cols, B, H, W, r.st);
-        GemmOp ci = dense_lin_op("conv_in", cols, B, H, W, 64, e->conv_in_fwd.fwd, C0, e->conv_in_fwd.bias, nullptr,
-                                 r.S<bf16>(L.x0));
+        bf16* xp = r.Walloc<bf16>(act_bytes(B, H, W, 64));
+        launch_conv_in_pack(x, xp, B, H, W, r.st);
+        GemmOp ci = dense_conv_op("conv_in", xp, B, H, W, 64, e->conv_in_fwd.fwd, C0, 1, H, W, e->conv_in_fwd.bias, nullptr,
+                                  r.S<bf16>(L.x0));
         r.pending = fuse_stats(ci, r.statbuf[1], H, W);
         RC(gemm_launch(ci, e->num_sms, r.st));
         r.wsa.reset(m);

@@ -1189,7 +1189,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                     float f = __uint_as_float(v[j]) + bias_c;
                     if constexpr (RES) f += __uint_as_float(uint32_t(r[j]) << 16);
                     const __nv_bfloat16 b = __float2bfloat16_rn(f);
-                    dp[(size_t)(k * STEP + j) * N] = b;
+                    if (p.dbg_no_epi != 2) dp[(size_t)(k * STEP + j) * N] = b;
                     const float fr = __bfloat162float(b);   // reductions see the values as stored
                     if constexpr (GNB) {
                         // GroupNorm backward: dxh = dy * act'(x*sc+sh) * gamma; sums of dxh and dxh*x
@@ -1387,7 +1387,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.hang_where = hang_word_device();
     { static const int mo = getenv("TML_DBG_MMA_ONLY") ? atoi(getenv("TML_DBG_MMA_ONLY")) : 0; p.dbg_mma_only = mo;   // 1 none, 2 no weights, 3 no rows
-      static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne == 1 ? 1 : 0; }
+      static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = (ne == 1 || ne == 2) ? ne : 0; }
     const int nc = op.N / 128;
     const int total_tiles = pair ? op.A_B * (op.OH / 2) * (op.OW / 128) * (nc / 2) : op.A_B * op.OH * (op.OW / 256) * nc;
     int grid = pair ? (2 * total_tiles < num_sms ? 2 * total_tiles : (num_sms & ~1)) : (total_tiles < num_sms ? total_tiles : num_sms);

@@ -63,7 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
     const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+        if ((++spins & 1023u) != 0) continue;   // (keeps the timer read out of the common iteration)
+        if (global_timer_ns() - t0 > 2000000000ull) {
             if (where) { *where = tag; __threadfence_system(); }
             __trap();
         }

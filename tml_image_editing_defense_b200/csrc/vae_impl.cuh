@@ -211,7 +211,7 @@ struct TmlEncoder {
     std::map<std::string, HostTensor> host;
     std::vector<void*> dev_allocs;
     // parameters
-    Lin conv_in_fwd;             // forward as a GEMM over im2col rows: [C0][64] = [w(27) | w(27) | 0]
+    Conv3 conv_in_fwd;           // forward as a 3x3 conv over 64 channels [hi(3) | lo(3) | 0]: weights on c and c+3
     Lin conv_in_bwd;             // input gradient, step 1: [32][C0], row (r*3+s)*3+ci = W[:, ci, r, s] (27 used)
     std::vector<Resnet> resnets;          // in forward order (down blocks then mid[0], mid[1])
     std::vector<Conv3> downs;
