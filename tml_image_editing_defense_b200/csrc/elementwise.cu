@@ -130,37 +130,40 @@ void launch_conv_in_pack(const float* x, bf16* a, int B, int H, int W, cudaStrea
     COUNT_LAUNCH();
 }
 
-// conv_in input gradient, step 2: gather the 9 shifted tap planes of each input channel (col2im).
-// Thread = one pixel (consecutive threads = consecutive w: every plane read is coalesced).
+// conv_in input gradient, step 2 (col2im): y [B][H][W][32] fp32 tap products, entry (r*3+s)*3+ci of pixel p is
+// sum_co dy[p][co] * W[co][ci][r][s];  dx[ci][h][w] = sum_{r,s} y[(h-r+1, w-s+1)][(r*3+s)*3+ci].
+// Block = 64 pixels of one row: the 3 x 66 neighbouring lines are staged in shared memory with coalesced 16-byte
+// loads, then thread = (pixel, channel) sums its nine entries.
 __global__ void __launch_bounds__(256) conv_in_col2im_kernel(const float* __restrict__ y, float* __restrict__ dx, int H,
                                                              int W, float beta) {
-    const int w = blockIdx.x * 256 + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
-    if (w >= W) return;
-    const size_t plane = (size_t)H * W;
-    const float* yb = y + (size_t)b * 27 * plane;
-    float acc[3] = {0.f, 0.f, 0.f};
+    __shared__ float sy[3][66][33];   // [row h-1..h+1][pixel w0-1..w0+64][32 floats + 1 pad: conflict-free column reads]
+    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 3 * 66 * 8; i += 256) {
+        const int v = i & 7, col = (i >> 3) % 66, rr = i / (66 * 8);
+        const int hh = h + rr - 1, ww = w0 + col - 1;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            t = __ldg(reinterpret_cast<const float4*>(y + (((size_t)b * H + hh) * W + ww) * 32) + v);
+        float* dst = &sy[rr][col][4 * v];
+        dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+    }
+    __syncthreads();
+    const int px = threadIdx.x & 63, ci = threadIdx.x >> 6;   // 64 pixels x (3 channels + one idle quarter)
+    if (ci >= 3 || w0 + px >= W) return;
+    float acc = 0.f;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int hh = h - r + 1;
-        if (hh < 0 || hh >= H) continue;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-            const int ww = w - s + 1;
-            if (ww < 0 || ww >= W) continue;
-            const float* src = yb + (size_t)((r * 3 + s) * 3) * plane + (size_t)hh * W + ww;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) acc[ci] += __ldg(src + (size_t)ci * plane);
+            // source pixel (h - r + 1, w - s + 1) -> staged row (2 - r), column px + 1 - s + 1
+            acc += sy[2 - r][px + 2 - s][(r * 3 + s) * 3 + ci];
         }
-    }
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-        float* d = dx + ((size_t)(b * 3 + ci) * H + h) * W + w;
-        *d = beta != 0.f ? fmaf(beta, *d, acc[ci]) : acc[ci];
-    }
+    float* d = dx + ((size_t)(b * 3 + ci) * H + h) * W + w0 + px;
+    *d = beta != 0.f ? fmaf(beta, *d, acc) : acc;
 }
 
 void launch_conv_in_col2im(const float* y, float* dx, int B, int H, int W, float beta, cudaStream_t s) {
-    conv_in_col2im_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, s>>>(y, dx, H, W, beta);
+    conv_in_col2im_kernel<<<dim3((W + 63) / 64, H, B), 256, 0, s>>>(y, dx, H, W, beta);
     COUNT_LAUNCH();
 }
 

@@ -330,10 +330,9 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
         // beta = 1 accumulates the grad_reps of main.py:88-102 in place.
         const int C0 = e->cfg.block_out_channels[0];
         const size_t m = r.wsa.mark();
-        float* Y = r.Walloc<float>((size_t)B * 27 * H * W * sizeof(float));   // [B][27][H][W] tap products
+        float* Y = r.Walloc<float>((size_t)B * H * W * 32 * sizeof(float));   // [B][H][W][32] tap products (27 used)
         GemmOp o = dense_lin_op("conv_in.dgrad", G[cur], B, H, W, C0, e->conv_in_bwd.fwd, 32, nullptr, nullptr, nullptr);
-        o.D = Y; o.out_fp32 = 1; o.n_store = 27;
-        o.D_sB = (int64_t)27 * H * W; o.D_sH = W; o.D_sW = 1; o.D_sN = (int64_t)H * W;
+        o.D = Y; o.out_fp32 = 1;   // dense rows of 32 floats = one 128-byte line per pixel
         RC(gemm_launch(o, e->num_sms, r.st));
         launch_conv_in_col2im(Y, dx, B, H, W, beta, r.st);
         r.wsa.reset(m);

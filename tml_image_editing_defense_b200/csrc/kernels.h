@@ -11,8 +11,8 @@ typedef __nv_bfloat16 bf16;
 // conv_in (3 -> C0, 3x3 s1 p1), step 1: fp32 NCHW image -> bf16 NHWC [B,H,W,64]
 // (channels [0,3) hi = bf16(x), [3,6) lo = bf16(x - hi), rest 0); step 2 is a 3x3 convolution on the GEMM kernels.
 void launch_conv_in_pack(const float* x, bf16* a, int B, int H, int W, cudaStream_t s);
-// conv_in input gradient, step 2 (col2im): y [B][27][H][W] fp32 tap products (plane (r*3+s)*3+ci) ->
-// dx[b][ci][h][w] = beta*dx + sum_{r,s} y[b][(r*3+s)*3+ci][h-r+1][w-s+1]   (zero outside the image)
+// conv_in input gradient, step 2 (col2im): y [B][H][W][32] fp32 tap products (entry (r*3+s)*3+ci) ->
+// dx[b][ci][h][w] = beta*dx + sum_{r,s} y[b][h-r+1][w-s+1][(r*3+s)*3+ci]   (zero outside the image)
 void launch_conv_in_col2im(const float* y, float* dx, int B, int H, int W, float beta, cudaStream_t s);
 
 // GroupNorm(32 groups) over bf16 [B, HW, C].
