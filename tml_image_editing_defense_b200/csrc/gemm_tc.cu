@@ -315,12 +315,21 @@ __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(_
 template <int NC>
 __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, float (&f)[NC],
                                                const uint4 (&rres)[4], bool valid, long long d_off, int n0) {
+    if (p.alpha != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
+    }
     if (!valid) return;
     if (p.bias != nullptr) {
+        // n0 is a multiple of 16: 16-byte loads (the same addresses for every lane: one L1 line per instruction)
 #pragma unroll
-        for (int j = 0; j < NC; ++j) f[j] += __ldg(p.bias + n0 + j);
+        for (int j = 0; j < NC / 4; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+        }
     }
     if (p.resid != nullptr) {
 #pragma unroll
@@ -348,8 +357,10 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
             for (int j = 0; j < NC / 8; ++j) {
                 o[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                f[8 * j + 0] = bf16_lo(o[j].x); f[8 * j + 1] = bf16_hi(o[j].x); f[8 * j + 2] = bf16_lo(o[j].y); f[8 * j + 3] = bf16_hi(o[j].y);
-                f[8 * j + 4] = bf16_lo(o[j].z); f[8 * j + 5] = bf16_hi(o[j].z); f[8 * j + 6] = bf16_lo(o[j].w); f[8 * j + 7] = bf16_hi(o[j].w);
+                if (p.gn_mode != 0) {   // the fused reductions see the values as stored
+                    f[8 * j + 0] = bf16_lo(o[j].x); f[8 * j + 1] = bf16_hi(o[j].x); f[8 * j + 2] = bf16_lo(o[j].y); f[8 * j + 3] = bf16_hi(o[j].y);
+                    f[8 * j + 4] = bf16_lo(o[j].z); f[8 * j + 5] = bf16_hi(o[j].z); f[8 * j + 6] = bf16_lo(o[j].w); f[8 * j + 7] = bf16_hi(o[j].w);
+                }
             }
             // full 32-byte sectors per lane (a 16-byte store would leave every sector half written)
 #pragma unroll
