@@ -192,9 +192,8 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
         t->mt = (BN <= 128 && op.OH % 2 == 0) ? 2 : 1;
         t->halo_bytes = (((t->mt + 2) * 130 * 128) + 1023) / 1024 * 1024;
         // CTA pairs (cta_group::2, M = 256 over two SMs): each CTA stages its own halo tile and half of every
-        // weight tile.  Correct (tests run it) but OFF by default: measured on B200 the MMA-only ceiling is the
-        // same as cta_group::1 (1160 / 1590 TFLOP/s at N = 128 / 256: the power-limited tensor peak, not shared-
-        // memory bandwidth), while the cross-CTA barrier round trips make the real kernel 25-35 % slower.
+        // weight tile.  Correct (tests run it); off by default here because the layers that would profit run on the
+        // operand-swapped kernel (TML_PAIR=1 switches it on for what is left in halo mode).
         static const bool use_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '1';   // experiment switch
         const long cta_m_tiles = (long)op.A_B * (op.OH / t->mt) * t->tiles_w;
         t->pair = (use_pair && cta_m_tiles % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
@@ -212,7 +211,13 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     const long sub_tiles = (long)op.A_B * t->tiles_h * t->tiles_w;
     static const bool no_mt2 = getenv("TML_NO_MT2") && getenv("TML_NO_MT2")[0] == '1';   // tuning switch
     t->mt = (!no_mt2 && BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
-    int stage_bytes = t->mt * kATileBytes + ((BN * 128 + 1023) / 1024) * 1024;
+    // CTA pairs for the weight-heavy long-K tiles (BN = 256, K >= 2048: the 512-channel convolutions at 64^2): M = 256
+    // pixels over two SMs, each CTA stages its own 128 pixels and HALF of every weight tile, which cuts the L2 -> SM
+    // traffic that bounds these layers by a third (48 -> 32 KB per four MMAs).
+    static const bool no_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
+    t->pair = (!no_pair && op.stride == 1 && op.B_sBatch == 0 && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
+               t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
+    int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
     if (stages > 8) stages = 8;
     // (the ring runs across tiles: with short K it holds several tiles' operands, which is what hides the load latency
@@ -483,17 +488,18 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         tma_prefetch_desc(&mapB);
     }
     if (warp == 1 && lane == 0) {
-        // pair mode: the "full" barriers live in the leader CTA and collect one arrival per CTA plus the
-        // transaction bytes of both CTAs' TMA loads; the accumulator-empty barrier collects both epilogues
+        // pair mode: the "full" barriers live in the leader CTA: ONE arrival (the leader's) plus the transaction
+        // bytes of both CTAs' TMA loads -- a per-stage remote arrive by the follower's producer throttles it to one
+        // stage per cross-SM round trip; the accumulator-empty barrier collects both epilogues
         const uint32_t nprod = PAIR ? 2u : 1u;
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], nprod);
+            mbar_init(&full_bar[s], 1);      // pair mode: the leader's arrival announces both CTAs' bytes (see below)
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], kEpiThreads * nprod);
-            mbar_init(&hfull_bar[a], nprod);
+            mbar_init(&hfull_bar[a], 1);
             mbar_init(&hempty_bar[a], 1);
         }
         fence_mbar_init();
@@ -538,13 +544,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             mbar_wait(&empty_bar[stage], phase ^ 1u, hw, htag + 1);
                             if constexpr (PAIR) {
                                 if (p.dbg_mma_only && (phase != 0 || tile != tile0)) {
-                                    if (crank == 0) mbar_arrive(&full_bar[stage]); else mbar_arrive_remote(&full_bar[stage], 0);
+                                    if (crank == 0) mbar_arrive(&full_bar[stage]);
                                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                                     continue;
                                 }
                                 // each CTA stages its half of the weight tile; bytes are counted on the leader's barrier
                                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], uint32_t(p.BN) * 128u);
-                                else mbar_arrive_remote(&full_bar[stage], 0);
                                 tma_load_3d_2sm(ring + size_t(stage) * p.stage_bytes, &mapB, &full_bar[stage],
                                                 (tap * p.kchunks + ch) * kBlockK, nt * p.BN + int(crank) * (p.BN / 2), 0);
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -566,6 +571,19 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     const int c0 = (kb - tap * p.kchunks) * kBlockK;
                     uint8_t* sA = ring + size_t(stage) * p.stage_bytes;
                     uint8_t* sB = sA + a_bytes;
+                    if constexpr (PAIR) {
+                        // pairs (stride 1, one sub-tile): each CTA stages its own 128 pixels (its half of M = 256) and
+                        // its half of the weight tile; the leader alone arrives, announcing both CTAs' bytes
+                        if (p.dbg_mma_only && (phase != 0 || tile != tile0)) {
+                            if (crank == 0) mbar_arrive(&full_bar[stage]);
+                        } else {
+                            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u);
+                            tma_load_4d_2sm(sA, &mapA, &full_bar[stage], c0, sb[0].ow0 + p.dw[tap], sb[0].oh0 + p.dh[tap], sb[0].img);
+                            tma_load_3d_2sm(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN + int(crank) * (p.BN / 2), 0);
+                        }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     if (p.dbg_mma_only && (phase != 0 || tile != tile0)) { mbar_arrive(&full_bar[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
@@ -597,13 +615,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     mbar_wait(&hempty_bar[hs], hphase ^ 1u, hw, htag + 2);
                     if constexpr (PAIR) {
                         if (p.dbg_mma_only && (hphase != 0 || tile != tile0)) {
-                            if (crank == 0) mbar_arrive(&hfull_bar[hs]); else mbar_arrive_remote(&hfull_bar[hs], 0);
+                            if (crank == 0) mbar_arrive(&hfull_bar[hs]);
                             hs ^= 1;
                             if (hs == 0) hphase ^= 1u;
                             continue;
                         }
                         if (crank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], 2u * halo_tx);
-                        else mbar_arrive_remote(&hfull_bar[hs], 0);
                         tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
                                         s0.oh0 - 1, s0.img);
                         hs ^= 1;
@@ -688,16 +705,24 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         if (p.dbg_bo) a_desc0 |= uint64_t(((a_addr + uint32_t(p.dbg_shift) * 128u) >> 7) & 7u) << 49;
                         const uint32_t first = kb != 0 ? 1u : 0u;
                         if (elect_one()) {
-                            for (int sub = 0; sub < p.mt; ++sub) {
-                                const uint64_t a_desc = a_desc0 + uint64_t(sub * (kATileBytes >> 4));
-                                const uint32_t d = d_tmem + uint32_t(sub * p.BN);
-                                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
-                                umma_bf16(d, a_desc, b_desc, idesc, first);
-                                umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
-                                umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
-                                umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                            if constexpr (PAIR) {
+                                umma_bf16_2sm(d_tmem, a_desc0, b_desc, idesc, first);
+                                umma_bf16_2sm(d_tmem, a_desc0 + 2, b_desc + 2, idesc, 1u);
+                                umma_bf16_2sm(d_tmem, a_desc0 + 4, b_desc + 4, idesc, 1u);
+                                umma_bf16_2sm(d_tmem, a_desc0 + 6, b_desc + 6, idesc, 1u);
+                                umma_commit_2sm(&empty_bar[stage], 3);
+                            } else {
+                                for (int sub = 0; sub < p.mt; ++sub) {
+                                    const uint64_t a_desc = a_desc0 + uint64_t(sub * (kATileBytes >> 4));
+                                    const uint32_t d = d_tmem + uint32_t(sub * p.BN);
+                                    // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
+                                    umma_bf16(d, a_desc, b_desc, idesc, first);
+                                    umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
+                                    umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
+                                    umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                }
+                                umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
                             }
-                            umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
                         }
                         __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
