@@ -215,7 +215,9 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // pixels over two SMs, each CTA stages its own 128 pixels and HALF of every weight tile, which cuts the L2 -> SM
     // traffic that bounds these layers by a third (48 -> 32 KB per four MMAs).
     static const bool no_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
-    t->pair = (!no_pair && op.stride == 1 && op.B_sBatch == 0 && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
+    // (a per-image B operand is fine when both CTAs of a pair always work on the same image)
+    const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
+    t->pair = (!no_pair && op.stride == 1 && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
@@ -579,7 +581,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         } else {
                             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u);
                             tma_load_4d_2sm(sA, &mapA, &full_bar[stage], c0, sb[0].ow0 + p.dw[tap], sb[0].oh0 + p.dh[tap], sb[0].img);
-                            tma_load_3d_2sm(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN + int(crank) * (p.BN / 2), 0);
+                            tma_load_3d_2sm(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN + int(crank) * (p.BN / 2),
+                                            p.b_batched ? sb[0].img : 0);
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         continue;
