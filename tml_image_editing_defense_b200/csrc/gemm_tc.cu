@@ -217,7 +217,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     static const bool no_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
     // (a per-image B operand is fine when both CTAs of a pair always work on the same image)
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
-    t->pair = (!no_pair && op.stride == 1 && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
+    t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
@@ -574,13 +574,20 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     uint8_t* sA = ring + size_t(stage) * p.stage_bytes;
                     uint8_t* sB = sA + a_bytes;
                     if constexpr (PAIR) {
-                        // pairs (stride 1, one sub-tile): each CTA stages its own 128 pixels (its half of M = 256) and
+                        // pairs (one sub-tile): each CTA stages its own 128 pixels (its half of M = 256) and
                         // its half of the weight tile; the leader alone arrives, announcing both CTAs' bytes
                         if (p.dbg_mma_only && (phase != 0 || tile != tile0)) {
                             if (crank == 0) mbar_arrive(&full_bar[stage]);
                         } else {
                             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u);
-                            tma_load_4d_2sm(sA, &mapA, &full_bar[stage], c0, sb[0].ow0 + p.dw[tap], sb[0].oh0 + p.dh[tap], sb[0].img);
+                            if (p.mode == 0) {
+                                tma_load_4d_2sm(sA, &mapA, &full_bar[stage], c0, sb[0].ow0 + p.dw[tap], sb[0].oh0 + p.dh[tap], sb[0].img);
+                            } else {
+                                const int dw = p.dw[tap], dh = p.dh[tap];
+                                for (int i = 0; i < p.TH; ++i)
+                                    tma_load_5d_2sm(sA + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
+                                                    sb[0].ow0 + (dw >> 1), 2 * (sb[0].oh0 + i) + dh, sb[0].img);
+                            }
                             tma_load_3d_2sm(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN + int(crank) * (p.BN / 2),
                                             p.b_batched ? sb[0].img : 0);
                         }
