@@ -194,6 +194,40 @@ def test_grad_cosine_512_vs_oracle_on_gpu(dev, models):
     torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
 
 
+def test_512_step_runs_on_the_fast_kernels(dev, models):
+    """No silent fallback: at the benchmark resolution the 3x3 convolutions of the 512^2 / 256^2 / 128^2 stages must run
+    on the operand-swapped kernel (single CTA for 128 channels, CTA pairs above) and the 64^2 stage on pixel-major CTA
+    pairs.  Read from the library's own per-launch record (key = name|M|N|K|mode; mode 2xxx swapped, 3xxx swapped
+    pairs, 1xxx pixel-major pairs)."""
+    import ctypes as C
+    _, vae = models
+    lib = vae._lib
+    g = torch.Generator().manual_seed(17)
+    x = (torch.rand((2, 3, 512, 512), generator=g) * 2 - 1).to(dev)
+    t = torch.randn((2, 4, 64, 64), generator=g).to(dev)
+    lib.tml_gemm_timing_enable(4096)
+    try:
+        vae.attack_grad(x, t, None, 0)
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        n = lib.tml_gemm_timing_report(buf, len(buf))
+    finally:
+        lib.tml_gemm_timing_enable(0)
+    modes = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, m, nn, k, mode = line.split("|")[:5]
+        modes[(name, int(m), int(nn), int(k))] = int(mode)
+    px = 2 * 512 * 512
+    assert modes[("resnet.conv1", px, 128, 1152)] // 1000 == 2          # 128 channels at 512^2: swapped, single CTA
+    assert modes[("resnet.conv2.dgrad", px, 128, 1152)] // 1000 == 2
+    assert modes[("conv_in", px, 128, 576)] // 1000 == 2
+    assert modes[("resnet.conv2", px // 4, 256, 2304)] // 1000 == 3      # 256 channels at 256^2: swapped, CTA pairs
+    assert modes[("resnet.conv2", px // 16, 512, 4608)] // 1000 == 3     # 512 channels at 128^2: swapped, CTA pairs
+    assert modes[("resnet.conv2.dgrad", px // 16, 512, 4608)] // 1000 == 3
+    assert modes[("resnet.conv2", px // 64, 512, 4608)] // 1000 == 1     # 64^2 stage: pixel-major CTA pairs
+    assert modes[("attn.pv", px // 64, 512, 4096)] // 1000 == 1
+
+
 def test_cli_main_runs_small(dev, tmp_path):
     from tml_image_editing_defense_b200.main import main
     rc = main(["--num_images", "3", "--resolution", "64", "--max_train_steps", "4", "--train_batch_size", "2",
