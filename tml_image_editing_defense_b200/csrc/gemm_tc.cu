@@ -179,6 +179,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     }
     if (halo) { TW = 128; TH = 1; }
     t->halo = halo ? 1 : 0;
+    t->out_bytes = 0;
     t->TW = TW;
     t->TH = TH;
     t->rows_valid = TW * TH;
@@ -219,15 +220,26 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
     t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
+    // Plain dense outputs (no residual, no fused reduction) leave through shared memory and TMA stores: the per-lane
+    // 32-byte global stores of the register epilogue cost one LSU request per sector (~0.2 ms per GB of output, measured),
+    // which is what bounds the thin GEMMs (1x1 shortcuts, parity-class dgrads, attention logits).
+    // Two column halves x two buffers of [128 rows][32 columns].
+    static const bool no_tma_store = getenv("TML_NO_TMA_STORE") && getenv("TML_NO_TMA_STORE")[0] == '1';   // tuning switch
+    const int es_out = op.out_fp32 ? 4 : 2;
+    const bool dense_rows = op.D_sN == 1 && (op.n_store == 0 || op.n_store == op.N) && !(op.out_fp32 && op.beta != 0.f) &&
+                            (op.D_sW * es_out) % 16 == 0 && (op.D_sH * es_out) % 16 == 0 && (op.D_sB * es_out) % 16 == 0;
+    if (!no_tma_store && !t->pair && op.gn_mode == 0 && op.resid == nullptr && dense_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
+        getenv("TML_DBG_NO_EPI") == nullptr)
+        t->out_bytes = 2 * 2 * 128 * 32 * es_out;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
-    int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes) / stage_bytes;
+    int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - t->out_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     // (the ring runs across tiles: with short K it holds several tiles' operands, which is what hides the load latency
     // of the memory-bound 1x1 / thin GEMMs -- capping it at one tile's k-blocks left them latency-bound)
     if (stages < 2) stages = 2;
     t->stages = stages;
     t->stage_bytes = stage_bytes;
-    t->smem_bytes = size_t(stages) * stage_bytes + kBarrierBytes + kGnSmemBytes + 1024;
+    t->smem_bytes = size_t(t->out_bytes) + size_t(stages) * stage_bytes + kBarrierBytes + kGnSmemBytes + 1024;
     return 0;
 }
 
@@ -268,6 +280,7 @@ struct TcParams {
     int halo, halo_bytes;
     int pair;          // halo mode on CTA pairs: cta_group::2 MMA (M = 256 over two SMs), each CTA stages half of B
     volatile int* hang_where;  // mapped host word that receives the id of a wait that timed out
+    int out_bytes;     // > 0: dense outputs are staged in shared memory ([2 halves][2 buffers][128 rows][32 cols]) and TMA-stored
     int dbg_no_epi;    // experiment: 1 = the epilogue only hands the accumulator back, 2 = no global memory ops, 3 = no GN math
     int dbg_mma_only;  // experiment: operands are loaded for the first pass over the ring only
 };
@@ -463,10 +476,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                         const TcParams p) {
+                         const __grid_constant__ CUtensorMap mapD, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ring = smem + 2 * size_t(p.halo_bytes);                   // halo mode: two halo tiles come first
+    uint8_t* out_stage = smem + 2 * size_t(p.halo_bytes);              // (halo mode: two halo tiles come first)
+    uint8_t* ring = out_stage + size_t(p.out_bytes);                   // output staging of the TMA-store epilogue, then the ring
     uint8_t* bar_base = ring + size_t(p.stages) * p.stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);        // [stages]
     uint64_t* empty_bar = full_bar + 8;                                // [stages]
@@ -488,6 +502,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
+        if (p.out_bytes) tma_prefetch_desc(&mapD);
     }
     if (warp == 1 && lane == 0) {
         // pair mode: the "full" barriers live in the leader CTA: ONE arrival (the leader's) plus the transaction
@@ -762,7 +777,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         const int ch_lo = half == 0 ? 0 : (nch + 1) / 2;  // this warp's chunk range
         const int ch_hi = half == 0 ? (nch + 1) / 2 : nch;
         const bool ld_res = p.resid != nullptr && p.dbg_no_epi != 2, ld_x = p.gn_mode == 2 && p.dbg_no_epi != 2;
-        int acc = 0;
+        int acc = 0, obuf = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int nt = tile % p.n_tiles;
@@ -832,6 +847,54 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         }
                     }
                     tmem_ld_wait();
+                    if (p.out_bytes) {
+                        // staged epilogue: [128 rows][32 columns] per column half, two buffers, one TMA store per chunk
+                        const int es = p.out_fp32 ? 4 : 2;
+                        uint8_t* sbuf = out_stage + size_t((half * 2 + obuf) * 128 * 32 * es);
+                        if (q == 0 && lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
+                        named_bar_sync(2 + half, 128);
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        }
+                        if (valid) {
+                            if (p.bias != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.BN + c) + j);
+                                    f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                                }
+                            }
+                            if (p.out_fp32) {
+                                // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+                                uint8_t* rowp = sbuf + size_t(row) * 128;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+                                        make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                   __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                            } else {
+                                // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+                                uint8_t* rowp = sbuf + size_t(row) * 64;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(rowp + ((j ^ ((row >> 1) & 3)) << 4)) =
+                                        make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                            }
+                        }
+                        fence_proxy_async();
+                        named_bar_sync(2 + half, 128);
+                        if (q == 0 && lane == 0) {
+                            tma_store_4d(&mapD, sbuf, nt * p.BN + c, stl.ow0, stl.oh0, img);
+                            bulk_commit_group();
+                        }
+                        obuf ^= 1;
+                        continue;
+                    }
                     epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
                     if (p.gn_mode != 0 && p.dbg_no_epi != 3) {
                         float gv[16];
@@ -879,6 +942,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if (p.out_bytes && q == 0 && lane == 0) bulk_wait_group<0>();   // staged tiles are in global memory before the CTA exits
     }
 
     tc_fence_before();
@@ -1330,12 +1394,13 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, const char* what) {
+                      const cuuint32_t* box, const char* what, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(%s) failed: %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", what, (int)r,
@@ -1530,8 +1595,20 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         if ((rc = encode_map(&mapB, op.Bm, 3, dims, str, box, op.name))) return rc;
     }
 
+    CUtensorMap mapD = mapB;   // placeholder unless the staged epilogue is on
+    if (t.out_bytes) {
+        const cuuint64_t es = op.out_fp32 ? 4 : 2;
+        cuuint64_t dims[4] = {(cuuint64_t)op.N, (cuuint64_t)op.OW, (cuuint64_t)op.OH, (cuuint64_t)op.A_B};
+        cuuint64_t str[3] = {(cuuint64_t)op.D_sW * es, (cuuint64_t)op.D_sH * es, (cuuint64_t)op.D_sB * es};
+        cuuint32_t box[4] = {32, (cuuint32_t)t.TW, (cuuint32_t)t.TH, 1};
+        if ((rc = encode_map(&mapD, op.D, 4, dims, str, box, op.name,
+                             op.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                             op.out_fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
+            return rc;
+    }
     TcParams p;
     memset(&p, 0, sizeof(p));
+    p.out_bytes = t.out_bytes;
     p.mode = op.stride == 2 ? 1 : 0;
     p.TW = t.TW; p.TH = t.TH; p.rows_valid = t.rows_valid;
     p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.nimg = op.A_B;
@@ -1579,7 +1656,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)(op.n_store > 0 ? op.n_store : op.N) * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
-                 op.ntaps * op.A_C, t.pair * 1000 + t.halo * 100 + op.gn_mode * 10 + t.mt);
+                 op.ntaps * op.A_C, (t.out_bytes ? 4000 : 0) + t.pair * 1000 + t.halo * 100 + op.gn_mode * 10 + t.mt);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;
@@ -1596,10 +1673,10 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true>, mapA, mapB, p);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true>, mapA, mapB, mapD, p);
         if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
     } else {
-        conv_gemm_tcgen05_kernel<false><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, p);
+        conv_gemm_tcgen05_kernel<false><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
     }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();
