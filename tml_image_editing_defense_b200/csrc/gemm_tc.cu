@@ -220,7 +220,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
     t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
-    // Plain dense outputs (no residual, no fused reduction) leave through shared memory and TMA stores: the per-lane
+    // Plain dense outputs (no fused reduction) leave through shared memory and TMA stores: the per-lane
     // 32-byte global stores of the register epilogue cost one LSU request per sector (~0.2 ms per GB of output, measured),
     // which is what bounds the thin GEMMs (1x1 shortcuts, parity-class dgrads, attention logits).
     // Two column halves x two buffers of [128 rows][32 columns].
@@ -228,7 +228,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     const int es_out = op.out_fp32 ? 4 : 2;
     const bool dense_rows = op.D_sN == 1 && (op.n_store == 0 || op.n_store == op.N) && !(op.out_fp32 && op.beta != 0.f) &&
                             (op.D_sW * es_out) % 16 == 0 && (op.D_sH * es_out) % 16 == 0 && (op.D_sB * es_out) % 16 == 0;
-    if (!no_tma_store && !t->pair && op.gn_mode == 0 && op.resid == nullptr && dense_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
+    if (!no_tma_store && !t->pair && op.gn_mode == 0 && dense_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
         getenv("TML_DBG_NO_EPI") == nullptr)
         t->out_bytes = 2 * 2 * 128 * 32 * es_out;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
@@ -868,6 +868,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                     f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
                                 }
                             }
+                            if (p.resid != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 r = rres[j];
+                                    f[8 * j + 0] += bf16_lo(r.x); f[8 * j + 1] += bf16_hi(r.x);
+                                    f[8 * j + 2] += bf16_lo(r.y); f[8 * j + 3] += bf16_hi(r.y);
+                                    f[8 * j + 4] += bf16_lo(r.z); f[8 * j + 5] += bf16_hi(r.z);
+                                    f[8 * j + 6] += bf16_lo(r.w); f[8 * j + 7] += bf16_hi(r.w);
+                                }
+                            }
                             if (p.out_fp32) {
                                 // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
                                 uint8_t* rowp = sbuf + size_t(row) * 128;
@@ -893,6 +903,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             bulk_commit_group();
                         }
                         obuf ^= 1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
                         continue;
                     }
                     epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
