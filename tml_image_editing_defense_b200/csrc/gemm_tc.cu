@@ -1,15 +1,20 @@
-// Implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (sm_100a).
+// Implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (sm_100a).  Two kernels:
 //
-//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared
-//     memory ring; convolution taps are expressed as shifted TMA box origins on the NHWC tensor,
-//     the hardware zero-fills out-of-range pixels (= the conv padding), so no im2col buffer exists;
-//   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16 per instruction, bf16 x bf16 ->
-//     fp32) with the accumulator in TMEM, double buffered (2 x BN columns) so that the epilogue of
-//     tile i overlaps the main loop of tile i+1;
-//   * four epilogue warps read the accumulator with tcgen05.ld (thread = output pixel), apply
-//     alpha / bias / residual and store bf16 NHWC (16-byte vectors) or a strided fp32 layout;
-//   * persistent grid (one CTA per SM), static round-robin tile schedule, warp-specialised roles
-//     synchronised only through mbarriers.
+//   conv_gemm_tcgen05_kernel  -- pixel-major (M = 128 output pixels, N = output channels): every GEMM shape of the
+//     path (3x3 s1/s2, 1x1, linears, attention products and their input-gradient forms).
+//       * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared memory ring;
+//         convolution taps are shifted TMA box origins on the NHWC tensor, the hardware zero-fills out-of-range
+//         pixels (= the conv padding), so no im2col buffer exists; in halo mode one (mt+2) x 130-pixel tile per
+//         64-channel chunk serves all nine taps through row-shifted UMMA descriptors;
+//       * one elected thread issues tcgen05.mma (M=128 or, on CTA pairs, 256; N<=256; K=16; bf16 x bf16 -> fp32) with
+//         the accumulator in TMEM, double buffered so that the epilogue of tile i overlaps the main loop of tile i+1;
+//       * eight epilogue warps read the accumulator with tcgen05.ld (thread = output pixel), apply alpha / bias /
+//         residual, reduce GroupNorm sums, and either store from registers (32 bytes per lane) or stage the tile in
+//         shared memory for a TMA store;
+//       * persistent grid (one CTA per SM), static round-robin tiles, warp-specialised roles synchronised only
+//         through mbarriers; cta_group::2 pairs for the weight-heavy long-K shapes.
+//   conv3x3_swapped_kernel  -- channel-major (M = 128/256 output channels, N = 256 pixels) for 3x3 stride-1
+//     convolutions on rows of >= 128 pixels: where most of the FLOPs of the path run (see the comment above it).
 //
 // Replaces the cuDNN conv fwd/dgrad + cuBLAS linear calls PyTorch makes for the reference's
 // vae.encode (main.py:75,191) and its autograd backward (main.py:176).
