@@ -997,8 +997,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 template <bool PAIR> struct SwGeo {
     static constexpr int kRowPx = PAIR ? 130 : 258;
     static constexpr int kRowBytes = PAIR ? 17 * 1024 : 33 * 1024;   // kRowPx * 128 B rounded up to the 1 KB swizzle atom
-    static constexpr int kRowSlots = 4;
-    static constexpr int kWStages = PAIR ? 8 : 5;
+    static constexpr int kRowSlots = PAIR ? 4 : 3;
+    static constexpr int kWStages = PAIR ? 8 : 7;
     static constexpr int kSmem = 1024 + kRowSlots * kRowBytes + kWStages * (128 * kBlockK * 2) + 256;
 };
 constexpr int kSwWBytes = 128 * kBlockK * 2;  // 16 KB: 128 output channels x 64 input channels
