@@ -170,16 +170,26 @@ def test_pgd_empty_and_unaligned(dev):
         ops.pgd_step_linf_(base[1:], base[1:].clone(), torch.zeros(8, device=dev), 0.1, 0.01, -1.0, 1.0)
 
 
-def test_tcgen05_gemm_suite_cta_pairs(dev):
-    """The cta_group::2 (CTA-pair) instantiation of the halo kernel, enabled with TML_PAIR=1 (off by default:
-    it is correct but slower).  Runs in a subprocess because the switch is read once."""
+def _run_gemm_suite(extra_env):
     import os
     import subprocess
     import sys
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
-    env = dict(os.environ, TML_PAIR="1")
+    env = dict(os.environ, **extra_env)
     r = subprocess.run([sys.executable, str(root / "tests" / "gpu_check.py"), "--gemm-only", "--impl", "tc"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "ALL OK" in r.stdout
+
+
+def test_tcgen05_gemm_suite_cta_pairs(dev):
+    """The cta_group::2 (CTA-pair) instantiation of the pixel-major kernel's halo mode, enabled with TML_PAIR=1 (by
+    default pairs are used outside halo mode only).  A subprocess because the switch is read once."""
+    _run_gemm_suite({"TML_PAIR": "1"})
+
+
+def test_tcgen05_gemm_suite_fallback_paths(dev):
+    """The same suite with the fast paths switched off (no operand-swapped kernel, no CTA pairs, register epilogue
+    instead of TMA stores): the A/B switches documented in DESIGN.md must stay correct."""
+    _run_gemm_suite({"TML_NO_SWAP": "1", "TML_PAIR": "0", "TML_NO_TMA_STORE": "1"})
