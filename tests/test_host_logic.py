@@ -41,6 +41,46 @@ def test_no_cpu_fallback_without_gpu():
         ops.pgd_step_linf_(torch.zeros(4), torch.zeros(4), torch.zeros(4), 0.1, 0.01, -1, 1)
 
 
+def _conv_desc(B, H, W, Cin, N, gn, taps=9):
+    """A dense 3x3 (or 1x1) stride-1 convolution descriptor with dummy (never dereferenced) pointers."""
+    from tml_image_editing_defense_b200 import _lib
+    d = _lib.TmlGemmDesc()
+    d.A = 256; d.A_C = Cin; d.A_W = W; d.A_H = H; d.A_B = B
+    d.A_sW = Cin; d.A_sH = W * Cin; d.A_sB = H * W * Cin
+    d.stride = 1; d.ntaps = taps
+    for t in range(taps):
+        d.dh[t] = (t // 3 - 1) if taps == 9 else 0
+        d.dw[t] = (t % 3 - 1) if taps == 9 else 0
+    d.OW = W; d.OH = H
+    d.Bm = 256; d.N = N; d.B_sN = taps * Cin; d.alpha = 1.0
+    d.D = 256; d.D_sW = N; d.D_sH = W * N; d.D_sB = H * W * N; d.D_sN = 1
+    d.R_sW = N; d.R_sH = W * N; d.R_sB = H * W * N
+    d.gn_mode = gn
+    if gn:
+        d.gn_partial = 256
+    if gn == 2:
+        d.gn_x = 256; d.gn_ss = 256; d.gn_mr = 256; d.gn_gamma = 256
+    return d
+
+
+def test_partial_sum_geometry_of_the_fused_reductions():
+    """Host-side tiling logic (no GPU needed): how many GroupNorm partial entries per image each kernel writes.
+    Operand-swapped kernel (rows of >= 128 pixels, 128/256/512 channels): one entry per 128 pixels for the statistics
+    (8 epilogue warps), per 64 pixels for the backward sums (16 warps); pixel-major kernel: one per 128-row tile."""
+    import ctypes as C
+    from tml_image_editing_defense_b200 import _lib
+    lib = _lib.load()
+    n = lambda d: lib.tml_debug_gn_chunks_per_image(C.byref(d))
+    assert n(_conv_desc(2, 8, 512, 128, 128, 1)) == 8 * 512 // 128          # swapped, single CTA
+    assert n(_conv_desc(2, 8, 512, 128, 128, 2)) == 8 * 512 // 64
+    assert n(_conv_desc(2, 8, 128, 512, 512, 1)) == 8 * 128 // 128          # swapped, CTA pairs (rows of 128 pixels)
+    assert n(_conv_desc(2, 8, 128, 512, 512, 2)) == 8 * 128 // 64
+    assert n(_conv_desc(2, 64, 64, 512, 512, 1)) == lib.tml_debug_gn_tiles_per_image(64, 64) == 32   # pixel-major
+    assert n(_conv_desc(2, 64, 64, 512, 512, 2)) == 32
+    assert n(_conv_desc(2, 7, 128, 512, 512, 1)) == lib.tml_debug_gn_tiles_per_image(7, 128)         # odd rows: no pairs
+    assert n(_conv_desc(2, 16, 16, 128, 256, 1, taps=1)) == lib.tml_debug_gn_tiles_per_image(16, 16)  # 1x1: pixel-major
+
+
 @pytest.mark.parametrize("ci,co", [(8, 16), (16, 8)])
 def test_pack_forward_s1_matches_conv2d(ci, co):
     g = torch.Generator().manual_seed(0)
