@@ -180,7 +180,7 @@ def run_ours(args):
     del weights
     cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
                       n_optimization_steps=1, device=str(dev), apply_loss_on_images=args.loss == "images",
-                      apply_loss_on_latents=args.loss != "images",
+                      apply_loss_on_latents=args.loss != "images",      # the encoder attack sets the latent mode explicitly
                       perturbation_loss_lambda=1.0 if args.loss == "images" else 0.0)
     tr = Trainer(cfg, vae, micro_batch=mb, num_streams=args.streams)
 

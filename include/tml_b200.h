@@ -105,6 +105,10 @@ int tml_batch_sum(const float* g, float* out, int B, int64_t per_image, float sc
 /* L2-normalised step, clamp to +-eps, optional image-range projection (:173-185); ws >= 1 KiB. */
 int tml_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
                        float hi, int64_t n, void* ws, void* stream);
+/* Image-range re-projection alone (:183-185): for each of the nsrc source images [nsrc][n] in order,
+ * delta = clamp(source + delta, lo, hi) - source.  One source = the reference statement; a sharded step
+ * passes the per-pixel (min, max) images of the whole dataset so every replica applies the same bounds. */
+int tml_universal_project(float* delta, const float* sources, int nsrc, float lo, float hi, int64_t n, void* stream);
 
 /* ---- introspection / test hooks ---- */
 /* number of kernels launched by this library since load: [0] tcgen05 GEMMs, [1] all other kernels */

@@ -79,6 +79,14 @@ def universal_update(delta: torch.Tensor, grad: torch.Tensor, source: Optional[t
     return delta
 
 
+def universal_project(delta: torch.Tensor, sources: torch.Tensor, lo: float = -1.0, hi: float = 1.0) -> torch.Tensor:
+    """old/train_noise.py:183-185 applied once per source image, in order:
+    ``perturbed = clamp(source + perturbation, lo, hi); perturbation = perturbed - source``."""
+    for s in sources:
+        delta = torch.clamp(s[None] + delta, lo, hi) - s[None]
+    return delta
+
+
 # ----------------------------------------------------------------------------------------------
 # Losses (reference: losses/losses.py:6-41)
 # ----------------------------------------------------------------------------------------------

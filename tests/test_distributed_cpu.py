@@ -33,14 +33,16 @@ def _worker_universal(rank, world, port, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
-    from oracle.pgd_oracle import universal_update
+    from oracle.pgd_oracle import universal_project, universal_update
     from tml_image_editing_defense_b200.configs import UniversalConfig
     from tml_image_editing_defense_b200.dataset import SyntheticImageDataset
     from tml_image_editing_defense_b200.universal import UniversalTrainer
-    cfg = UniversalConfig(grad_reps=1, eps=0.05, step_size=0.02, resolution=16)
+    # eps large enough that the image-range re-projection (apply_image_pertubation, default True) binds
+    cfg = UniversalConfig(grad_reps=1, eps=0.5, step_size=0.4, resolution=16)
+    assert cfg.apply_image_pertubation
     model = _tiny_model()
     ut = UniversalTrainer(cfg, _grad_fn(model), lambda g: g.sum(0, keepdim=True), lambda x, d: x + d,
-                          lambda d, g: universal_update(d, g, None, cfg.eps, cfg.step_size))
+                          lambda d, g: universal_update(d, g, None, cfg.eps, cfg.step_size), universal_project)
     n = 5
     ds = SyntheticImageDataset(n, resolution=16, seed=3)
     idx = ut.local_indices(n)
@@ -55,8 +57,8 @@ def _worker_universal(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def _single_process_universal():
-    from oracle.pgd_oracle import universal_update
+def _single_process_universal(project=True):
+    from oracle.pgd_oracle import universal_project, universal_update
     from tml_image_editing_defense_b200.dataset import SyntheticImageDataset
     model = _tiny_model()
     gf = _grad_fn(model)
@@ -67,7 +69,11 @@ def _single_process_universal():
     delta = torch.zeros(1, 3, 16, 16)
     for _ in range(3):
         g = gf(imgs + delta, tg, None).sum(0, keepdim=True) / n
-        delta = universal_update(delta, g, None, 0.05, 0.02)
+        delta = universal_update(delta, g, None, 0.5, 0.4)
+        if project:
+            delta = universal_project(delta, imgs)     # the reference statement, image after image (:183-185)
+    if project:
+        assert float((imgs + delta).abs().max()) <= 1.0 + 1e-6
     return delta
 
 
@@ -79,8 +85,9 @@ def test_universal_allreduce_two_ranks_matches_single_process():
         d2 = ret["delta"]
     d1 = _single_process_universal()
     # the all-reduce changes the summation order: equal up to fp32 rounding of the gradient sum
-    torch.testing.assert_close(d2, d1, rtol=0, atol=1e-6)
+    torch.testing.assert_close(d2, d1, rtol=0, atol=2e-6)
     assert float(d2.abs().max()) > 0
+    assert not torch.equal(d1, _single_process_universal(project=False))   # the re-projection did bind somewhere
 
 
 def _worker_sharded(rank, world, port, ret):

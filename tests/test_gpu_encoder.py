@@ -130,8 +130,8 @@ def test_loss_trajectory_100_steps_within_1pct(dev, models):
     encoder_attack(od, x, t, noise, 100, eps, step, -1.0, 1.0, kind=0,
                    record=lambda xa, gr, ls: ref_losses.append(float(ls.sum())))
     oracle.to("cpu")
-    cfg = TrainConfig(norm_type="linf", eps=eps, step_size=step, grad_reps=1, override_from_norm_type=False,
-                      n_optimization_steps=100, device=str(dev))
+    cfg = TrainConfig.encoder_attack(norm_type="linf", eps=eps, step_size=step, grad_reps=1,
+                                     override_from_norm_type=False, n_optimization_steps=100, device=str(dev))
     tr = Trainer(cfg, vae)
     tr.noises = [noise]
     tr._noise_shape = tuple(noise.shape)
@@ -151,8 +151,8 @@ def test_trainer_l2_runs_and_respects_ball(dev, models):
     g = torch.Generator().manual_seed(2)
     x = (torch.rand((2, 3, 64, 64), generator=g) * 2 - 1).to(dev)
     t = torch.randn((2, 4, 8, 8), generator=g).to(dev)
-    cfg = TrainConfig(norm_type="l2", eps=2.0, step_size=0.5, grad_reps=2, override_from_norm_type=False,
-                      n_optimization_steps=8, device=str(dev))
+    cfg = TrainConfig.encoder_attack(norm_type="l2", eps=2.0, step_size=0.5, grad_reps=2, override_from_norm_type=False,
+                                     n_optimization_steps=8, device=str(dev))
     tr = Trainer(cfg, vae)
     xa = tr.run(x, target_latent=t)
     d = (xa - x).reshape(2, -1).norm(dim=1)
@@ -175,6 +175,33 @@ def test_universal_step_single_rank(dev, models):
     # the same shard processed with another micro-batching gives the same summed gradient
     d2 = ut.step(torch.zeros_like(delta), imgs, tg, None, n_global=3, micro_batch=3)
     torch.testing.assert_close(d1, d2, rtol=0, atol=1e-6)
+
+
+def test_universal_for_b200_honours_image_range_projection(dev, models):
+    """UniversalConfig.apply_image_pertubation (old/train_noise.py:41,182-185; default True) through the real driver
+    path: after every step x_i + delta stays in [-1, 1] for every image; switched off, only the +-eps clamp holds.
+    Posterior noise is passed per step (latent_dist.sample(generator), :133)."""
+    from tml_image_editing_defense_b200.configs import UniversalConfig
+    from tml_image_editing_defense_b200.universal import UniversalTrainer
+    _, vae = models
+    g = torch.Generator().manual_seed(19)
+    imgs = (torch.rand((4, 3, 64, 64), generator=g) * 2 - 1)
+    imgs[:, :, :8] = imgs[:, :, :8].sign()                      # saturated rows: any step outwards must be undone
+    imgs = imgs.to(dev)
+    tg = torch.randn((4, 4, 8, 8), generator=g).to(dev)
+    out = {}
+    for flag in (True, False):
+        cfg = UniversalConfig(grad_reps=2, eps=0.25, step_size=40.0, resolution=64, apply_image_pertubation=flag)
+        ut = UniversalTrainer.for_b200(cfg, vae)
+        delta = torch.zeros((1, 3, 64, 64), device=dev)
+        gen = torch.Generator(device=dev).manual_seed(3)
+        for _ in range(3):
+            nz = torch.randn(tg.shape, generator=gen, device=dev)
+            delta = ut.step(delta, imgs, tg, nz, n_global=4, micro_batch=2)
+        out[flag] = delta.clone()
+        assert float(delta.abs().max()) <= 0.25 + 1e-7
+    assert float((imgs + out[True]).abs().max()) <= 1.0 + 1e-6
+    assert float((imgs + out[False]).abs().max()) > 1.0 + 1e-3      # without the projection the range is left
 
 
 def test_grad_cosine_512_vs_oracle_on_gpu(dev, models):
@@ -251,8 +278,8 @@ def test_non_square_and_ragged_batch(dev, models):
     od = oracle.to(dev)
     g_ref, l_ref, _ = encoder_attack_grad(od, x, t, n, 1)
     oracle.to("cpu")
-    cfg = TrainConfig(norm_type="linf", eps=0.1, step_size=0.01, grad_reps=1, override_from_norm_type=False,
-                      latent_loss="mse", device=str(dev))
+    cfg = TrainConfig.encoder_attack(norm_type="linf", eps=0.1, step_size=0.01, grad_reps=1,
+                                     override_from_norm_type=False, latent_loss="mse", device=str(dev))
     tr = Trainer(cfg, vae, micro_batch=2)
     grad, loss, _, ld = tr.compute_grad(x, None, x, None, t, [n])
     assert cosine(grad, g_ref) >= 0.999

@@ -92,6 +92,26 @@ def test_universal_step_vs_reference_golden(golden_dir, dev, name):
     np.testing.assert_allclose(out.cpu().numpy(), d["out"], rtol=0, atol=2e-6)
 
 
+def test_universal_project_bit_exact_vs_oracle(dev):
+    """old/train_noise.py:183-185 as its own entry point: one source (the reference statement, bit-exact) and the
+    (min, max) pair a sharded step uses; +-0, NaN and on-boundary values included."""
+    from oracle.pgd_oracle import universal_project
+    g = torch.Generator().manual_seed(5)
+    n = 3 * 37 * 41
+    delta = (torch.rand((1, n), generator=g) - 0.5) * 0.8
+    src = torch.rand((4, n), generator=g) * 2 - 1
+    src[0, :8] = torch.tensor([1.0, -1.0, 0.0, -0.0, 1.0, -1.0, 0.999999, -0.999999])
+    delta[0, :8] = torch.tensor([0.3, -0.3, 0.0, -0.0, -0.3, 0.3, float("nan"), 1e-8])
+    for k in (1, 2, 4):
+        out = ops.universal_project_(delta.clone().to(dev), src[:k].contiguous().to(dev))
+        ref = universal_project(delta, src[:k])
+        assert torch.equal(out.cpu().view(torch.int32), ref.view(torch.int32)), k
+    lo, hi = src.amin(0), src.amax(0)
+    out = ops.universal_project_(delta.clone().to(dev), torch.stack([lo, hi]).to(dev)).cpu()
+    ok = ~torch.isnan(out)
+    assert float(((src + out)[:, ok[0]]).abs().max()) <= 1.0 + 1e-6
+
+
 def test_add_delta_and_batch_sum(dev):
     from tml_image_editing_defense_b200 import ops
     g = torch.Generator().manual_seed(0)

@@ -140,6 +140,13 @@ def test_trainconfig_mirrors_reference_override():
     assert c.eps == 32 / 255 and c.grad_reps == 1
     with pytest.raises(ValueError):
         TrainConfig(apply_loss_on_images=False, apply_loss_on_latents=False)
+    # defaults are the reference's (configs.py:103-111): losses on decoded images, perturbation loss on
+    d = TrainConfig()
+    assert (d.apply_loss_on_images, d.apply_loss_on_latents, d.perturbation_loss_lambda) == (True, False, 1.0)
+    assert (d.rec_loss_lambda, d.n_optimization_steps, d.n_denoising_steps_per_iteration, d.seed) == (1.0, 200, 4, 42)
+    assert (d.guidance_scale, d.eta, d.use_fixed_noise, d.n_noise, d.norm_type) == (3.0, 0.9, True, 1, "l2")
+    e = TrainConfig.encoder_attack(norm_type="linf")
+    assert (e.apply_loss_on_images, e.apply_loss_on_latents, e.perturbation_loss_lambda) == (False, True, 0.0)
 
 
 def test_shard_indices_partition():
@@ -169,3 +176,57 @@ def test_parser_flag_names():
     from tml_image_editing_defense_b200.parser import parse_args
     a = parse_args(["--resolution", "1024", "--train_batch_size", "4", "--seed", "7", "--mixed_precision", "bf16"])
     assert a.resolution == 1024 and a.train_batch_size == 4 and a.seed == 7
+
+
+def test_image_prompt_dataset_from_jpegs(tmp_path):
+    """data/dataset.py:7-43: rglob('*.jpg') -> Resize(bilinear) -> CenterCrop -> ToTensor -> Normalize(.5,.5)."""
+    from PIL import Image
+    from torchvision import transforms
+    from tml_image_editing_defense_b200.dataset import ImagePromptDataset
+    rng = np.random.default_rng(0)
+    sub = tmp_path / "nested"
+    sub.mkdir()
+    paths = [tmp_path / "b.jpg", sub / "a.jpg"]
+    for p, (h, w) in zip(paths, [(96, 160), (200, 120)]):            # landscape and portrait, neither square
+        Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(p, quality=95)
+    (tmp_path / "ignored.png").write_bytes(b"")                        # only *.jpg is collected (dataset.py:13)
+    ds = ImagePromptDataset(str(tmp_path), "a photo", resolution=64)
+    assert len(ds) == 2
+    ref_tf = transforms.Compose([transforms.Resize(64, interpolation=transforms.InterpolationMode.BILINEAR),
+                                 transforms.CenterCrop(64), transforms.ToTensor(), transforms.Normalize([0.5], [0.5])])
+    for i, p in enumerate(sorted(paths)):                              # this build sorts the paths (deterministic shards)
+        img, prompt = ds[i]
+        assert prompt == "a photo"
+        assert img.shape == (3, 64, 64) and img.dtype == torch.float32
+        assert float(img.min()) >= -1.0 and float(img.max()) <= 1.0
+        assert torch.equal(img, ref_tf(Image.open(p).convert("RGB")))
+    raw = ImagePromptDataset.get_image_transform_no_normalization(64)(Image.open(paths[0]).convert("RGB"))
+    assert float(raw.min()) >= 0.0 and float(raw.max()) <= 1.0
+    assert len(ImagePromptDataset(str(sub), "", resolution=64)) == 1
+    assert len(ImagePromptDataset(str(tmp_path / "nested"), "", resolution=32)[0][0][0]) == 32
+
+
+def test_load_checkpoint_round_trip(tmp_path):
+    from tml_image_editing_defense_b200.vae import SD15_VAE
+    from tml_image_editing_defense_b200.weights import encoder_param_shapes, load_checkpoint, random_init_state_dict
+    sd = random_init_state_dict(SD15_VAE, seed=3, include_decoder=True)
+    assert list(sd) == [n for n, _ in encoder_param_shapes(SD15_VAE, include_decoder=True)]
+    assert sum(v.numel() for v in sd.values()) == 83_653_863          # the SD VAE (encoder 34 163 664 + decoder)
+    torch.save(sd, tmp_path / "vae.pt")
+    back = load_checkpoint(str(tmp_path / "vae.pt"))
+    assert list(back) == list(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    torch.save({"state_dict": {k: v.to(torch.bfloat16) for k, v in sd.items()}}, tmp_path / "wrapped.pt")
+    wrapped = load_checkpoint(str(tmp_path / "wrapped.pt"))             # Lightning-style wrapper, bf16 payload
+    assert list(wrapped) == list(sd) and wrapped["encoder.conv_in.weight"].dtype == torch.bfloat16
+    torch.testing.assert_close(wrapped["quant_conv.weight"].float(), sd["quant_conv.weight"], rtol=1e-2, atol=1e-3)
+
+
+def test_parser_keeps_reference_flag_names():
+    from tml_image_editing_defense_b200.parser import parse_args
+    a = parse_args(["--gradient_checkpointing", "--allow_tf32", "--resolution", "256", "--train_batch_size", "4",
+                    "--seed", "7", "--mixed_precision", "bf16", "--max_train_steps", "3", "--output_dir", "o",
+                    "--local_rank", "0"])
+    assert a.gradient_checkpointing and a.allow_tf32 and a.resolution == 256 and a.train_batch_size == 4
+    assert a.seed == 7 and a.max_train_steps == 3 and a.output_dir == "o"
+    b = parse_args([])
+    assert not b.gradient_checkpointing and not b.allow_tf32

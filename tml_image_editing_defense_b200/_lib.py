@@ -78,6 +78,7 @@ SIGNATURES = {
     "tml_batch_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
     "tml_universal_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_int64, C.c_void_p, C.c_void_p]),
+    "tml_universal_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "tml_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "tml_gemm_timing_enable": (None, [C.c_int]),
     "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),

@@ -17,11 +17,11 @@ class TrainConfig:
     experiment_name: str = "experiment_l2_fixed_noise"
     n_optimization_steps: int = 200
     n_denoising_steps_per_iteration: int = 4     # UNet steps: 0 in the encoder attack
-    apply_loss_on_images: bool = False           # needs vae.decode -> off in this build
-    apply_loss_on_latents: bool = True
+    apply_loss_on_images: bool = True            # reference default (configs.py:103): losses on vae.decode(z)
+    apply_loss_on_latents: bool = False          # reference default (configs.py:105); the encoder attack sets it
     limit_timesteps: bool = True
     rec_loss_lambda: float = 1.0
-    perturbation_loss_lambda: float = 0.0        # reference default 1.0 acts on decoded images
+    perturbation_loss_lambda: float = 1.0        # reference default (configs.py:111); image-space loss only
     seed: int = 42
     prompts: List[str] = field(default_factory=lambda: [""])
     device: str = "cuda:0"
@@ -68,6 +68,15 @@ class TrainConfig:
     @property
     def loss_kind(self) -> int:
         return {"l2norm": 0, "mse": 1}[self.latent_loss]
+
+    @classmethod
+    def encoder_attack(cls, **kw) -> "TrainConfig":
+        """The VAE-encoder attack of BASELINE configs[1]: loss between latents (main.py:161-162), no decode,
+        no image-space perturbation loss.  The defaults of this class are the reference's (image losses)."""
+        kw.setdefault("apply_loss_on_images", False)
+        kw.setdefault("apply_loss_on_latents", True)
+        kw.setdefault("perturbation_loss_lambda", 0.0)
+        return cls(**kw)
 
 
 @dataclass

@@ -195,9 +195,39 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
+static int dec_forward_walk(TmlEncoder* e, Run& r, const float* z, float* image);
+static int dec_backward_walk(TmlEncoder* e, Run& r, const float* dimage, float* dz);
+
+// layout + scratch size measured by a dry run of both walks (see enc_layout in encoder.cu)
+static int dec_layout(TmlEncoder* e, int B, int h, int w) {
+    if (B <= 0 || h <= 0 || w <= 0) { set_error("bad shape B=%d h=%d w=%d", B, h, w); return -30; }
+    RC(build_dec_layout(e, B, h, w));
+    DecLayout& L = e->dlay;
+    if (L.measured) return 0;
+    char* fake = reinterpret_cast<char*>(uintptr_t(1) << 20);   // never dereferenced
+    size_t peak = 0;
+    int rc = 0;
+    g_dry_run = true;
+    {
+        Run r{e, fake, fake, Arena(), nullptr, B};
+        rc = dec_forward_walk(e, r, reinterpret_cast<const float*>(fake), reinterpret_cast<float*>(fake));
+        peak = r.wsa.peak;
+    }
+    if (rc == 0) {
+        Run r{e, fake, fake, Arena(), nullptr, B};
+        rc = dec_backward_walk(e, r, reinterpret_cast<const float*>(fake), reinterpret_cast<float*>(fake));
+        peak = std::max(peak, r.wsa.peak);
+    }
+    g_dry_run = false;
+    if (rc) { L = DecLayout(); return rc; }
+    L.ws_bytes = peak + 1024;
+    L.measured = true;
+    return 0;
+}
+
 int tml_decoder_query(TmlEncoder* e, int B, int h, int w, size_t* workspace_bytes, size_t* saved_bytes) {
     if (!e || !e->finalized || !e->has_decoder) { set_error("decoder weights were not loaded"); return -1; }
-    RC(build_dec_layout(e, B, h, w));
+    RC(dec_layout(e, B, h, w));
     if (workspace_bytes) *workspace_bytes = e->dlay.ws_bytes;
     if (saved_bytes) *saved_bytes = e->dlay.saved_bytes;
     return 0;
@@ -207,11 +237,19 @@ int tml_decoder_forward(TmlEncoder* e, const float* z, int B, int h, int w, floa
                         void* stream) {
     if (!e || !e->finalized || !e->has_decoder) { set_error("decoder weights were not loaded"); return -1; }
     if (!z || !image || !saved || !ws) { set_error("null buffer"); return -1; }
-    RC(build_dec_layout(e, B, h, w));
+    DeviceGuard guard(e->device);
+    RC(dec_layout(e, B, h, w));
+    Run r{e, reinterpret_cast<char*>(saved), reinterpret_cast<char*>(ws), Arena(), reinterpret_cast<cudaStream_t>(stream), B};
+    RC(dec_forward_walk(e, r, z, image));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int dec_forward_walk(TmlEncoder* e, Run& r, const float* z, float* image) {
     const DecLayout& L = e->dlay;
     const TmlEncoderCfg& c = e->cfg;
     const int nb = c.num_blocks, ns = e->num_sms;
-    Run r{e, reinterpret_cast<char*>(saved), reinterpret_cast<char*>(ws), Arena(), reinterpret_cast<cudaStream_t>(stream), B};
+    const int B = L.B, h = L.h, w = L.w;
     r.statbuf[0] = r.Walloc<float>(fused_partial_bytes(B, L.Hl, L.Wl));
     r.statbuf[1] = r.Walloc<float>(fused_partial_bytes(B, L.Hl, L.Wl));
     const int Ctop = c.block_out_channels[nb - 1];
@@ -256,8 +294,7 @@ int tml_decoder_forward(TmlEncoder* e, const float* z, int B, int h, int w, floa
         o.D_sB = (int64_t)3 * H * W; o.D_sH = W; o.D_sW = 1; o.D_sN = (int64_t)H * W;
         RC(gemm_launch(o, ns, r.st));
     }
-    if (r.wsa.peak > L.ws_bytes) { set_error("internal: decoder workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
-    CUDA_OK(cudaGetLastError());
+    if (L.measured && r.wsa.peak > L.ws_bytes) { set_error("internal: decoder workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     return 0;
 }
 
@@ -265,12 +302,20 @@ int tml_decoder_backward(TmlEncoder* e, const float* dimage, int B, int h, int w
                          void* ws, void* stream) {
     if (!e || !e->finalized || !e->has_decoder) { set_error("decoder weights were not loaded"); return -1; }
     if (!dimage || !saved || !ws || !dz) { set_error("null buffer"); return -1; }
-    RC(build_dec_layout(e, B, h, w));
+    DeviceGuard guard(e->device);
+    RC(dec_layout(e, B, h, w));
+    Run r{e, const_cast<char*>(reinterpret_cast<const char*>(saved)), reinterpret_cast<char*>(ws), Arena(),
+          reinterpret_cast<cudaStream_t>(stream), B};
+    RC(dec_backward_walk(e, r, dimage, dz));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int dec_backward_walk(TmlEncoder* e, Run& r, const float* dimage, float* dz) {
     const DecLayout& L = e->dlay;
     const TmlEncoderCfg& c = e->cfg;
     const int nb = c.num_blocks, ns = e->num_sms;
-    Run r{e, const_cast<char*>(reinterpret_cast<const char*>(saved)), reinterpret_cast<char*>(ws), Arena(),
-          reinterpret_cast<cudaStream_t>(stream), B};
+    const int B = L.B, h = L.h, w = L.w;
     // ping-pong gradient buffers sized for the largest activation
     size_t gmax = act_bytes(B, h, w, c.block_out_channels[nb - 1]);
     {
@@ -338,8 +383,7 @@ int tml_decoder_backward(TmlEncoder* e, const float* dimage, int B, int h, int w
                                      nullptr, d_zp), ns, r.st));
         launch_latent_unpack_bwd(d_zp, e->pq_w, dz, B, h * w, r.st);
     }
-    if (r.wsa.peak > L.ws_bytes) { set_error("internal: decoder workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
-    CUDA_OK(cudaGetLastError());
+    if (L.measured && r.wsa.peak > L.ws_bytes) { set_error("internal: decoder workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     return 0;
 }
 

@@ -12,6 +12,7 @@
 
 namespace tml {
 
+thread_local bool g_dry_run = false;
 static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(); }
 #define COUNT_LAUNCH() g_launches.fetch_add(1)
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(256) conv_in_pack_kernel(const float* __restri
 }
 
 void launch_conv_in_pack(const float* x, bf16* a, int B, int H, int W, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total_px = (long long)B * H * W;
     conv_in_pack_kernel<<<(unsigned)((total_px * 8 + 255) / 256), 256, 0, s>>>(x, a, H * W, total_px);
     COUNT_LAUNCH();
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) conv_in_col2im_kernel(const float* __rest
 }
 
 void launch_conv_in_col2im(const float* y, float* dx, int B, int H, int W, float beta, cudaStream_t s) {
+    if (g_dry_run) return;
     conv_in_col2im_kernel<<<dim3((W + 63) / 64, H, B), 256, 0, s>>>(y, dx, H, W, beta);
     COUNT_LAUNCH();
 }
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
 }
 
 void launch_gn_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s) {
+    if (g_dry_run) return;
     dim3 grid(gn_num_chunks(HW, C), B);
     gn_stats_kernel<<<grid, 256, 0, s>>>(x, partial, HW, C);
     COUNT_LAUNCH();
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
 
 void launch_gn_finalize(const float* partial, const float* gamma, const float* beta, float2* ss, float2* mr, int B,
                         int HW, int C, float eps, int nchunks, cudaStream_t s) {
+    if (g_dry_run) return;
     gn_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partial, gamma, beta, ss, mr, nchunks, HW, C, eps);
     COUNT_LAUNCH();
 }
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 }
 
 void launch_gn_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s) {
+    if (g_dry_run) return;
     dim3 grid(gn_num_chunks(HW, C), B);
     gn_apply_kernel<<<grid, 256, 0, s>>>(x, ss, y, HW, C, silu);
     COUNT_LAUNCH();
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const bf16* __restr
 
 void launch_gn_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
                            float* partial, int B, int HW, int C, int silu, cudaStream_t s) {
+    if (g_dry_run) return;
     dim3 grid(gn_num_chunks(HW, C), B);
     gn_bwd_partial_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, gamma, partial, HW, C, silu);
     COUNT_LAUNCH();
@@ -419,6 +426,7 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
 }
 
 void launch_gn_bwd_finalize(const float* partial, float2* mm, int B, int HW, int C, int nchunks, cudaStream_t s) {
+    if (g_dry_run) return;
     gn_bwd_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partial, mm, nchunks, HW, C);
     COUNT_LAUNCH();
 }
@@ -490,6 +498,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const bf16* __rest
 void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
                          const float* gamma, const bf16* resid, bf16* dx, int B, int HW, int C, int silu,
                          cudaStream_t s) {
+    if (g_dry_run) return;
     dim3 grid(gn_num_chunks(HW, C), B);
     gn_bwd_apply_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, mm, gamma, resid, dx, HW, C, silu);
     COUNT_LAUNCH();
@@ -527,6 +536,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 }
 
 void launch_softmax_rows(const float* S, bf16* P, long long rows, int cols, cudaStream_t s) {
+    if (g_dry_run) return;
     softmax_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(S, P, cols);
     COUNT_LAUNCH();
 }
@@ -556,6 +566,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __res
 
 void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float scale, long long rows, int cols,
                              cudaStream_t s) {
+    if (g_dry_run) return;
     softmax_bwd_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, dS, scale, cols);
     COUNT_LAUNCH();
 }
@@ -601,6 +612,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
 
 void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
                       long long ld_out, long long bs_out, cudaStream_t s) {
+    if (g_dry_run) return;
     dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
     transpose_kernel<<<grid, 256, 0, s>>>(in, out, R, C, ld_in, bs_in, ld_out, bs_out);
     COUNT_LAUNCH();
@@ -659,6 +671,7 @@ __global__ void __launch_bounds__(256) latent_loss_kernel(int kind, const float*
 
 void launch_latent_loss(int kind, const float* moments, const float* noise, const float* target, int B, int h, int w,
                         float grad_scale, float* z, float* loss, float* dmoments, cudaStream_t s) {
+    if (g_dry_run) return;
     latent_loss_kernel<<<B, 256, 0, s>>>(kind, moments, noise, target, h * w, grad_scale, z, loss, dmoments);
     COUNT_LAUNCH();
 }
@@ -679,6 +692,7 @@ __global__ void dmoments_pack_kernel(const float* __restrict__ dm, bf16* __restr
 }
 
 void launch_dmoments_pack(const float* dm, bf16* out, int B, int h, int w, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * h * w * 8;
     dmoments_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dm, out, h * w, total);
     COUNT_LAUNCH();
@@ -710,6 +724,7 @@ __global__ void latent_pack_kernel(const float* __restrict__ z, const float* __r
     *reinterpret_cast<uint4*>(out + pix * 64 + oct * 8) = pack8(f);
 }
 void launch_latent_pack(const float* z, const float* wpq, const float* bpq, bf16* out, int B, int hw, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * hw * 8;
     latent_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, wpq, bpq, out, hw, total);
     COUNT_LAUNCH();
@@ -731,6 +746,7 @@ __global__ void latent_unpack_bwd_kernel(const bf16* __restrict__ d, const float
     }
 }
 void launch_latent_unpack_bwd(const bf16* d, const float* wpq, float* dz, int B, int hw, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * hw;
     latent_unpack_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d, wpq, dz, hw, total);
     COUNT_LAUNCH();
@@ -753,6 +769,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict_
     }
 }
 void launch_upsample2x(const bf16* in, bf16* out, int B, int h, int w, int C, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * h * w * (C / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -785,6 +802,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restr
     }
 }
 void launch_upsample2x_bwd(const bf16* dout, bf16* din, int B, int h, int w, int C, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * h * w * (C / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -806,6 +824,7 @@ __global__ void image_pack_kernel(const float* __restrict__ dimg, bf16* __restri
     *reinterpret_cast<uint4*>(out + pix * 64 + oct * 8) = pack8(f);
 }
 void launch_image_pack(const float* dimg, bf16* out, int B, long long hw, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * hw * 8;
     image_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dimg, out, hw, total);
     COUNT_LAUNCH();
@@ -871,6 +890,7 @@ __global__ void __launch_bounds__(256) image_loss_grad_kernel(const float* __res
 }
 void launch_image_loss(const float* out, const float* target, const float* source, int B, long long per_image,
                        float rec_l, float pert_l, float* rec, float* pert, float* dout, void* ws, cudaStream_t s) {
+    if (g_dry_run) return;
     double* part = reinterpret_cast<double*>(ws);
     dim3 grid(kImgChunks, B);
     image_loss_partial_kernel<<<grid, 256, 0, s>>>(out, target, source, part, per_image);
@@ -888,6 +908,7 @@ __global__ void posterior_sample_kernel(const float* __restrict__ moments, const
     z[i] = noise ? fmaf(expf(0.5f * lv), noise[i], mu) : mu;
 }
 void launch_posterior_sample(const float* moments, const float* noise, float* z, int B, int hw, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * 4 * hw;
     posterior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(moments, noise, z, 4 * hw, total);
     COUNT_LAUNCH();
@@ -906,6 +927,7 @@ __global__ void posterior_sample_bwd_kernel(const float* __restrict__ moments, c
 }
 void launch_posterior_sample_bwd(const float* moments, const float* noise, const float* dz, float* dmoments, int B,
                                  int hw, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * 4 * hw;
     posterior_sample_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(moments, noise, dz, dmoments, 4 * hw, total);
     COUNT_LAUNCH();
@@ -950,6 +972,7 @@ __global__ void __launch_bounds__(256) pgd_linf_kernel(float* __restrict__ x_adv
 
 void launch_pgd_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
                      long long n, cudaStream_t s) {
+    if (g_dry_run) return;
     long long blocks = ((n >> 2) + 255) / 256;
     const long long cap = (long long)kNumSMs * 8;  // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
@@ -1022,6 +1045,7 @@ __global__ void __launch_bounds__(256) l2_project_kernel(float* __restrict__ x_a
 
 void launch_pgd_l2(float* x_adv, const float* grad, const float* x, const float* mask, float eps, float step, float lo,
                    float hi, int B, int C, long long hw, void* ws, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long per_image = (long long)C * hw;
     double* part = reinterpret_cast<double*>(ws);
     double* part2 = part + (size_t)B * kL2Chunks;
@@ -1042,6 +1066,7 @@ __global__ void add_delta_kernel(const float* __restrict__ x, const float* __res
         out[i] = __fadd_rn(x[i], delta[i % per_image]);   // :132  source_image + perturbation
 }
 void launch_add_delta(const float* x, const float* delta, float* out, int B, long long per_image, cudaStream_t s) {
+    if (g_dry_run) return;
     const long long total = (long long)B * per_image;
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -1060,6 +1085,7 @@ __global__ void batch_sum_kernel(const float* __restrict__ g, float* __restrict_
     }
 }
 void launch_batch_sum(const float* g, float* out, int B, long long per_image, float scale, cudaStream_t s) {
+    if (g_dry_run) return;
     long long blocks = (per_image + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     batch_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, out, B, per_image, scale);
@@ -1082,6 +1108,7 @@ __global__ void __launch_bounds__(256) universal_step_kernel(float* __restrict__
 }
 void launch_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
                            float hi, long long n, void* ws, cudaStream_t s) {
+    if (g_dry_run) return;
     double* part = reinterpret_cast<double*>(ws);
     dim3 grid(kL2Chunks, 1);
     l2_sumsq_kernel<<<grid, 256, 0, s>>>(grad, part, n);
@@ -1089,6 +1116,29 @@ void launch_universal_step(float* delta, const float* grad, const float* source,
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     universal_step_kernel<<<(unsigned)blocks, 256, 0, s>>>(delta, grad, source, part, eps, step, lo, hi, n);
     COUNT_LAUNCH(); COUNT_LAUNCH();
+}
+
+
+// delta <- for each source image s in order: clamp(source_s + delta, lo, hi) - source_s      (old/train_noise.py:183-185,
+// one image per reference step; several sources = the same statement applied once per image of the step's batch)
+__global__ void __launch_bounds__(256) universal_project_kernel(float* __restrict__ delta, const float* __restrict__ sources,
+                                                                int nsrc, float lo, float hi, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float d = delta[i];
+        for (int s = 0; s < nsrc; ++s) {
+            const float x = sources[(size_t)s * n + i];
+            d = __fsub_rn(clamp_nan(__fadd_rn(x, d), lo, hi), x);
+        }
+        delta[i] = d;
+    }
+}
+void launch_universal_project(float* delta, const float* sources, int nsrc, float lo, float hi, long long n, cudaStream_t s) {
+    if (g_dry_run) return;
+    long long blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    universal_project_kernel<<<(unsigned)blocks, 256, 0, s>>>(delta, sources, nsrc, lo, hi, n);
+    COUNT_LAUNCH();
 }
 
 }  // namespace tml

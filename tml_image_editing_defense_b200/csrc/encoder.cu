@@ -202,9 +202,40 @@ int tml_encoder_finalize(TmlEncoder* e, void* stream) {
     return 0;
 }
 
+static int enc_forward_walk(TmlEncoder* e, Run& r, const float* x, float* moments);
+static int enc_backward_walk(TmlEncoder* e, Run& r, const float* dmoments, float* dx, float beta);
+
+// build_layout + the scratch size: a dry run (launchers disabled) of both walks with the same arena gives the exact
+// peak, so the size reported by tml_encoder_query is what the real walks use -- nothing is launched on an estimate.
+static int enc_layout(TmlEncoder* e, int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) { set_error("bad shape B=%d H=%d W=%d", B, H, W); return -30; }
+    RC(build_layout(e, B, H, W));
+    Layout& L = e->lay;
+    if (L.measured) return 0;
+    char* fake = reinterpret_cast<char*>(uintptr_t(1) << 20);   // never dereferenced
+    size_t peak = 0;
+    int rc = 0;
+    g_dry_run = true;
+    {
+        Run r{e, fake, fake, Arena(), nullptr, B};
+        rc = enc_forward_walk(e, r, reinterpret_cast<const float*>(fake), reinterpret_cast<float*>(fake));
+        peak = r.wsa.peak;
+    }
+    if (rc == 0) {
+        Run r{e, fake, fake, Arena(), nullptr, B};
+        rc = enc_backward_walk(e, r, reinterpret_cast<const float*>(fake), reinterpret_cast<float*>(fake), 0.f);
+        peak = std::max(peak, r.wsa.peak);
+    }
+    g_dry_run = false;
+    if (rc) { L = Layout(); return rc; }
+    L.ws_bytes = peak + 1024;
+    L.measured = true;
+    return 0;
+}
+
 int tml_encoder_query(TmlEncoder* e, int B, int H, int W, size_t* workspace_bytes, size_t* saved_bytes) {
     if (!e) { set_error("null handle"); return -1; }
-    RC(build_layout(e, B, H, W));
+    RC(enc_layout(e, B, H, W));
     if (workspace_bytes) *workspace_bytes = e->lay.ws_bytes;
     if (saved_bytes) *saved_bytes = e->lay.saved_bytes;
     return 0;
@@ -214,9 +245,17 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
                         void* stream) {
     if (!e || !e->finalized) { set_error("encoder not finalized"); return -1; }
     if (!x || !moments || !saved || !ws) { set_error("null buffer"); return -1; }
-    RC(build_layout(e, B, H, W));
-    const Layout& L = e->lay;
+    DeviceGuard guard(e->device);
+    RC(enc_layout(e, B, H, W));
     Run r{e, reinterpret_cast<char*>(saved), reinterpret_cast<char*>(ws), Arena(), reinterpret_cast<cudaStream_t>(stream), B};
+    RC(enc_forward_walk(e, r, x, moments));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int enc_forward_walk(TmlEncoder* e, Run& r, const float* x, float* moments) {
+    const Layout& L = e->lay;
+    const int B = L.B, H = L.H, W = L.W;
     const int C0 = e->cfg.block_out_channels[0];
     r.statbuf[0] = r.Walloc<float>(fused_partial_bytes(B, H, W));
     r.statbuf[1] = r.Walloc<float>(fused_partial_bytes(B, H, W));
@@ -255,8 +294,7 @@ int tml_encoder_forward(TmlEncoder* e, const float* x, int B, int H, int W, floa
         o.D_sB = (int64_t)L2 * h * w; o.D_sH = w; o.D_sW = 1; o.D_sN = (int64_t)h * w;
         RC(gemm_launch(o, e->num_sms, r.st));
     }
-    if (r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
-    CUDA_OK(cudaGetLastError());
+    if (L.measured && r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     return 0;
 }
 
@@ -264,10 +302,18 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
                          float beta, void* ws, void* stream) {
     if (!e || !e->finalized) { set_error("encoder not finalized"); return -1; }
     if (!dmoments || !saved || !ws || !dx) { set_error("null buffer"); return -1; }
-    RC(build_layout(e, B, H, W));
-    const Layout& L = e->lay;
+    DeviceGuard guard(e->device);
+    RC(enc_layout(e, B, H, W));
     Run r{e, const_cast<char*>(reinterpret_cast<const char*>(saved)), reinterpret_cast<char*>(ws), Arena(),
           reinterpret_cast<cudaStream_t>(stream), B};
+    RC(enc_backward_walk(e, r, dmoments, dx, beta));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int enc_backward_walk(TmlEncoder* e, Run& r, const float* dmoments, float* dx, float beta) {
+    const Layout& L = e->lay;
+    const int B = L.B, H = L.H, W = L.W;
     // ping-pong gradient buffers
     size_t gmax = 0;
     {
@@ -337,8 +383,7 @@ int tml_encoder_backward(TmlEncoder* e, const float* dmoments, int B, int H, int
         launch_conv_in_col2im(Y, dx, B, H, W, beta, r.st);
         r.wsa.reset(m);
     }
-    if (r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
-    CUDA_OK(cudaGetLastError());
+    if (L.measured && r.wsa.peak > L.ws_bytes) { set_error("internal: workspace overrun (%zu > %zu)", r.wsa.peak, L.ws_bytes); return -40; }
     return 0;
 }
 
@@ -390,6 +435,14 @@ int tml_universal_step(float* delta, const float* grad, const float* source, flo
                        int64_t n, void* ws, void* stream) {
     if (!delta || !grad || !ws) { set_error("null buffer"); return -1; }
     launch_universal_step(delta, grad, source, eps, step, lo, hi, n, ws, reinterpret_cast<cudaStream_t>(stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tml_universal_project(float* delta, const float* sources, int nsrc, float lo, float hi, int64_t n, void* stream) {
+    if (!delta || (!sources && nsrc > 0)) { set_error("null buffer"); return -1; }
+    if (nsrc <= 0 || n <= 0) return 0;
+    launch_universal_project(delta, sources, nsrc, lo, hi, n, reinterpret_cast<cudaStream_t>(stream));
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -1428,13 +1428,21 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     return 0;
 }
 
+// "dynamic shared memory limit raised" flags, one per (device, kernel family): the attribute is per device
+static bool& attr_flag(int family) {
+    static bool flags[2][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return flags[family][dev & 63];
+}
+
 // One mapped host word per process: a kernel whose mbarrier wait times out stores the id of that wait here
 // before trapping, so the failure can be attributed after the context is gone.
 static int* g_hang_host = nullptr;
 static int* g_hang_dev = nullptr;
 static volatile int* hang_word_device() {
     if (!g_hang_host) {
-        if (cudaHostAlloc(reinterpret_cast<void**>(&g_hang_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_hang_host), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             g_hang_host = nullptr;
             return nullptr;
@@ -1538,7 +1546,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
         static const SwKernel table[3][2][2] = {SW_ROW(1, false), SW_ROW(2, false), SW_ROW(4, false)};
         static const SwKernel ptable[2][2][2] = {SW_ROW(2, true), SW_ROW(4, true)};
 #undef SW_ROW
-        static bool attr_set = false;
+        bool& attr_set = attr_flag(0);   // cudaFuncSetAttribute is per device
         if (!attr_set) {
             for (int b = 0; b < 2; ++b)
                 for (int c = 0; c < 2; ++c) {
@@ -1655,7 +1663,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne; }
 
-    static bool attr_set = false;
+    bool& attr_set = attr_flag(1);   // cudaFuncSetAttribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxSmem);
@@ -1703,6 +1711,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
 }
 
 int gemm_launch(const GemmOp& op, int num_sms, cudaStream_t stream) {
+    if (g_dry_run) return 0;
     if (g_impl.load() == 1) return gemm_launch_simt(op, stream);
     return gemm_launch_tc(op, num_sms, stream);
 }

@@ -8,6 +8,11 @@ namespace tml {
 
 typedef __nv_bfloat16 bf16;
 
+// Dry run (host only): while set, every launcher of this library returns without touching the GPU.  The network
+// walks are replayed this way when a layout is built, so the scratch size handed to the caller is the peak the real
+// walk will reach -- measured, not hand-accounted -- before any kernel has been enqueued.
+extern thread_local bool g_dry_run;
+
 // conv_in (3 -> C0, 3x3 s1 p1), step 1: fp32 NCHW image -> bf16 NHWC [B,H,W,64]
 // (channels [0,3) hi = bf16(x), [3,6) lo = bf16(x - hi), rest 0); step 2 is a 3x3 convolution on the GEMM kernels.
 void launch_conv_in_pack(const float* x, bf16* a, int B, int H, int W, cudaStream_t s);
@@ -57,6 +62,7 @@ void launch_add_delta(const float* x, const float* delta, float* out, int B, lon
 void launch_batch_sum(const float* g, float* out, int B, long long per_image, float scale, cudaStream_t s);
 void launch_universal_step(float* delta, const float* grad, const float* source, float eps, float step, float lo,
                            float hi, long long n, void* ws, cudaStream_t s);
+void launch_universal_project(float* delta, const float* sources, int nsrc, float lo, float hi, long long n, cudaStream_t s);
 
 // ---- decoder-side helpers (vae.decode, main.py:156; image-space losses main.py:160,168) ----
 // z fp32 NCHW [B,4,hw] -> post_quant_conv (4x4 1x1 conv + bias, fp32) -> bf16 NHWC [B,hw,64], channels 4..63 zero

@@ -51,7 +51,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (the launch fails with an error the host
-// reports), never as a hung GPU.  No legitimate wait in these kernels lasts anywhere near 2 s.
+// reports), never as a hung GPU.  The budget is wall time (%globaltimer), so it has to cover everything that can
+// stretch a legitimate wait -- profiler replay, a debugger, time-slicing with another context, a co-scheduled kernel
+// on another stream: 20 s by default (no wait of these kernels lasts longer than a tile, ~10 us).
+// -DTML_WAIT_TIMEOUT_NS=0 compiles the plain unbounded try_wait loop.
+#ifndef TML_WAIT_TIMEOUT_NS
+#define TML_WAIT_TIMEOUT_NS 20000000000ull
+#endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -60,15 +66,20 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // `where` (optional, mapped host memory) receives `tag` before the trap so the host can tell which wait hung.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* where = nullptr, int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
+#if TML_WAIT_TIMEOUT_NS == 0
+    (void)where; (void)tag;
+    while (!mbar_try_wait(bar, parity)) {}
+#else
     const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 1023u) != 0) continue;   // (keeps the timer read out of the common iteration)
-        if (global_timer_ns() - t0 > 2000000000ull) {
+        if (global_timer_ns() - t0 > TML_WAIT_TIMEOUT_NS) {
             if (where) { *where = tag; __threadfence_system(); }
             __trap();
         }
     }
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -60,6 +60,17 @@ static float half2f(uint16_t h) {
         if (_r) return _r;    \
     } while (0)
 
+// Makes the handle's device current for the duration of a C-ABI call and restores the caller's device afterwards
+// (the caller may be a framework that tracks the current device itself).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 struct HostTensor {
     std::vector<float> v;
     std::vector<int64_t> shape;
@@ -181,6 +192,7 @@ struct Arena {
 struct Layout {
     int B = 0, H = 0, W = 0;
     size_t saved_bytes = 0, ws_bytes = 0;
+    bool measured = false;   // ws_bytes has been replaced by the peak of a dry run of both walks
     size_t x0 = 0;  // conv_in output
     std::vector<ResnetRec> res;
     std::vector<DownRec> down;
@@ -194,6 +206,7 @@ struct UpRec { size_t out = 0; int h = 0, w = 0; };   // Upsample2D: (h, w) = in
 struct DecLayout {
     int B = 0, h = 0, w = 0;             // latent size
     size_t saved_bytes = 0, ws_bytes = 0;
+    bool measured = false;               // as in Layout
     size_t x0 = 0;                       // decoder.conv_in output
     std::vector<ResnetRec> res;
     AttnRec attn;
@@ -465,7 +478,7 @@ inline char* g_dump_base = nullptr;
 inline size_t g_dump_slot = 0;
 inline int g_dump_slots = 0, g_dump_next = 0;
 inline void dump_grad(const void* p, size_t bytes, cudaStream_t st) {
-    if (!g_dump_base || g_dump_next >= g_dump_slots) return;
+    if (g_dry_run || !g_dump_base || g_dump_next >= g_dump_slots) return;
     cudaMemcpyAsync(g_dump_base + (size_t)g_dump_next * g_dump_slot, p, bytes < g_dump_slot ? bytes : g_dump_slot,
                     cudaMemcpyDeviceToDevice, st);
     ++g_dump_next;

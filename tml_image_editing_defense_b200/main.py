@@ -69,8 +69,12 @@ def main(argv=None) -> int:
         ut = UniversalTrainer.for_b200(ucfg, vae)
         delta = torch.zeros((1, 3, args.resolution, args.resolution), device=dev)
         tg = target.expand(len(idx), -1, -1, -1).contiguous()
+        ut.prepare_projection(images)
+        # latent_dist.sample(generator) (old/train_noise.py:133): seeded posterior noise, fresh every step, per image
+        gen = torch.Generator(device=dev).manual_seed(args.seed * 7919 + rank)
         for _ in range(args.max_train_steps):
-            delta = ut.step(delta, images, tg, None, n_global=n, micro_batch=args.train_batch_size)
+            nz = torch.randn(tg.shape, generator=gen, device=dev)
+            delta = ut.step(delta, images, tg, nz, n_global=n, micro_batch=args.train_batch_size)
         same = ut.check_replicas_identical(delta)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -79,7 +83,7 @@ def main(argv=None) -> int:
                           "seconds": dt, "image_grad_evals_per_s": len(idx) * args.max_train_steps * args.grad_reps / dt,
                           "replicas_identical": same, "delta_abs_max": float(delta.abs().max())}), flush=True)
     else:
-        cfg = TrainConfig(norm_type=args.norm_type, eps=args.eps, step_size=args.step_size, grad_reps=args.grad_reps,
+        cfg = TrainConfig.encoder_attack(norm_type=args.norm_type, eps=args.eps, step_size=args.step_size, grad_reps=args.grad_reps,
                           min_value=args.min_value, max_value=args.max_value, override_from_norm_type=False,
                           n_optimization_steps=args.max_train_steps, latent_loss=args.latent_loss, seed=args.seed,
                           device=dev, resolution=args.resolution, output_path=out_dir)
@@ -88,6 +92,9 @@ def main(argv=None) -> int:
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         torch.save({"indices": idx, "x_adv": x_adv.cpu()}, out_dir / f"adversarial_rank{rank}.pt")
+        # main.py:619: the fixed training noises, so inference can replay them (main.py:622)
+        torch.save([n.cpu() for n in tr.noises] if tr.noises is not None else None,
+                   out_dir / ("noise.pt" if world == 1 else f"noise_rank{rank}.pt"))
         try:
             for i, im in zip(idx[:4], Trainer.to_pil(x_adv[:4])):
                 im.save(out_dir / f"adversarial_image_{i}.png")   # main.py:618

@@ -12,8 +12,14 @@ import torch
 from . import _lib
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: torch.Tensor) -> int:
+    """The current stream of the tensor's own device (not of whatever device happens to be current)."""
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Pointer-only entry points launch on the current device: make it the tensor's device for the call."""
+    return torch.cuda.device(t.device)
 
 
 def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
@@ -32,8 +38,9 @@ def pgd_step_linf_(x_adv: torch.Tensor, grad: torch.Tensor, x: torch.Tensor, eps
     _chk(x_adv, "x_adv"), _chk(grad, "grad"), _chk(x, "x")
     assert x_adv.shape == grad.shape == x.shape
     lib = _lib.load()
-    _lib.check(lib.tml_pgd_step_linf(x_adv.data_ptr(), grad.data_ptr(), x.data_ptr(), eps, step, lo, hi,
-                                     x_adv.numel(), _stream()))
+    with _on(x_adv):
+        _lib.check(lib.tml_pgd_step_linf(x_adv.data_ptr(), grad.data_ptr(), x.data_ptr(), eps, step, lo, hi,
+                                         x_adv.numel(), _stream(x_adv)))
     return x_adv
 
 
@@ -48,9 +55,10 @@ def pgd_step_l2_(x_adv: torch.Tensor, grad: torch.Tensor, x: torch.Tensor, mask:
         assert mask.numel() == B * hw
     lib = _lib.load()
     ws = torch.empty(lib.tml_pgd_l2_workspace(B), dtype=torch.uint8, device=x.device)
-    _lib.check(lib.tml_pgd_step_l2(x_adv.data_ptr(), grad.data_ptr(), x.data_ptr(),
-                                   mask.data_ptr() if mask is not None else None, eps, step, lo, hi, B, Cc, hw,
-                                   ws.data_ptr(), _stream()))
+    with _on(x_adv):
+        _lib.check(lib.tml_pgd_step_l2(x_adv.data_ptr(), grad.data_ptr(), x.data_ptr(),
+                                       mask.data_ptr() if mask is not None else None, eps, step, lo, hi, B, Cc, hw,
+                                       ws.data_ptr(), _stream(x_adv)))
     return x_adv
 
 
@@ -69,9 +77,10 @@ def latent_loss(moments: torch.Tensor, noise: Optional[torch.Tensor], target: to
     loss = torch.empty(B, dtype=torch.float32, device=moments.device)
     dm = torch.empty_like(moments) if need_grad else None
     lib = _lib.load()
-    _lib.check(lib.tml_latent_loss(kind, moments.data_ptr(), noise.data_ptr() if noise is not None else None,
-                                   target.data_ptr(), B, h, w, grad_scale, z.data_ptr(), loss.data_ptr(),
-                                   dm.data_ptr() if dm is not None else None, _stream()))
+    with _on(moments):
+        _lib.check(lib.tml_latent_loss(kind, moments.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                       target.data_ptr(), B, h, w, grad_scale, z.data_ptr(), loss.data_ptr(),
+                                       dm.data_ptr() if dm is not None else None, _stream(moments)))
     return z, loss, dm
 
 
@@ -79,8 +88,9 @@ def add_delta(x: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
     """x[b] + delta for a shared perturbation (old/train_noise.py:132)."""
     _chk(x, "x"), _chk(delta, "delta")
     out = torch.empty_like(x)
-    _lib.check(_lib.load().tml_add_delta(x.data_ptr(), delta.data_ptr(), out.data_ptr(), x.shape[0], x[0].numel(),
-                                         _stream()))
+    with _on(x):
+        _lib.check(_lib.load().tml_add_delta(x.data_ptr(), delta.data_ptr(), out.data_ptr(), x.shape[0], x[0].numel(),
+                                             _stream(x)))
     return out
 
 
@@ -88,7 +98,8 @@ def batch_sum(g: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """scale * sum over the batch dimension in image order (gradient of the shared delta)."""
     _chk(g, "g")
     out = torch.empty((1,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
-    _lib.check(_lib.load().tml_batch_sum(g.data_ptr(), out.data_ptr(), g.shape[0], g[0].numel(), scale, _stream()))
+    with _on(g):
+        _lib.check(_lib.load().tml_batch_sum(g.data_ptr(), out.data_ptr(), g.shape[0], g[0].numel(), scale, _stream(g)))
     return out
 
 
@@ -99,9 +110,22 @@ def universal_step_(delta: torch.Tensor, grad: torch.Tensor, source: Optional[to
     if source is not None:
         _chk(source, "source")
     ws = torch.empty(4096, dtype=torch.uint8, device=delta.device)
-    _lib.check(_lib.load().tml_universal_step(delta.data_ptr(), grad.data_ptr(),
-                                              source.data_ptr() if source is not None else None, eps, step, lo, hi,
-                                              delta.numel(), ws.data_ptr(), _stream()))
+    with _on(delta):
+        _lib.check(_lib.load().tml_universal_step(delta.data_ptr(), grad.data_ptr(),
+                                                  source.data_ptr() if source is not None else None, eps, step, lo, hi,
+                                                  delta.numel(), ws.data_ptr(), _stream(delta)))
+    return delta
+
+
+def universal_project_(delta: torch.Tensor, sources: torch.Tensor, lo: float = -1.0, hi: float = 1.0) -> torch.Tensor:
+    """In place, for each source image in order: delta = clamp(source + delta, lo, hi) - source
+    (old/train_noise.py:183-185).  ``sources``: [n, *delta.shape[1:]]."""
+    _chk(delta, "delta"), _chk(sources, "sources")
+    assert sources.numel() % delta.numel() == 0
+    with _on(delta):
+        _lib.check(_lib.load().tml_universal_project(delta.data_ptr(), sources.data_ptr(),
+                                                     sources.numel() // delta.numel(), lo, hi, delta.numel(),
+                                                     _stream(delta)))
     return delta
 
 
@@ -112,8 +136,9 @@ def posterior_sample(moments: torch.Tensor, noise: Optional[torch.Tensor]) -> to
     z = torch.empty((B, c2 // 2, h, w), dtype=torch.float32, device=moments.device)
     if noise is not None:
         _chk(noise, "noise")
-    _lib.check(_lib.load().tml_posterior_sample(moments.data_ptr(), noise.data_ptr() if noise is not None else None,
-                                                z.data_ptr(), B, h, w, _stream()))
+    with _on(moments):
+        _lib.check(_lib.load().tml_posterior_sample(moments.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                                    z.data_ptr(), B, h, w, _stream(moments)))
     return z
 
 
@@ -121,9 +146,10 @@ def posterior_sample_backward(moments: torch.Tensor, noise: Optional[torch.Tenso
     _chk(moments, "moments"), _chk(dz, "dz")
     B, c2, h, w = moments.shape
     dm = torch.empty_like(moments)
-    _lib.check(_lib.load().tml_posterior_sample_backward(moments.data_ptr(),
-                                                         noise.data_ptr() if noise is not None else None,
-                                                         dz.data_ptr(), dm.data_ptr(), B, h, w, _stream()))
+    with _on(moments):
+        _lib.check(_lib.load().tml_posterior_sample_backward(moments.data_ptr(),
+                                                             noise.data_ptr() if noise is not None else None,
+                                                             dz.data_ptr(), dm.data_ptr(), B, h, w, _stream(moments)))
     return dm
 
 
@@ -141,7 +167,8 @@ def image_loss(out: torch.Tensor, target: torch.Tensor, source: Optional[torch.T
     dout = torch.empty_like(out) if need_grad else None
     lib = _lib.load()
     ws = torch.empty(lib.tml_image_loss_workspace(B), dtype=torch.uint8, device=out.device)
-    _lib.check(lib.tml_image_loss(out.data_ptr(), target.data_ptr(), source.data_ptr() if source is not None else None,
-                                  B, out[0].numel(), rec_lambda, pert_lambda, rec.data_ptr(), pert.data_ptr(),
-                                  dout.data_ptr() if dout is not None else None, ws.data_ptr(), _stream()))
+    with _on(out):
+        _lib.check(lib.tml_image_loss(out.data_ptr(), target.data_ptr(), source.data_ptr() if source is not None else None,
+                                      B, out[0].numel(), rec_lambda, pert_lambda, rec.data_ptr(), pert.data_ptr(),
+                                      dout.data_ptr() if dout is not None else None, ws.data_ptr(), _stream(out)))
     return rec, pert, dout

@@ -1,7 +1,8 @@
 """Command-line flags for the launcher, named after the (unused) argparse list the reference
 carries in utils/parser.py (``--resolution`` :116, ``--train_batch_size`` :139, ``--seed`` :114,
 ``--mixed_precision`` :322, ``--local_rank`` :332, ``--pretrained_vae_model_name_or_path``,
-``--max_train_steps``, ``--output_dir``) plus the PGD options of configs.py:121-141."""
+``--max_train_steps``, ``--output_dir``, ``--gradient_checkpointing`` :180, ``--allow_tf32`` :266) plus the
+PGD options of configs.py:121-141."""
 from __future__ import annotations
 
 import argparse
@@ -22,6 +23,12 @@ def parse_args(input_args=None):
     p.add_argument("--mixed_precision", type=str, default="bf16", choices=["bf16"],
                    help="Activations/weights inside the encoder kernels; the iterate stays fp32.")
     p.add_argument("--local_rank", type=int, default=-1)
+    p.add_argument("--gradient_checkpointing", action="store_true",
+                   help="Diffusion attack: recompute each UNet step in the backward (activation checkpointing, "
+                        "utils/parser.py:180).  The encoder attack keeps only what its input gradient needs.")
+    p.add_argument("--allow_tf32", action="store_true",
+                   help="Accepted for call-site compatibility (utils/parser.py:266); the sm_100a kernels compute in "
+                        "bf16 with fp32 accumulation and take no TF32 path, so the flag changes nothing here.")
     p.add_argument("--norm_type", type=str, default="linf", choices=["linf", "l2"])
     p.add_argument("--eps", type=float, default=32 / 255)
     p.add_argument("--step_size", type=float, default=4 / 255)

@@ -4,7 +4,7 @@ Method names, argument names and return shapes follow the reference so call site
 
   * ``run()``                main.py:47-142   loop: grad_reps x compute_grad -> mean -> perturbation_step
   * ``compute_grad(...)``    main.py:144-177  -> (grad, loss: float, output_image, {'rec_loss','pert_loss'})
-  * ``attack_forward(...)``  main.py:179-246  encoder line :191 (the UNet loop is SURVEY 8f n2, not built)
+  * ``attack_forward(...)``  main.py:179-246  encoder line :191 (the UNet loop lives in diffusion.py::DiffusionAttack)
   * ``perturbation_step()``  main.py:248-276  linf / l2
 
 All arithmetic on images and latents runs in the CUDA kernels behind the C ABI; this file is
@@ -87,7 +87,7 @@ class Trainer:
                                                grad_out=grad[s:e], beta=beta, grad_scale=self.cfg.rec_loss_lambda)
                 losses[s:e] = l
         else:
-            main = torch.cuda.current_stream()
+            main = torch.cuda.current_stream(self.device)
             ready = torch.cuda.Event()
             ready.record(main)
             used = self._streams[:min(len(self._streams), len(chunks))]

@@ -3,8 +3,14 @@
 One shared ``delta`` [1,3,H,W]; each rank owns the images ``rank::world_size``; per step every rank
 sums d loss_i / d delta over its images, the sums are all-reduced (the only collective on the whole
 hot path: 3*H*W fp32 = 3.1 MB at 512^2, NCCL over NVLink/NVSwitch), divided by the global image
-count, and every rank applies the identical update (L2-normalised step, +-eps clamp, optional
-image-range projection, old/train_noise.py:173-185).
+count, and every rank applies the identical update (L2-normalised step, +-eps clamp, old/train_noise.py:173-180).
+
+``cfg.apply_image_pertubation`` (:182-185, default True): the reference re-projects the perturbation so that the one
+image of its step stays in [-1, 1]: ``perturbation = clamp(source + perturbation, -1, 1) - source``.  A sharded step
+sees every image, so the same statement is applied against the two extreme images that bound them all -- the
+per-pixel minimum and maximum over the whole dataset (``prepare_projection``: computed once, MIN/MAX all-reduced, so
+every replica clamps to the identical interval [-1 - min_i x_i, 1 - max_i x_i], which is what applying the
+reference statement image after image converges to since every per-image interval contains 0).
 
 The compute callables are injected so the host logic (sharding, reduction, identical replicas) is
 testable on CPU with the gloo backend and the oracle; the default callables are the B200 kernels.
@@ -31,13 +37,17 @@ class UniversalTrainer:
                  grad_fn: Callable[[torch.Tensor, torch.Tensor, Optional[torch.Tensor]], torch.Tensor],
                  sum_fn: Callable[[torch.Tensor], torch.Tensor],
                  add_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
-                 step_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]):
+                 step_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                 project_fn: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None):
         """grad_fn(x_perturbed, target_latent, noise) -> d sum_i loss_i / d x  [b,3,H,W]
         sum_fn(g) -> [1,3,H,W] sum over the batch in image order
-        add_fn(x, delta) -> x + delta ; step_fn(delta, grad) -> updated delta (in place allowed)."""
+        add_fn(x, delta) -> x + delta ; step_fn(delta, grad) -> updated delta (in place allowed)
+        project_fn(delta, sources [n,3,H,W]) -> delta re-projected against each source in order (:183-185)."""
         self.cfg = cfg
         self.grad_fn, self.sum_fn, self.add_fn, self.step_fn = grad_fn, sum_fn, add_fn, step_fn
+        self.project_fn = project_fn
         self.rank, self.world = _world()
+        self._bounds: Optional[torch.Tensor] = None     # [2,3,H,W]: per-pixel (min, max) image of the whole dataset
 
     @classmethod
     def for_b200(cls, cfg: UniversalConfig, vae) -> "UniversalTrainer":
@@ -50,7 +60,26 @@ class UniversalTrainer:
         def step_fn(delta, grad):
             return ops.universal_step_(delta, grad, None, float(cfg.eps), float(cfg.step_size))
 
-        return cls(cfg, grad_fn, ops.batch_sum, ops.add_delta, step_fn)
+        return cls(cfg, grad_fn, ops.batch_sum, ops.add_delta, step_fn, ops.universal_project_)
+
+    def prepare_projection(self, images: torch.Tensor) -> None:
+        """Per-pixel (min, max) over every rank's images: the bounds of old/train_noise.py:183-185 for the whole
+        dataset.  Called once (the images do not change); a no-op when ``apply_image_pertubation`` is off."""
+        if not self.cfg.apply_image_pertubation:
+            self._bounds = None
+            return
+        if self.project_fn is None:
+            raise ValueError("apply_image_pertubation=True needs a project_fn (old/train_noise.py:182-185)")
+        if images.shape[0]:
+            lo, hi = images.amin(dim=0), images.amax(dim=0)
+        else:   # an empty shard must not constrain the others
+            shape = images.shape[1:]
+            lo = torch.full(shape, float("inf"), dtype=images.dtype, device=images.device)
+            hi = torch.full(shape, float("-inf"), dtype=images.dtype, device=images.device)
+        if self.world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        self._bounds = torch.stack([lo, hi]).contiguous()
 
     def local_indices(self, n_images: int) -> List[int]:
         return shard_indices(n_images, self.rank, self.world)
@@ -58,6 +87,8 @@ class UniversalTrainer:
     def step(self, delta: torch.Tensor, images: torch.Tensor, targets: torch.Tensor,
              noises: Optional[torch.Tensor], n_global: int, micro_batch: int = 16) -> torch.Tensor:
         """One update of the shared delta from this rank's shard (`images` = local shard)."""
+        if self.cfg.apply_image_pertubation and self._bounds is None:
+            self.prepare_projection(images)
         total = torch.zeros_like(delta)
         for _ in range(self.cfg.grad_reps):                       # old/train_noise.py:130
             for s in range(0, images.shape[0], micro_batch):
@@ -68,7 +99,10 @@ class UniversalTrainer:
         if self.world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.SUM)          # the one exchange step
         total /= float(n_global * self.cfg.grad_reps)             # :166 mean over reps (and images)
-        return self.step_fn(delta, total)
+        delta = self.step_fn(delta, total)                        # :169-180
+        if self.cfg.apply_image_pertubation and self._bounds is not None:
+            delta = self.project_fn(delta, self._bounds)          # :182-185
+        return delta
 
     def check_replicas_identical(self, delta: torch.Tensor) -> bool:
         if self.world == 1:

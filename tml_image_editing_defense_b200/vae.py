@@ -8,7 +8,8 @@ Seams mirrored (file:line in /root/reference):
   * differentiable w.r.t. the image under ``torch.autograd.grad``    main.py:176
 
 The encoder forward and its input-gradient backward run in the sm_100a kernels behind the C ABI
-(``include/tml_b200.h``).  ``vae.decode`` is outside this round's scope and raises.
+(``include/tml_b200.h``); so do ``vae.decode`` (main.py:156) and its gradient w.r.t. the latent when the
+state dict carries the decoder ("decoder.*", "post_quant_conv.*") -- without those keys ``decode`` raises.
 """
 from __future__ import annotations
 
@@ -113,6 +114,8 @@ class AutoencoderKL:
     def __init__(self, config: Optional[EncoderConfig] = None, device: str = "cuda:0"):
         self.config = config or EncoderConfig()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())   # a concrete index: streams are per device
         self.dtype = torch.float32          # image / moments dtype at the seam (reference runs fp32, main.py:33)
         self.compute_dtype = torch.bfloat16  # activations and weights inside the kernels; fp32 accumulate
         self._lib = _lib.load()
@@ -189,7 +192,7 @@ class AutoencoderKL:
         ws_b, sv_b = C.c_size_t(), C.c_size_t()
         q = self._lib.tml_decoder_query if decoder else self._lib.tml_encoder_query
         _lib.check(q(self._h, B, H, W, C.byref(ws_b), C.byref(sv_b)))
-        key = torch.cuda.current_stream().cuda_stream
+        key = torch.cuda.current_stream(self.device).cuda_stream
         ws = self._ws.get(key)
         if ws is None or ws.numel() < ws_b.value:
             self._ws.pop(key, None)
@@ -210,7 +213,7 @@ class AutoencoderKL:
             if keep:
                 saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
             else:
-                key = torch.cuda.current_stream().cuda_stream
+                key = torch.cuda.current_stream(self.device).cuda_stream
                 saved = self._scratch_saved.get(key)
                 if saved is None or saved.numel() < sv_bytes:
                     self._scratch_saved.pop(key, None)
@@ -221,7 +224,7 @@ class AutoencoderKL:
         f = 2 ** (len(self.config.block_out_channels) - 1)
         moments = torch.empty((B, L2, H // f, W // f), dtype=torch.float32, device=self.device)
         _lib.check(self._lib.tml_encoder_forward(self._h, x.data_ptr(), B, H, W, moments.data_ptr(), saved.data_ptr(),
-                                                 ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                                 ws.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
         return moments, saved
 
     def _backward_raw(self, dmoments: torch.Tensor, saved: torch.Tensor, shape, out: Optional[torch.Tensor] = None,
@@ -233,7 +236,7 @@ class AutoencoderKL:
             beta = 0.0
         _lib.check(self._lib.tml_encoder_backward(self._h, dmoments.data_ptr(), B, H, W, saved.data_ptr(),
                                                   out.data_ptr(), beta, ws.data_ptr(),
-                                                  torch.cuda.current_stream().cuda_stream))
+                                                  torch.cuda.current_stream(self.device).cuda_stream))
         return out
 
     # ------------------------------------------------------------------ reference-facing API
@@ -259,7 +262,7 @@ class AutoencoderKL:
         if keep:
             saved = torch.empty(sv_bytes, dtype=torch.uint8, device=self.device)
         else:
-            key = torch.cuda.current_stream().cuda_stream
+            key = torch.cuda.current_stream(self.device).cuda_stream
             saved = self._scratch_saved_dec.get(key)
             if saved is None or saved.numel() < sv_bytes:
                 self._scratch_saved_dec.pop(key, None)
@@ -269,7 +272,7 @@ class AutoencoderKL:
         f = 2 ** (len(self.config.block_out_channels) - 1)
         image = torch.empty((B, 3, h * f, w * f), dtype=torch.float32, device=self.device)
         _lib.check(self._lib.tml_decoder_forward(self._h, z.data_ptr(), B, h, w, image.data_ptr(), saved.data_ptr(),
-                                                 ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                                 ws.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
         return image, saved
 
     def _decode_backward_raw(self, dimage: torch.Tensor, saved: torch.Tensor, zshape) -> torch.Tensor:
@@ -277,7 +280,7 @@ class AutoencoderKL:
         ws, _ = self._buffers(B, h, w, decoder=True)
         dz = torch.empty(zshape, dtype=torch.float32, device=self.device)
         _lib.check(self._lib.tml_decoder_backward(self._h, dimage.data_ptr(), B, h, w, saved.data_ptr(), dz.data_ptr(),
-                                                  ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                                  ws.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
         return dz
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
