@@ -5,10 +5,18 @@
     python bench.py --gpus N --steps K --warmup W              # this framework (one rank per GPU)
     python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
 
-One "step" = one PGD iteration for every image of the per-GPU batch: encoder forward, latent loss
-and its gradient, encoder input-gradient backward, fused sign-step / eps-projection / clamp.
-Images are independent, so N GPUs each run their own batch with no data-path collective
-(weak scaling: per-GPU batch fixed).  Prints ONE JSON line on rank 0.
+One "step" = one PGD iteration for every image of the batch: encoder forward, latent loss and its
+gradient, encoder input-gradient backward, fused sign-step / eps-projection / clamp.  Images are
+independent: rank r owns images r::N with no data-path collective.
+
+    --scaling strong (default)  the GLOBAL batch is fixed (configs[1]: 64 images "sharded across 1/2/4/8"):
+                                64 / 32 / 16 / 8 images per GPU; at N > 1 the same run also times the weak
+                                case (64 per GPU) and reports it under "weak".
+    --scaling weak              64 images per GPU whatever N.
+    --mode universal            configs[3]: shared-perturbation training (old/train_noise.py) over a synthetic
+                                dataset sharded r::N, one NCCL all-reduce of the 3xHxW gradient per step.
+
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -90,15 +98,25 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(res: int, B: int, world: int, mb: int, streams: int = 1):
+def workload_config(res: int, B: int, world: int, mb: int, streams: int = 1, scaling: str = "strong"):
     name = "SDXL VAE-encoder PGD attack (BASELINE configs[2])" if res == 1024 else \
         "SD-1.5 VAE-encoder PGD attack (BASELINE configs[1])"
-    return {"workload": f"{name}: batch {B} x {res}^2 per GPU, "
+    return {"workload": f"{name}: global batch {B * world} x {res}^2 ({B} per GPU, {scaling} scaling), "
                         f"bf16 activations/weights, fp32 accumulate, fp32 iterate, linf eps=16/255 step=2/255, "
                         f"random-init weights",
-            "global_batch": B * world, "per_gpu_batch": B, "micro_batch": mb, "streams": streams, "resolution": res,
-            "parallelism": f"dp{world} (independent images, no collective)",
+            "global_batch": B * world, "per_gpu_batch": B, "micro_batch": min(mb, B), "streams": streams,
+            "resolution": res,
+            "parallelism": f"dp{world} (images r::{world}, independent, no data-path collective)",
             "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)"}
+
+
+def per_gpu_batch(args, world: int) -> int:
+    """--batch is the configuration's batch: the global one under strong scaling, the per-GPU one under weak."""
+    if args.scaling == "weak":
+        return args.batch
+    if args.batch % world:
+        raise SystemExit(f"--scaling strong: global batch {args.batch} is not divisible by {world} GPUs")
+    return args.batch // world
 
 
 def synth_inputs(batch: int, res: int, seed: int, pin: bool):
@@ -140,8 +158,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.res, args.batch, args.gpus, args.micro_batch, args.streams),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.res, per_gpu_batch(args, max(1, args.gpus)), max(1, args.gpus), args.micro_batch,
+                                  args.streams, args.scaling),
         "cpu_baseline": {"value": value, "unit": "image-PGD-iters/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,7 +193,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    res, B, mb = args.res, args.batch, args.micro_batch
+    res, mb = args.res, args.micro_batch
+    B = per_gpu_batch(args, world)
     weights = random_init_state_dict(seed=0, include_decoder=args.loss == "images")
     vae = AutoencoderKL(device=str(dev)).load_state_dict(weights)
     del weights
@@ -184,46 +204,61 @@ def run_ours(args):
                       perturbation_loss_lambda=1.0 if args.loss == "images" else 0.0)
     tr = Trainer(cfg, vae, micro_batch=mb, num_streams=args.streams)
 
-    xh, th, nh = synth_inputs(B, res, 1000 + rank, pin=True)
-    x = xh.to(dev)
-    tgt, noise = th.to(dev), nh.to(dev)
-    x_adv = x.clone()
-    grad = torch.empty_like(x)
-    tr.noises = [noise]
-
-    tgt_img = None
-    if args.loss == "images":   # the reference's default losses on decoded images (main.py:156-171), UNet removed
-        tgt_img = (torch.rand((B, 3, res, res), generator=torch.Generator().manual_seed(7)) * 2 - 1).to(dev)
-
-    def step_device():
-        tr.compute_grad(x_adv, None, x, tgt_img, tgt, tr.noises, grad_out=grad, beta=0.0)
-        tr.perturbation_step(x_adv, grad, x, None)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def time_device(Bl: int, steps: int, warm: int, timed_gemms: bool):
+        """Device-resident throughput of `steps` PGD iterations over Bl images per GPU (inputs already in HBM).
+        Returns (ms max over ranks, this rank's tensors, GEMM timing tuple or None, launches)."""
+        xh_, th_, nh_ = synth_inputs(Bl, res, 1000 + rank, pin=True)
+        x_ = xh_.to(dev)
+        tgt_, noise_ = th_.to(dev), nh_.to(dev)
+        xa_ = x_.clone()
+        grad_ = torch.empty_like(x_)
+        tgt_img_ = None
+        if args.loss == "images":   # the reference's default losses on decoded images (main.py:156-171), UNet removed
+            tgt_img_ = (torch.rand((Bl, 3, res, res), generator=torch.Generator().manual_seed(7)) * 2 - 1).to(dev)
+
+        def step_device():
+            tr.compute_grad(xa_, None, x_, tgt_img_, tgt_, [noise_], grad_out=grad_, beta=0.0)
+            tr.perturbation_step(xa_, grad_, x_, None)
+
+        for _ in range(warm):
+            step_device()
+        barrier()
+        c0 = _lib.launch_counts()
+        if timed_gemms:
+            if rank == 0:
+                sampler.start()              # clocks are sampled during the timed region only
+            lib.tml_gemm_timing_enable(200000)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_device()
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        gt_ = None
+        if timed_gemms:
+            if rank == 0:
+                clock_box.append(sampler.stop())
+            gt_ = (C.c_double * 4)()
+            lib.tml_gemm_timing_collect(gt_)
+        c1 = _lib.launch_counts()
+        t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item()), (xh_, th_, nh_, x_, tgt_, noise_, xa_, grad_), gt_, (c1[0] - c0[0]) + (c1[1] - c0[1])
+
     # ------------------------------------------------------------------ device-resident throughput
     n_warm = args.warmup if args.quick else max(args.warmup, 3)
-    for _ in range(n_warm):
-        step_device()
-    barrier()
-    c0 = _lib.launch_counts()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    lib.tml_gemm_timing_enable(200000)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    gt = (C.c_double * 4)()
-    lib.tml_gemm_timing_collect(gt)
+    clock_box = []
+    ms_max, tensors, gt, launches = time_device(B, args.steps, n_warm, True)
+    xh, th, nh, x, tgt, noise, x_adv, grad = tensors
     if args.gemm_table and rank == 0:
         buf = C.create_string_buffer(1 << 16)
         n = lib.tml_gemm_timing_report(buf, len(buf))
@@ -237,14 +272,21 @@ def run_ours(args):
             print(f"{r[0]:24s} {r[1]:9d} {r[2]:5d} {r[3]:5d} {r[4]:4d} {r[5]:4d} {r[6] / args.steps:8.3f} "
                   f"{r[7] / (r[6] * 1e-3) / 1e12:8.1f}", file=sys.stderr)
     lib.tml_gemm_timing_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
-    c1 = _lib.launch_counts()
-    launches = (c1[0] - c0[0]) + (c1[1] - c0[1])
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    clocks = clock_box[0] if clock_box else None
     value = world * B * args.steps / (ms_max / 1e3)
+
+    # the other scaling mode, timed in the same run (N > 1 only: at N = 1 the two coincide)
+    other = None
+    if world > 1 and not args.quick and args.loss == "latents":
+        Bo = args.batch if args.scaling == "strong" else (args.batch // world if args.batch % world == 0 else 0)
+        if Bo > 0 and Bo != B:
+            ko = max(2, min(args.steps, 5))
+            ms_o, _t, _g, _l = time_device(Bo, ko, 2, False)
+            del _t
+            torch.cuda.empty_cache()
+            other = {"scaling": "weak" if args.scaling == "strong" else "strong", "per_gpu_batch": Bo,
+                     "global_batch": Bo * world, "steps": ko, "ms_per_step": ms_o / ko,
+                     "value": world * Bo * ko / (ms_o / 1e3), "unit": "image-PGD-iters/s"}
 
     if args.quick:
         if rank == 0:
@@ -296,7 +338,8 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     barrier()
-    k2 = max(2, min(args.steps, 5))
+    k2 = max(2, args.steps)      # the end-to-end number is timed over all --steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(k2):
         step_e2e()
@@ -366,15 +409,115 @@ def run_ours(args):
     line = {
         "metric": "image-PGD-iters/sec", "value": value, "unit": "image-PGD-iters/s", "n_gpus": world,
         "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(res, B, world, mb, args.streams),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(res, B, world, mb, args.streams, args.scaling),
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "image-PGD-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": k2},
         "roofline": roofline, "roofline_pgd_update": roofline_pgd, "cpu_baseline": cpu,
     }
+    if other is not None:
+        line[other["scaling"]] = other
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_universal(args):
+    """BASELINE configs[3]: universal-perturbation training (old/train_noise.py:115-185) over a synthetic dataset of
+    --dataset images sharded r::N.  One step = one update of the shared delta: every rank evaluates the encoder-attack
+    gradient of its images at x_i + delta, sums them in image order, ONE fp32 [1,3,H,W] NCCL all-reduce, then the
+    identical L2-normalised update, +-eps clamp and image-range re-projection on every rank."""
+    import torch.distributed as dist
+    from tml_image_editing_defense_b200 import _lib
+    from tml_image_editing_defense_b200.configs import UniversalConfig
+    from tml_image_editing_defense_b200.dataset import SyntheticImageDataset, shard_indices
+    from tml_image_editing_defense_b200.universal import UniversalTrainer
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    from tml_image_editing_defense_b200.weights import random_init_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    res, n_global, mb = args.res, args.dataset, args.micro_batch
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(random_init_state_dict(seed=0))
+    ucfg = UniversalConfig(grad_reps=1, eps=16 / 255 * 2, step_size=1.0, resolution=res, device=str(dev))
+    ut = UniversalTrainer.for_b200(ucfg, vae)
+    ut.comm_events = []
+    idx = shard_indices(n_global, rank, world)
+    ds = SyntheticImageDataset(n_global, resolution=res, seed=0)
+    images = ds.batch(idx).to(dev)
+    g = torch.Generator().manual_seed(17)
+    tg = torch.randn((1, 4, res // 8, res // 8), generator=g).to(dev).expand(len(idx), -1, -1, -1).contiguous()
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    delta = torch.zeros((1, 3, res, res), device=dev)
+    ut.prepare_projection(images)
+
+    def step(d):
+        nz = torch.randn(tg.shape, generator=gen, device=dev)      # latent_dist.sample(generator), :133
+        return ut.step(d, images, tg, nz, n_global=n_global, micro_batch=mb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        delta = step(delta)
+    barrier()
+    ut.comm_events = []
+    c0 = _lib.launch_counts()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        delta = step(delta)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = _lib.launch_counts()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    comm_us = [1e3 * a.elapsed_time(b) for a, b in ut.comm_events]
+    tc = torch.tensor([sum(comm_us) / max(1, len(comm_us))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tc, op=dist.ReduceOp.MIN)        # the rank that arrived last waits least: ~ the collective itself
+    same = ut.check_replicas_identical(delta)
+    in_range = bool(float((images + delta).abs().max()) <= 1.0 + 1e-6) if len(idx) else True
+    if rank == 0:
+        ms = float(t.item())
+        payload = delta.numel() * 4
+        line = {
+            "mode": "universal", "metric": "image-grad-evals/sec (universal perturbation step)",
+            "value": n_global * args.steps / (ms / 1e3), "unit": "image-grad-evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: universal perturbation (old/train_noise.py) over {n_global} synthetic "
+                                   f"{res}^2 images sharded r::{world}, grad_reps 1, one fp32 [1,3,{res},{res}] NCCL "
+                                   f"all-reduce per step, eps 32/255 step 1.0, image-range projection on",
+                       "dataset": n_global, "images_per_gpu": len(idx), "micro_batch": mb, "resolution": res},
+            "allreduce": {"payload_bytes": payload, "per_step": 1,
+                          "us_mean_rank0_incl_wait": sum(comm_us) / max(1, len(comm_us)),
+                          "us_mean_min_over_ranks": float(tc.item()),
+                          "share_of_step": (float(tc.item()) * 1e-3) / (ms / args.steps) if world > 1 else 0.0,
+                          "backend": "nccl" if world > 1 else "none (single rank)"},
+            "replicas_identical": same, "images_plus_delta_in_range": in_range,
+            "delta_abs_max": float(delta.abs().max()), "clocks": clocks,
+            "gpu_launches": (c1[0] - c0[0]) + (c1[1] - c0[1]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -443,14 +586,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU (configs[1]: 64)")
+    ap.add_argument("--batch", type=int, default=64,
+                    help="the configuration's batch (configs[1]: 64; configs[2]: --res 1024 --batch 16): the GLOBAL batch "
+                         "under --scaling strong, the per-GPU batch under --scaling weak")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: global batch fixed, images sharded r::N (BASELINE configs[1]); weak: --batch per GPU")
+    ap.add_argument("--dataset", type=int, default=512, help="--mode universal: images in the synthetic dataset (global)")
     ap.add_argument("--micro_batch", type=int, default=0,
                     help="images per encoder pass (0 = 32 up to 512^2, 16 above: measured 16 -> 32: +1 %% device, +1.7 %% end to end)")
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the micro-batches alternate on")
     ap.add_argument("--loss", default="latents", choices=["latents", "images"],
                     help="latents: the BASELINE encoder attack; images: + decoder and image-space losses (needs --quick)")
-    ap.add_argument("--mode", default="encoder", choices=["encoder", "diffusion"],
-                    help="diffusion: BASELINE configs[4] (4 DDIM steps of the SD-1.5 UNet, checkpointed; informational)")
+    ap.add_argument("--mode", default="encoder", choices=["encoder", "universal", "diffusion"],
+                    help="universal: BASELINE configs[3] (shared perturbation, one NCCL all-reduce per step); "
+                         "diffusion: BASELINE configs[4] (4 DDIM steps of the SD-1.5 UNet, checkpointed; informational)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--gemm_table", action="store_true", help="print per-shape GEMM times (stderr)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
@@ -459,6 +608,10 @@ def main():
         args.micro_batch = 32 if args.res <= 512 else 16
     if args.mode == "diffusion":
         return run_diffusion(args)
+    if args.mode == "universal":
+        if args.impl == "reference":
+            raise SystemExit("--mode universal has no reference arm")
+        return run_universal(args)
     if args.loss == "images" and not args.quick:
         raise SystemExit("--loss images is an informational mode: use it with --quick")
     if args.impl == "reference":

@@ -233,9 +233,12 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     const int es_out = op.out_fp32 ? 4 : 2;
     const bool dense_rows = op.D_sN == 1 && (op.n_store == 0 || op.n_store == op.N) && !(op.out_fp32 && op.beta != 0.f) &&
                             (op.D_sW * es_out) % 16 == 0 && (op.D_sH * es_out) % 16 == 0 && (op.D_sB * es_out) % 16 == 0;
-    if (!no_tma_store && !t->pair && op.gn_mode == 0 && dense_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
+    // (each of the 8 epilogue warps stages its own [32 rows][32 columns] x 2 buffers: rows_valid is a multiple of 32 and
+    // a warp's 32 rows are 32 pixels of one row or whole rows of the tile)
+    const bool warp_rows = t->rows_valid % 32 == 0 && (TW % 32 == 0 || 32 % TW == 0);
+    if (!no_tma_store && !t->pair && op.gn_mode == 0 && dense_rows && warp_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
         getenv("TML_DBG_NO_EPI") == nullptr)
-        t->out_bytes = 2 * 2 * 128 * 32 * es_out;
+        t->out_bytes = 8 * 2 * 32 * 32 * es_out;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
     int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - t->out_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -476,9 +479,134 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Lean epilogues (EPI != 0): compile-time specialised for the short-K GEMMs whose run time is the epilogue
+// (1x1 shortcuts, stride-2 parity dgrads, attention projections, conv_in tap products).  ncu of the generic
+// epilogue on a K = 128 shortcut (profiles/r02_prof_thin_shortcut_base.txt): ~390 SASS instructions per warp and
+// 32-column chunk -- runtime feature branches, operand-prefetch register shuffles, two 128-thread named barriers --
+// and 8000 clk per 128 x 256 sub-tile where the MMAs need 1024.  Here a warp owns its 32 rows end to end:
+// tcgen05.ld 32 columns -> alpha / bias (from shared memory) / residual -> pack -> its own [32 rows][32 cols]
+// staging buffer (two of them) -> its own TMA store.  Only __syncwarp between the steps; ~70 instructions per chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int EPI_GENERIC = 0, EPI_LEAN_BF16 = 1, EPI_LEAN_F32 = 2;
+
+template <int EPI>
+__device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorMap* mapD, uint8_t* out_stage, float* bias_s,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base, int tile0,
+                                              int tile_step, int total_tiles, volatile int* hw) {
+    constexpr int ES = EPI == EPI_LEAN_F32 ? 4 : 2;
+    constexpr int ROWB = 32 * ES;                       // bytes of one staged row (32 columns)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = warp - 4, q = e & 3, half = e >> 2;   // TMEM lane quadrant (rows 32q..32q+31), column half
+    const int et = int(threadIdx.x) - 128;
+    const int row = q * 32 + lane;
+    const bool warp_valid = q * 32 < p.rows_valid;      // rows_valid is a multiple of 32 here (host checks)
+    const int nch = p.BN >> 5;
+    const int ch_lo = half == 0 ? 0 : (nch + 1) / 2, ch_hi = half == 0 ? (nch + 1) / 2 : nch;
+    const int acc_cols = p.mt * p.BN;
+    uint8_t* const sbase = out_stage + size_t(e) * (2 * 32 * ROWB);
+    // the warp's 32 rows inside the tile's TW x TH pixel rectangle: 32 pixels of one row (TW >= 32) or 32/TW rows
+    const int wr = (q * 32) / p.TW, wc = q * 32 - wr * p.TW;
+    const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
+    const float alpha = p.alpha;
+    const bool has_bias = p.bias != nullptr, has_res = p.resid != nullptr;
+    int acc = 0, buf = 0, bias_nt = -1;
+    uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int nt = tile % p.n_tiles;
+        const int mtile = tile / p.n_tiles;
+        if (has_bias && nt != bias_nt) {   // this tile's bias columns -> shared memory (warp-uniform branch)
+            named_bar_sync(1, kEpiThreads);
+            for (int c = et; c < p.BN; c += kEpiThreads) bias_s[c] = __ldg(p.bias + nt * p.BN + c);
+            named_bar_sync(1, kEpiThreads);
+            bias_nt = nt;
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase, hw, 6);
+        tc_fence_after();
+        if (warp_valid) {
+            for (int sub = 0; sub < p.mt; ++sub) {
+                const SubTile stl = decode_sub(p, mtile, sub);
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
+                const __nv_bfloat16* rrow = nullptr;
+                if (has_res)
+                    rrow = p.resid + (long long)stl.img * p.R_sB + (long long)(stl.oh0 + r_th) * p.R_sH +
+                           (long long)(stl.ow0 + r_tw) * p.R_sW + nt * p.BN;
+#pragma unroll 1
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    const int c = ch * 32;
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + uint32_t(c), v);
+                    uint4 rr[4];
+                    if (has_res) {
+                        ld_global_nc_256(rrow + c, rr[0], rr[1]);
+                        ld_global_nc_256(rrow + c + 16, rr[2], rr[3]);
+                    }
+                    if (lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
+                    __syncwarp();
+                    tmem_ld_wait();
+                    float f[32];
+                    if (has_bias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+                            f[4 * j] = fmaf(__uint_as_float(v[4 * j]), alpha, b4.x);
+                            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b4.y);
+                            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b4.z);
+                            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+                    }
+                    if (has_res) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[8 * j + 0] += bf16_lo(rr[j].x); f[8 * j + 1] += bf16_hi(rr[j].x);
+                            f[8 * j + 2] += bf16_lo(rr[j].y); f[8 * j + 3] += bf16_hi(rr[j].y);
+                            f[8 * j + 4] += bf16_lo(rr[j].z); f[8 * j + 5] += bf16_hi(rr[j].z);
+                            f[8 * j + 6] += bf16_lo(rr[j].w); f[8 * j + 7] += bf16_hi(rr[j].w);
+                        }
+                    }
+                    uint8_t* sb = sbase + size_t(buf) * (32 * ROWB);
+                    uint8_t* rowp = sb + size_t(lane) * ROWB;
+                    if constexpr (EPI == EPI_LEAN_F32) {
+                        // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                                make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                    } else {
+                        // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(mapD, sb, nt * p.BN + c, stl.ow0 + wc, stl.oh0 + wr, stl.img);
+                        bulk_commit_group();
+                    }
+                    buf ^= 1;
+                }
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) bulk_wait_group<0>();   // staged tiles are in global memory before the CTA exits
+}
+
 // PAIR = true is the cta_group::2 instantiation (launched as clusters of two CTAs); the PAIR = false
-// instantiation contains no cluster instruction and is launched as an ordinary grid.
-template <bool PAIR>
+// instantiation contains no cluster instruction and is launched as an ordinary grid.  EPI selects the epilogue
+// (EPI_GENERIC: every feature behind runtime switches; EPI_LEAN_*: see above, single-CTA only).
+template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                          const __grid_constant__ CUtensorMap mapD, const TcParams p) {
@@ -766,6 +894,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
+    } else if (warp >= 4 && EPI != EPI_GENERIC) {
+        if constexpr (EPI != EPI_GENERIC && !PAIR)
+            lean_epilogue<EPI>(p, &mapD, out_stage, gn_red, tfull_bar, tempty_bar, tmem_base, tile0, tile_step, total_tiles, hw);
     } else if (warp >= 4) {
         // ===================================================================== epilogue
         // 8 warps: warp e handles TMEM lane quadrant e % 4 (rows 32q .. 32q+31 of the sub-tile) and
@@ -782,7 +913,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         const int ch_lo = half == 0 ? 0 : (nch + 1) / 2;  // this warp's chunk range
         const int ch_hi = half == 0 ? (nch + 1) / 2 : nch;
         const bool ld_res = p.resid != nullptr && p.dbg_no_epi != 2, ld_x = p.gn_mode == 2 && p.dbg_no_epi != 2;
-        int acc = 0, obuf = 0;
+        int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int nt = tile % p.n_tiles;
@@ -852,66 +983,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         }
                     }
                     tmem_ld_wait();
-                    if (p.out_bytes) {
-                        // staged epilogue: [128 rows][32 columns] per column half, two buffers, one TMA store per chunk
-                        const int es = p.out_fp32 ? 4 : 2;
-                        uint8_t* sbuf = out_stage + size_t((half * 2 + obuf) * 128 * 32 * es);
-                        if (q == 0 && lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
-                        named_bar_sync(2 + half, 128);
-                        if (p.alpha != 1.0f) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        }
-                        if (valid) {
-                            if (p.bias != nullptr) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.BN + c) + j);
-                                    f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-                                }
-                            }
-                            if (p.resid != nullptr) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint4 r = rres[j];
-                                    f[8 * j + 0] += bf16_lo(r.x); f[8 * j + 1] += bf16_hi(r.x);
-                                    f[8 * j + 2] += bf16_lo(r.y); f[8 * j + 3] += bf16_hi(r.y);
-                                    f[8 * j + 4] += bf16_lo(r.z); f[8 * j + 5] += bf16_hi(r.z);
-                                    f[8 * j + 6] += bf16_lo(r.w); f[8 * j + 7] += bf16_hi(r.w);
-                                }
-                            }
-                            if (p.out_fp32) {
-                                // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
-                                uint8_t* rowp = sbuf + size_t(row) * 128;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
-                                        make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                                   __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
-                            } else {
-                                // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
-                                uint8_t* rowp = sbuf + size_t(row) * 64;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    *reinterpret_cast<uint4*>(rowp + ((j ^ ((row >> 1) & 3)) << 4)) =
-                                        make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                            }
-                        }
-                        fence_proxy_async();
-                        named_bar_sync(2 + half, 128);
-                        if (q == 0 && lane == 0) {
-                            tma_store_4d(&mapD, sbuf, nt * p.BN + c, stl.ow0, stl.oh0, img);
-                            bulk_commit_group();
-                        }
-                        obuf ^= 1;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
-                        continue;
-                    }
                     epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
                     if (p.gn_mode != 0 && p.dbg_no_epi != 3) {
                         float gv[16];
@@ -959,7 +1030,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (p.out_bytes && q == 0 && lane == 0) bulk_wait_group<0>();   // staged tiles are in global memory before the CTA exits
     }
 
     tc_fence_before();
@@ -1625,7 +1695,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         const cuuint64_t es = op.out_fp32 ? 4 : 2;
         cuuint64_t dims[4] = {(cuuint64_t)op.N, (cuuint64_t)op.OW, (cuuint64_t)op.OH, (cuuint64_t)op.A_B};
         cuuint64_t str[3] = {(cuuint64_t)op.D_sW * es, (cuuint64_t)op.D_sH * es, (cuuint64_t)op.D_sB * es};
-        cuuint32_t box[4] = {32, (cuuint32_t)t.TW, (cuuint32_t)t.TH, 1};
+        const cuuint32_t bw = t.TW < 32 ? (cuuint32_t)t.TW : 32u;      // one epilogue warp's 32 rows of the tile
+        cuuint32_t box[4] = {32, bw, 32u / bw, 1};
         if ((rc = encode_map(&mapD, op.D, 4, dims, str, box, op.name,
                              op.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                              op.out_fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
@@ -1665,10 +1736,14 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
 
     bool& attr_set = attr_flag(1);   // cudaFuncSetAttribute is per device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set = true;
     }
@@ -1698,10 +1773,15 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true>, mapA, mapB, mapD, p);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_GENERIC>, mapA, mapB, mapD, p);
         if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
     } else {
-        conv_gemm_tcgen05_kernel<false><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
+        if (t.out_bytes && op.out_fp32)
+            conv_gemm_tcgen05_kernel<false, EPI_LEAN_F32><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
+        else if (t.out_bytes)
+            conv_gemm_tcgen05_kernel<false, EPI_LEAN_BF16><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
+        else
+            conv_gemm_tcgen05_kernel<false, EPI_GENERIC><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
     }
     if (timed) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
     cudaError_t e = cudaGetLastError();

@@ -48,6 +48,9 @@ class UniversalTrainer:
         self.project_fn = project_fn
         self.rank, self.world = _world()
         self._bounds: Optional[torch.Tensor] = None     # [2,3,H,W]: per-pixel (min, max) image of the whole dataset
+        # set to a list to have (start, end) CUDA events recorded around every all-reduce on the current stream
+        # (bench.py --mode universal); the interval includes the wait for the slowest rank
+        self.comm_events: Optional[list] = None
 
     @classmethod
     def for_b200(cls, cfg: UniversalConfig, vae) -> "UniversalTrainer":
@@ -97,7 +100,14 @@ class UniversalTrainer:
                 g = self.grad_fn(xp, targets[s:e], None if noises is None else noises[s:e])
                 total += self.sum_fn(g)
         if self.world > 1:
+            ev = None
+            if self.comm_events is not None and total.is_cuda:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             dist.all_reduce(total, op=dist.ReduceOp.SUM)          # the one exchange step
+            if ev is not None:
+                ev[1].record()
+                self.comm_events.append(ev)
         total /= float(n_global * self.cfg.grad_reps)             # :166 mean over reps (and images)
         delta = self.step_fn(delta, total)                        # :169-180
         if self.cfg.apply_image_pertubation and self._bounds is not None:
