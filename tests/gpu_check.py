@@ -134,6 +134,12 @@ def run_gemm_suite(lib, dev):
         ("1x1 N16", dict(B=1, H=8, W=8, Cin=64, N=16, mode=-1)),
         ("1x1 N1536", dict(B=1, H=8, W=8, Cin=128, N=1536, mode=-1)),
         ("1x1 alpha", dict(B=1, H=8, W=8, Cin=128, N=64, mode=-1, alpha=0.125)),
+        # lean per-warp TMA-store epilogue: multi-wave, bias + residual, narrow tiles (TW < 32), odd column-chunk counts
+        ("lean 1x1 128->256 64x64 B=8 bias resid", dict(B=8, H=64, W=64, Cin=128, N=256, mode=-1, bias=True, resid=True)),
+        ("lean 1x1 256->128 64x64 B=12 resid (mt=2)", dict(B=12, H=64, W=64, Cin=256, N=128, mode=-1, resid=True)),
+        ("lean 1x1 W=8 bias", dict(B=3, H=8, W=8, Cin=128, N=128, mode=-1, bias=True)),
+        ("lean 1x1 W=16 N=96 alpha", dict(B=2, H=16, W=16, Cin=64, N=96, mode=-1, bias=True, alpha=0.5)),
+        ("lean 1x1 W=24 (register fallback)", dict(B=2, H=8, W=24, Cin=64, N=64, mode=-1, bias=True)),
         ("conv3x3 fwd 128->128", dict(B=2, H=16, W=16, Cin=128, N=128, mode=0, bias=True)),
         ("conv3x3 fwd 128->256 W=128", dict(B=1, H=4, W=128, Cin=128, N=256, mode=0)),
         ("conv3x3 fwd 512->512 8x8", dict(B=2, H=8, W=8, Cin=512, N=512, mode=0, resid=True)),

@@ -9,7 +9,12 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libtml_b200.so"
+import os
+
+# TML_LIB_PATH selects another build of the same sources (A/B timing of compile-time tuning constants); the default
+# is the in-tree library every test and benchmark uses.
+_LIB_PATH = Path(os.environ["TML_LIB_PATH"]).resolve() if os.environ.get("TML_LIB_PATH") else \
+    Path(__file__).resolve().parent / "csrc" / "libtml_b200.so"
 
 
 class TmlError(RuntimeError):

@@ -532,11 +532,11 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                 if (has_res)
                     rrow = p.resid + (long long)stl.img * p.R_sB + (long long)(stl.oh0 + r_th) * p.R_sH +
                            (long long)(stl.ow0 + r_tw) * p.R_sW + nt * p.BN;
+                uint32_t v[32];
+                if (ch_lo < ch_hi) tmem_ld32(t_addr + uint32_t(ch_lo * 32), v);
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
                     const int c = ch * 32;
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + uint32_t(c), v);
                     uint4 rr[4];
                     if (has_res) {
                         ld_global_nc_256(rrow + c, rr[0], rr[1]);
@@ -559,6 +559,8 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
                     }
+                    // the accumulator registers are consumed: the next chunk's TMEM load runs under the rest of this one
+                    if (ch + 1 < ch_hi) tmem_ld32(t_addr + uint32_t(c + 32), v);
                     if (has_res) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -1064,11 +1066,17 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 // (its half of A) and input row 2*yp + r (+ halo, a 130-pixel slot: its half of B).  The two 128-pixel halves of the
 // N operand live in DIFFERENT shared memories, which is what makes a two-row tile expressible at all: inside one
 // CTA, rows of 128+2 pixels cannot be 128 pixels apart.
+#ifndef TML_SW_ROWSLOTS     // ring depths of the single-CTA geometry (A/B builds)
+#define TML_SW_ROWSLOTS 3
+#endif
+#ifndef TML_SW_WSTAGES
+#define TML_SW_WSTAGES 7
+#endif
 template <bool PAIR> struct SwGeo {
     static constexpr int kRowPx = PAIR ? 130 : 258;
     static constexpr int kRowBytes = PAIR ? 17 * 1024 : 33 * 1024;   // kRowPx * 128 B rounded up to the 1 KB swizzle atom
-    static constexpr int kRowSlots = PAIR ? 4 : 3;
-    static constexpr int kWStages = PAIR ? 8 : 7;
+    static constexpr int kRowSlots = PAIR ? 4 : TML_SW_ROWSLOTS;
+    static constexpr int kWStages = PAIR ? 8 : TML_SW_WSTAGES;
     static constexpr int kSmem = 1024 + kRowSlots * kRowBytes + kWStages * (128 * kBlockK * 2) + 256;
 };
 constexpr int kSwWBytes = 128 * kBlockK * 2;  // 16 KB: 128 output channels x 64 input channels
@@ -1089,6 +1097,7 @@ struct SwParams {
     int gn_silu;
     volatile int* hang_where;
     int dbg_no_epi, dbg_mma_only;
+    int l2_prefetch;             // row producer pulls the NEXT tile's input rows into L2 while this tile runs
 };
 
 // The GNB instantiations run 16 epilogue warps (64 pixels each, 8-pixel steps, <= 102 registers) because their
@@ -1240,6 +1249,14 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             bool first_pass = true;
             for (int tile = tile0; tile < total_tiles; tile += tstep) {
                 const SwTile t = sw_decode<NC, PAIR>(p, tile, int(crank));
+                if (p.l2_prefetch && tile + tstep < total_tiles) {
+                    // The input rows are streamed from HBM (the first tile that touches a row misses L2); the ring only
+                    // looks two slots ahead, so the next tile's rows are requested a whole tile early.
+                    const SwTile n = sw_decode<NC, PAIR>(p, tile + tstep, int(crank));
+                    for (int ch = 0; ch < p.kchunks; ++ch)
+                        for (int r = 0; r < 3; ++r)
+                            tma_prefetch_l2_4d(&mapRow, ch * kBlockK, n.bx0 - 1, n.brow + r - 1, n.img);
+                }
                 for (int ch = 0; ch < p.kchunks; ++ch)
                     for (int r = 0; r < 3; ++r) {
                         mbar_wait(&rempty[rs], rphase ^ 1u, hw, htag + 2);
@@ -1592,6 +1609,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.hang_where = hang_word_device();
+    { static const int pf = getenv("TML_SW_PREFETCH") ? atoi(getenv("TML_SW_PREFETCH")) : 0; p.l2_prefetch = pf; }   // tuning switch
     { static const int mo = getenv("TML_DBG_MMA_ONLY") ? atoi(getenv("TML_DBG_MMA_ONLY")) : 0; p.dbg_mma_only = mo;   // 1 none, 2 no weights, 3 no rows
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = (ne == 1 || ne == 2) ? ne : 0; }
     const int nc = op.N / 128;
