@@ -152,12 +152,10 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
         a.g = alloc_gn(S, B, Ctop);
         a.qkv = S.alloc((size_t)B * tok * 3 * Ctop * sizeof(bf16));
         a.P = S.alloc((size_t)B * tok * tok * sizeof(bf16));
+        a.a = S.alloc(act_bytes(B, hh, ww, Ctop));
+        a.inv_l = S.alloc((size_t)B * tok * sizeof(float));
         a.out = S.alloc(act_bytes(B, hh, ww, Ctop));
-        const size_t act = act_bytes(B, hh, ww, Ctop);
-        const size_t fwd_ws = gn_partial_bytes(B, (int)tok) + 3 * act + (size_t)B * tok * tok * 4 + 8192;
-        const size_t bwd_ws = 8 * act + (size_t)B * tok * tok * 4 + 3 * (size_t)B * tok * tok * 2 +
-                              gn_partial_bytes(B, (int)tok) + fused_partial_bytes(B, hh, ww) + 16384;
-        ws_peak = std::max(ws_peak, std::max(fwd_ws, bwd_ws));
+        // (scratch of the attention walks is measured by the dry run, see dec_layout)
         L.attn = a;
         cur = a.out;
     }

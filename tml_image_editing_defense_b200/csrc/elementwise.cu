@@ -573,9 +573,10 @@ void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float sca
 
 // out[b][c][r] = in[b][r][c].  64x64 tiles; each thread moves bf16 pairs (4-byte accesses, 128-byte
 // warp transactions on both sides); the +2 padding keeps the column reads bank-conflict free.
+// row_scale (optional): input row r of batch b is multiplied by row_scale[b * R + r] on the way.
 __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R,
                                                         int C, long long ld_in, long long bs_in, long long ld_out,
-                                                        long long bs_out) {
+                                                        long long bs_out, const float* __restrict__ row_scale) {
     __shared__ bf16 tile[64][66];
     const int b = blockIdx.z;
     const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
@@ -584,7 +585,11 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
     if (full) {
 #pragma unroll
         for (int i = ty; i < 64; i += 8) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(in + (size_t)b * bs_in + (size_t)(r0 + i) * ld_in + c0 + 2 * tx);
+            uint32_t v = *reinterpret_cast<const uint32_t*>(in + (size_t)b * bs_in + (size_t)(r0 + i) * ld_in + c0 + 2 * tx);
+            if (row_scale) {
+                const float sc = row_scale[(size_t)b * R + r0 + i];
+                v = pack2(bf_lo(v) * sc, bf_hi(v) * sc);
+            }
             *reinterpret_cast<uint32_t*>(&tile[i][2 * tx]) = v;
         }
         __syncthreads();
@@ -599,7 +604,11 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
         for (int i = ty; i < 64; i += 8)
             for (int j = tx; j < 64; j += 32) {
                 const int r = r0 + i, c = c0 + j;
-                if (r < R && c < C) tile[i][j] = in[(size_t)b * bs_in + (size_t)r * ld_in + c];
+                if (r < R && c < C) {
+                    bf16 v = in[(size_t)b * bs_in + (size_t)r * ld_in + c];
+                    if (row_scale) v = __float2bfloat16_rn(__bfloat162float(v) * row_scale[(size_t)b * R + r]);
+                    tile[i][j] = v;
+                }
             }
         __syncthreads();
         for (int i = ty; i < 64; i += 8)
@@ -611,10 +620,55 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
 }
 
 void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
-                      long long ld_out, long long bs_out, cudaStream_t s) {
+                      long long ld_out, long long bs_out, cudaStream_t s, const float* row_scale) {
     if (g_dry_run) return;
     dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
-    transpose_kernel<<<grid, 256, 0, s>>>(in, out, R, C, ld_in, bs_in, ld_out, bs_out);
+    transpose_kernel<<<grid, 256, 0, s>>>(in, out, R, C, ld_in, bs_in, ld_out, bs_out, row_scale);
+    COUNT_LAUNCH();
+}
+
+// ================================================================================================
+// Row helpers of the attention softmax, whose exp / normalisation / backward run in GEMM epilogues:
+//   row_reduce: out[r] = max_k part[r][k]  (op 0)   or   1 / sum_k part[r][k]  (op 1), fixed order
+//   row_dot:    out[r] = sum_c a[r][c] * b[r][c]    (D = rowsum(dO * O) of the softmax backward)
+// ================================================================================================
+__global__ void __launch_bounds__(256) row_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                         long long rows, int n, int op) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* pr = part + r * n;
+    float acc = op == 0 ? -INFINITY : 0.f;
+    for (int k = 0; k < n; ++k) acc = op == 0 ? fmaxf(acc, pr[k]) : acc + pr[k];
+    out[r] = op == 0 ? acc : __fdiv_rn(1.f, acc);
+}
+void launch_row_reduce(const float* part, float* out, long long rows, int n, int op, cudaStream_t s) {
+    if (g_dry_run) return;
+    row_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(part, out, rows, n, op);
+    COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) row_dot_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                      float* __restrict__ out, long long rows, int C) {
+    const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;   // one warp per row
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const uint4* pa = reinterpret_cast<const uint4*>(a + r * C);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + r * C);
+    float acc = 0.f;
+    for (int i = lane; i < C / 8; i += 32) {
+        float fa[8], fb[8];
+        unpack8(pa[i], fa);
+        unpack8(pb[i], fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(fa[j], fb[j], acc);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) out[r] = acc;
+}
+void launch_row_dot(const bf16* a, const bf16* b, float* out, long long rows, int C, cudaStream_t s) {
+    if (g_dry_run) return;
+    row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(a, b, out, rows, C);
     COUNT_LAUNCH();
 }
 

@@ -48,6 +48,17 @@ struct GemmOp {
     const float2* gn_mr = nullptr;     // [A_B][32]
     const float* gn_gamma = nullptr;   // [N]
     int gn_silu = 0;
+    // Row-wise epilogues of the attention products (thread = output row = query token; dense bf16 output, lean path):
+    //   epi_mode 1: no output; row_part[row][2*n_tiles] = max_j acc[row][j] per (column tile, column half)
+    //   epi_mode 2: D = bf16(exp2((acc - row_a[row]) * exp_scale)); row_part[...] = sum of the stored values
+    //   epi_mode 3: D = bf16(resid[row][col] * (acc - row_a[row]) * alpha * row_b[row])     (softmax backward)
+    // row = image * OH*OW + pixel.  row_scale (any epilogue): result row multiplied by row_scale[row] (after alpha).
+    int epi_mode = 0;
+    const float* row_a = nullptr;
+    const float* row_b = nullptr;
+    float* row_part = nullptr;
+    float exp_scale = 0.f;
+    const float* row_scale = nullptr;
     // hardware experiment (tests only): A tile loaded `dbg_shift` pixels early into a (TW+8)-row box and
     // consumed through a row-shifted UMMA descriptor; dbg_bo = 1 also sets the descriptor base_offset field
     int dbg_shift = 0, dbg_bo = 0;
@@ -67,6 +78,9 @@ int gemm_plan(const GemmOp& op, GemmTiling* t);
 int gemm_gn_tiles_per_image(int OH, int OW);
 // partial-sum entries per image this op's fused reduction writes (gn_mode set); at most 2 x tiles per image
 int gemm_gn_chunks_per_image(const GemmOp& op);
+
+// entries per output row of `row_part` for an epi_mode 1 / 2 op (2 x column tiles), or a negative error code
+int gemm_row_partials(const GemmOp& op);
 
 // true when gemm_launch_tc runs this op on the operand-swapped 3x3 kernel (channels as M, 256 pixels of a row as N),
 // whose fused GroupNorm reductions are cheap enough to use at any K

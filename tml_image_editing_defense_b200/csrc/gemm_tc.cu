@@ -140,6 +140,11 @@ int gemm_gn_tiles_per_image(int OH, int OW) {
 
 bool gemm_swapped_shape(const GemmOp& op);
 int sw_px_per_warp(bool gnb);
+int gemm_row_partials(const GemmOp& op) {
+    GemmTiling t;
+    const int rc = gemm_plan(op, &t);
+    return rc ? rc : 2 * t.n_tiles;
+}
 // Partial-sum entries per image written by the fused GroupNorm reduction of this op.
 int gemm_gn_chunks_per_image(const GemmOp& op) {
     if (op.gn_mode != 0 && gemm_swapped_shape(op))   // one entry per epilogue warp's pixel range (64 or 128 pixels)
@@ -223,8 +228,10 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     static const bool no_pair = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
     // (a per-image B operand is fine when both CTAs of a pair always work on the same image)
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
+    // (the attention logits, K = 512 and a per-image B operand, are L2-bound on single CTAs: 48 KB per four MMAs)
     t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
-               t->rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 4) ? 1 : 0;
+               t->rows_valid == 128 && (op.ntaps * op.A_C >= 2048 || op.epi_mode != 0) && sub_tiles % 2 == 0 &&
+               sub_tiles * t->n_tiles >= 4) ? 1 : 0;
     // Plain dense outputs (no fused reduction) leave through shared memory and TMA stores: the per-lane
     // 32-byte global stores of the register epilogue cost one LSU request per sector (~0.2 ms per GB of output, measured),
     // which is what bounds the thin GEMMs (1x1 shortcuts, parity-class dgrads, attention logits).
@@ -236,7 +243,14 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // (each of the 8 epilogue warps stages its own [32 rows][32 columns] x 2 buffers: rows_valid is a multiple of 32 and
     // a warp's 32 rows are 32 pixels of one row or whole rows of the tile)
     const bool warp_rows = t->rows_valid % 32 == 0 && (TW % 32 == 0 || 32 % TW == 0);
-    if (!no_tma_store && !t->pair && op.gn_mode == 0 && dense_rows && warp_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
+    if (op.epi_mode != 0) {
+        if (op.gn_mode != 0 || op.out_fp32 || !dense_rows || !warp_rows || BN % 32 != 0 || op.dbg_shift != 0 || op.bias ||
+            (op.epi_mode != 3 && op.epi_mode != 1 && op.epi_mode != 2)) {
+            set_error("%s: row-wise epilogue %d needs a dense bf16 output of whole 32-row warps", op.name, op.epi_mode);
+            return -1;
+        }
+        t->out_bytes = 8 * 2 * 32 * 32 * es_out;
+    } else if (!no_tma_store && !t->pair && op.gn_mode == 0 && dense_rows && warp_rows && BN % 32 == 0 && op.dbg_shift == 0 &&
         getenv("TML_DBG_NO_EPI") == nullptr)
         t->out_bytes = 8 * 2 * 32 * 32 * es_out;
     int stage_bytes = t->mt * kATileBytes + (((t->pair ? BN / 2 : BN) * 128 + 1023) / 1024) * 1024;
@@ -291,6 +305,14 @@ struct TcParams {
     int out_bytes;     // > 0: dense outputs are staged in shared memory ([2 halves][2 buffers][128 rows][32 cols]) and TMA-stored
     int dbg_no_epi;    // experiment: 1 = the epilogue only hands the accumulator back, 2 = no global memory ops, 3 = no GN math
     int dbg_mma_only;  // experiment: operands are loaded for the first pass over the ring only
+    // row-wise attention epilogues (see GemmOp::epi_mode) and the per-row output scale
+    int epi_mode;
+    const float* row_a;
+    const float* row_b;
+    float* row_part;
+    float exp_scale;
+    const float* row_scale;
+    int rows_img, ow_full;   // output pixels per image, output row length (global row = img * rows_img + oh * ow_full + ow)
 };
 
 constexpr int kHaloW = 130;  // 128 output pixels + one halo pixel on each side
@@ -336,16 +358,21 @@ __device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4&
                  : "l"(p));
 }
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // Epilogue for NC (<=32) accumulator columns held by one thread (= one output pixel): alpha, bias,
 // residual (already in registers: rres, loaded one chunk ahead), store.  On return f[] holds the
 // values as stored (bf16-rounded for bf16 outputs).
 template <int NC>
 __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, float (&f)[NC],
-                                               const uint4 (&rres)[4], bool valid, long long d_off, int n0) {
-    if (p.alpha != 1.0f) {
+                                               const uint4 (&rres)[4], bool valid, long long d_off, int n0, float alpha) {
+    if (alpha != 1.0f) {
 #pragma unroll
-        for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) * alpha;
     } else {
 #pragma unroll
         for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
@@ -491,10 +518,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // ------------------------------------------------------------------------------------------------
 constexpr int EPI_GENERIC = 0, EPI_LEAN_BF16 = 1, EPI_LEAN_F32 = 2;
 
-template <int EPI>
+template <int EPI, bool PAIR>
 __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorMap* mapD, uint8_t* out_stage, float* bias_s,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base, int tile0,
-                                              int tile_step, int total_tiles, volatile int* hw) {
+                                              int tile_step, int total_tiles, uint32_t crank, volatile int* hw) {
     constexpr int ES = EPI == EPI_LEAN_F32 ? 4 : 2;
     constexpr int ROWB = 32 * ES;                       // bytes of one staged row (32 columns)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -511,18 +538,20 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
     const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
     const float alpha = p.alpha;
     const bool has_bias = p.bias != nullptr, has_res = p.resid != nullptr;
+    const int mode = EPI == EPI_LEAN_BF16 ? p.epi_mode : 0;   // 0 plain, 1 row max, 2 exp, 3 softmax backward
+    const int htag = int(crank) * 100;
     int acc = 0, buf = 0, bias_nt = -1;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
-        const int mtile = tile / p.n_tiles;
+        const int mtile = PAIR ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles;
         if (has_bias && nt != bias_nt) {   // this tile's bias columns -> shared memory (warp-uniform branch)
             named_bar_sync(1, kEpiThreads);
             for (int c = et; c < p.BN; c += kEpiThreads) bias_s[c] = __ldg(p.bias + nt * p.BN + c);
             named_bar_sync(1, kEpiThreads);
             bias_nt = nt;
         }
-        mbar_wait(&tfull_bar[acc], acc_phase, hw, 6);
+        mbar_wait(&tfull_bar[acc], acc_phase, hw, htag + 6);
         tc_fence_after();
         if (warp_valid) {
             for (int sub = 0; sub < p.mt; ++sub) {
@@ -532,43 +561,85 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                 if (has_res)
                     rrow = p.resid + (long long)stl.img * p.R_sB + (long long)(stl.oh0 + r_th) * p.R_sH +
                            (long long)(stl.ow0 + r_tw) * p.R_sW + nt * p.BN;
+                // row-wise modes: this thread's row constants / running reduction
+                const long long grow = (long long)stl.img * p.rows_img + (long long)(stl.oh0 + r_th) * p.ow_full + (stl.ow0 + r_tw);
+                float ra = 0.f, rb = 1.f, red = mode == 1 ? -INFINITY : 0.f;
+                float al = alpha;                                         // plain mode: alpha x the per-row output scale
+                if (mode == 0 && p.row_scale != nullptr) al *= __ldg(p.row_scale + grow);
+                if (mode >= 2) ra = __ldg(p.row_a + grow);
+                if (mode == 2) ra *= -p.exp_scale;                       // exp2(acc * c - m * c)
+                if (mode == 3) rb = alpha * __ldg(p.row_b + grow);
                 uint32_t v[32];
-                if (ch_lo < ch_hi) tmem_ld32(t_addr + uint32_t(ch_lo * 32), v);
+                uint4 rr[4], rn[4];   // residual / P~ values of this chunk and (in flight) of the next one
+                if (ch_lo < ch_hi) {
+                    tmem_ld32(t_addr + uint32_t(ch_lo * 32), v);
+                    if (has_res) {
+                        ld_global_nc_256(rrow + ch_lo * 32, rr[0], rr[1]);
+                        ld_global_nc_256(rrow + ch_lo * 32 + 16, rr[2], rr[3]);
+                    }
+                }
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
                     const int c = ch * 32;
-                    uint4 rr[4];
-                    if (has_res) {
-                        ld_global_nc_256(rrow + c, rr[0], rr[1]);
-                        ld_global_nc_256(rrow + c + 16, rr[2], rr[3]);
+                    if (has_res && ch + 1 < ch_hi) {
+                        ld_global_nc_256(rrow + c + 32, rn[0], rn[1]);
+                        ld_global_nc_256(rrow + c + 48, rn[2], rn[3]);
                     }
-                    if (lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
-                    __syncwarp();
+                    if (mode != 1) {
+                        if (lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
+                        __syncwarp();
+                    }
                     tmem_ld_wait();
                     float f[32];
-                    if (has_bias) {
+                    if (mode == 0) {
+                        if (has_bias) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
-                            f[4 * j] = fmaf(__uint_as_float(v[4 * j]), alpha, b4.x);
-                            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b4.y);
-                            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b4.z);
-                            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b4.w);
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+                                f[4 * j] = fmaf(__uint_as_float(v[4 * j]), al, b4.x);
+                                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), al, b4.y);
+                                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), al, b4.z);
+                                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), al, b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * al;
                         }
+                    } else if (mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) red = fmaxf(red, __uint_as_float(v[j]));
+                    } else if (mode == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = ex2_approx(fmaf(__uint_as_float(v[j]), p.exp_scale, ra));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+                        for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) - ra) * rb;
                     }
                     // the accumulator registers are consumed: the next chunk's TMEM load runs under the rest of this one
                     if (ch + 1 < ch_hi) tmem_ld32(t_addr + uint32_t(c + 32), v);
+                    if (mode == 1) continue;
+                    if (has_res) {
+                        if (mode == 3) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[8 * j + 0] *= bf16_lo(rr[j].x); f[8 * j + 1] *= bf16_hi(rr[j].x);
+                                f[8 * j + 2] *= bf16_lo(rr[j].y); f[8 * j + 3] *= bf16_hi(rr[j].y);
+                                f[8 * j + 4] *= bf16_lo(rr[j].z); f[8 * j + 5] *= bf16_hi(rr[j].z);
+                                f[8 * j + 6] *= bf16_lo(rr[j].w); f[8 * j + 7] *= bf16_hi(rr[j].w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[8 * j + 0] += bf16_lo(rr[j].x); f[8 * j + 1] += bf16_hi(rr[j].x);
+                                f[8 * j + 2] += bf16_lo(rr[j].y); f[8 * j + 3] += bf16_hi(rr[j].y);
+                                f[8 * j + 4] += bf16_lo(rr[j].z); f[8 * j + 5] += bf16_hi(rr[j].z);
+                                f[8 * j + 6] += bf16_lo(rr[j].w); f[8 * j + 7] += bf16_hi(rr[j].w);
+                            }
+                        }
+                    }
                     if (has_res) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            f[8 * j + 0] += bf16_lo(rr[j].x); f[8 * j + 1] += bf16_hi(rr[j].x);
-                            f[8 * j + 2] += bf16_lo(rr[j].y); f[8 * j + 3] += bf16_hi(rr[j].y);
-                            f[8 * j + 4] += bf16_lo(rr[j].z); f[8 * j + 5] += bf16_hi(rr[j].z);
-                            f[8 * j + 6] += bf16_lo(rr[j].w); f[8 * j + 7] += bf16_hi(rr[j].w);
-                        }
+                        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
                     }
                     uint8_t* sb = sbase + size_t(buf) * (32 * ROWB);
                     uint8_t* rowp = sb + size_t(lane) * ROWB;
@@ -582,10 +653,14 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                     } else {
                         // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+                            if (mode == 2)   // the softmax denominator sums the probabilities as stored (bf16), in a fixed order
+                                red += ((bf16_lo(o.x) + bf16_hi(o.x)) + (bf16_lo(o.y) + bf16_hi(o.y))) +
+                                       ((bf16_lo(o.z) + bf16_hi(o.z)) + (bf16_lo(o.w) + bf16_hi(o.w)));
+                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -595,10 +670,17 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                     }
                     buf ^= 1;
                 }
+                if (mode == 1 || mode == 2)   // (a column half without chunks writes the identity)
+                    p.row_part[(grow * p.n_tiles + nt) * 2 + half] = red;
             }
         }
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
+        if constexpr (PAIR) {
+            if (crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
+            else mbar_arrive(&tempty_bar[acc]);
+        } else {
+            mbar_arrive(&tempty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
     }
@@ -897,8 +979,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             }
         }
     } else if (warp >= 4 && EPI != EPI_GENERIC) {
-        if constexpr (EPI != EPI_GENERIC && !PAIR)
-            lean_epilogue<EPI>(p, &mapD, out_stage, gn_red, tfull_bar, tempty_bar, tmem_base, tile0, tile_step, total_tiles, hw);
+        if constexpr (EPI != EPI_GENERIC)
+            lean_epilogue<EPI, PAIR>(p, &mapD, out_stage, gn_red, tfull_bar, tempty_bar, tmem_base, tile0, tile_step,
+                                     total_tiles, crank, hw);
     } else if (warp >= 4) {
         // ===================================================================== epilogue
         // 8 warps: warp e handles TMEM lane quadrant e % 4 (rows 32q .. 32q+31 of the sub-tile) and
@@ -932,6 +1015,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
                 const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
+                float alpha_row = p.alpha;   // alpha x the per-row scale (attention PV: 1 / softmax denominator)
+                if (p.row_scale != nullptr && valid)
+                    alpha_row *= __ldg(p.row_scale + (long long)img * p.rows_img + (long long)oh * p.ow_full + ow);
 
                 // operands of the first chunk are requested before waiting for the accumulator
                 uint4 rres[4], xreg[4];
@@ -985,7 +1071,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         }
                     }
                     tmem_ld_wait();
-                    epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c);
+                    epilogue_store<32>(p, v, f, rres, valid, d_off, nt * p.BN + c, alpha_row);
                     if (p.gn_mode != 0 && p.dbg_no_epi != 3) {
                         float gv[16];
                         if (cpg == 4) gn_chunk_sums<4>(p, f, gv, valid, xreg, c, gn_sc, gn_sh, gn_gm, gn_mrs);
@@ -1004,7 +1090,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     float f[16];
                     tmem_ld16(t_addr, v);
                     tmem_ld_wait();
-                    epilogue_store<16>(p, v, f, rres, valid, d_off, nt * p.BN);
+                    epilogue_store<16>(p, v, f, rres, valid, d_off, nt * p.BN, alpha_row);
                 }
                 if (p.gn_mode != 0) {
                     // cross-warp combine in fixed order, one (group, value) per thread: the chunk of a group
@@ -1682,6 +1768,12 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     GemmTiling t;
     int rc = gemm_plan(op, &t);
     if (rc) return rc;
+    if (op.epi_mode != 0 && ((op.epi_mode == 3) != (op.resid != nullptr) || (op.epi_mode != 3 && !op.row_part) ||
+                             (op.epi_mode >= 2 && !op.row_a) || (op.epi_mode == 3 && !op.row_b) ||
+                             (op.epi_mode != 1 && !op.D))) {
+        set_error("%s: row-wise epilogue %d is missing one of its buffers", op.name, op.epi_mode);
+        return -1;
+    }
 
     CUtensorMap mapA, mapB;
     if (op.stride == 1) {
@@ -1708,8 +1800,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         if ((rc = encode_map(&mapB, op.Bm, 3, dims, str, box, op.name))) return rc;
     }
 
-    CUtensorMap mapD = mapB;   // placeholder unless the staged epilogue is on
-    if (t.out_bytes) {
+    CUtensorMap mapD = mapB;   // placeholder unless the staged epilogue is on (epi_mode 1 stores no tile)
+    if (t.out_bytes && op.epi_mode != 1) {
         const cuuint64_t es = op.out_fp32 ? 4 : 2;
         cuuint64_t dims[4] = {(cuuint64_t)op.N, (cuuint64_t)op.OW, (cuuint64_t)op.OH, (cuuint64_t)op.A_B};
         cuuint64_t str[3] = {(cuuint64_t)op.D_sW * es, (cuuint64_t)op.D_sH * es, (cuuint64_t)op.D_sB * es};
@@ -1748,6 +1840,9 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.dbg_shift = op.dbg_shift; p.dbg_bo = op.dbg_bo;
     p.halo = t.halo; p.halo_bytes = t.halo_bytes;
     p.pair = t.pair;
+    p.epi_mode = op.epi_mode; p.row_a = op.row_a; p.row_b = op.row_b; p.row_part = op.row_part; p.exp_scale = op.exp_scale;
+    p.row_scale = op.row_scale;
+    p.rows_img = op.OH * op.OW; p.ow_full = op.OW;
     p.hang_where = hang_word_device();
     { static const bool mo = getenv("TML_DBG_MMA_ONLY") && getenv("TML_DBG_MMA_ONLY")[0] == '1'; p.dbg_mma_only = mo ? 1 : 0;
       static const int ne = getenv("TML_DBG_NO_EPI") ? atoi(getenv("TML_DBG_NO_EPI")) : 0; p.dbg_no_epi = ne; }
@@ -1762,6 +1857,8 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
             e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, EPI_LEAN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set = true;
     }
@@ -1791,7 +1888,9 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_GENERIC>, mapA, mapB, mapD, p);
+        cudaError_t le = t.out_bytes
+            ? cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_LEAN_BF16>, mapA, mapB, mapD, p)
+            : cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_GENERIC>, mapA, mapB, mapD, p);
         if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
     } else {
         if (t.out_bytes && op.out_fp32)

@@ -43,7 +43,10 @@ void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float sca
                              cudaStream_t s);
 // out[b][c][r] = in[b][r][c]; in row stride ld_in, batch strides in elements
 void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
-                      long long ld_out, long long bs_out, cudaStream_t s);
+                      long long ld_out, long long bs_out, cudaStream_t s, const float* row_scale = nullptr);
+// softmax row helpers (the exp / normalisation / backward live in GEMM epilogues, see GemmOp::epi_mode)
+void launch_row_reduce(const float* part, float* out, long long rows, int n, int op /*0 max, 1 reciprocal sum*/, cudaStream_t s);
+void launch_row_dot(const bf16* a, const bf16* b, float* out, long long rows, int C /*multiple of 8, dense rows*/, cudaStream_t s);
 
 // posterior sample + latent loss + d(loss)/d(moments)          (main.py:162,191; losses.py:39-41)
 void launch_latent_loss(int kind, const float* moments, const float* noise, const float* target, int B, int h, int w,

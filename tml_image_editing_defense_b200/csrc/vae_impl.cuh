@@ -175,7 +175,9 @@ struct Attn {
 struct GnSaved { size_t ss = 0, mr = 0; };
 struct ResnetRec { size_t x = 0, h1 = 0, out = 0; GnSaved g1, g2; int h = 0, w = 0; };
 struct DownRec { size_t x = 0, out = 0; int h = 0, w = 0; };
-struct AttnRec { size_t x = 0, qkv = 0, P = 0, out = 0; GnSaved g; int h = 0, w = 0; };
+// P: unnormalised softmax numerators exp(s - rowmax) (bf16 [B][tok][tok]); inv_l: 1 / row sums (fp32 [B][tok]);
+// a: attention output before the projection (bf16 [B][tok][C])
+struct AttnRec { size_t x = 0, qkv = 0, P = 0, a = 0, inv_l = 0, out = 0; GnSaved g; int h = 0, w = 0; };
 
 struct Arena {
     size_t off = 0, peak = 0;
@@ -417,12 +419,10 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
             a.g = alloc_gn(S, B, cin);
             a.qkv = S.alloc((size_t)B * tok * 3 * cin * sizeof(bf16));
             a.P = S.alloc((size_t)B * tok * tok * sizeof(bf16));
+            a.a = S.alloc(act_bytes(B, h, w, cin));
+            a.inv_l = S.alloc((size_t)B * tok * sizeof(float));
             a.out = S.alloc(act_bytes(B, h, w, cin));
-            const size_t act = act_bytes(B, h, w, cin);
-            const size_t fwd_ws = gn_partial_bytes(B, (int)tok) + act /*t*/ + (size_t)B * tok * tok * 4 /*S*/ + act /*Vt*/ + act /*a*/ + 8192;
-            const size_t bwd_ws = 2 * act /*da, daT*/ + (size_t)B * tok * tok * 4 /*dP*/ + 3 * (size_t)B * tok * tok * 2 /*dS,dST,PT*/ +
-                                  2 * act /*Kt,Qt*/ + 3 * act /*dqkv*/ + act /*dt*/ + gn_partial_bytes(B, (int)tok) + 16384;
-            ws_peak = std::max(ws_peak, std::max(fwd_ws, bwd_ws));
+            // (scratch of the attention walks is measured by the dry run, see enc_layout)
             L.attn = a;
             cur = a.out;
         }
@@ -629,33 +629,58 @@ static int resnet_backward(Run& r, const Resnet& p, const ResnetRec& rec, const 
     return 0;
 }
 
+// Attention (1 head, d = C) without fp32 logits in memory: the softmax lives in the epilogues of the GEMMs around it.
+//   pass 1  QK^T, epilogue keeps only the row maxima            (GemmOp::epi_mode 1)
+//   pass 2  QK^T again, epilogue stores P~ = exp(scale*(s - max)) as bf16 and the row sums of what it stored (mode 2)
+//   PV      rows scaled by 1 / sum in the epilogue               (row_scale)
+// The second QK^T costs 2*tok^2*C flops per image (0.7 % of the step at 512^2) and replaces a 4-byte-per-logit write,
+// the softmax kernel's 4-byte read and its 2-byte write.
+static GemmOp attn_logits_op(const char* name, const bf16* A, const bf16* Bk, int B, int h, int w, int C, int ldA, int ldB) {
+    const int tok = h * w;
+    GemmOp o;   // D[tok, tok'] = A[tok, C] * Bk[tok', C]^T, both operands rows of a [B][tok][ld] tensor
+    o.name = name;
+    o.A = A; o.A_C = C; o.A_W = w; o.A_H = h; o.A_B = B;
+    o.A_sW = ldA; o.A_sH = (int64_t)w * ldA; o.A_sB = (int64_t)tok * ldA;
+    o.OW = w; o.OH = h;
+    o.Bm = Bk; o.N = tok; o.B_sN = ldB; o.B_sBatch = (int64_t)tok * ldB;
+    o.D_sW = tok; o.D_sH = (int64_t)w * tok; o.D_sB = (int64_t)tok * tok; o.D_sN = 1;
+    return o;
+}
+
 static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
     const int B = r.B, h = rec.h, w = rec.w, C = p.C, ns = r.e->num_sms;
     const int tok = h * w;
+    const long long rows = (long long)B * tok;
+    const float scale = 1.0f / sqrtf((float)C);
     const bf16* x = r.S<bf16>(rec.x);
     const size_t m = r.wsa.mark();
     bf16* t = r.Walloc<bf16>(act_bytes(B, h, w, C));
     RC(gn_forward(r, x, p.gn, rec.g, t, tok, 0, r.pending));
     bf16* qkv = r.S<bf16>(rec.qkv);
     RC(gemm_launch(dense_lin_op("attn.qkv", t, B, h, w, C, p.qkv.fwd, 3 * C, p.qkv.bias, nullptr, qkv), ns, r.st));
-    // S = QK^T / sqrt(C)   (fp32, [B][tok][tok])
-    float* S = r.Walloc<float>((size_t)B * tok * tok * sizeof(float));
-    {
-        GemmOp o;
-        o.name = "attn.qk";
-        o.A = qkv; o.A_C = C; o.A_W = w; o.A_H = h; o.A_B = B;
-        o.A_sW = 3 * C; o.A_sH = (int64_t)w * 3 * C; o.A_sB = (int64_t)tok * 3 * C;
-        o.OW = w; o.OH = h;
-        o.Bm = qkv + C; o.N = tok; o.B_sN = 3 * C; o.B_sBatch = (int64_t)tok * 3 * C;
-        o.alpha = 1.0f / sqrtf((float)C);
-        o.D = S; o.out_fp32 = 1; o.D_sW = tok; o.D_sH = (int64_t)w * tok; o.D_sB = (int64_t)tok * tok; o.D_sN = 1;
-        RC(gemm_launch(o, ns, r.st));
-    }
     bf16* P = r.S<bf16>(rec.P);
-    launch_softmax_rows(S, P, (long long)B * tok, tok, r.st);
+    float* inv_l = r.S<float>(rec.inv_l);
+    {
+        GemmOp o = attn_logits_op("attn.qk.max", qkv, qkv + C, B, h, w, C, 3 * C, 3 * C);
+        o.epi_mode = 1;
+        const int np = gemm_row_partials(o);
+        if (np < 0) return np;
+        float* part = r.Walloc<float>((size_t)rows * np * sizeof(float));
+        float* rmax = r.Walloc<float>((size_t)rows * sizeof(float));
+        o.row_part = part;
+        RC(gemm_launch(o, ns, r.st));
+        launch_row_reduce(part, rmax, rows, np, 0, r.st);
+        GemmOp e = attn_logits_op("attn.qk.exp", qkv, qkv + C, B, h, w, C, 3 * C, 3 * C);
+        e.epi_mode = 2;
+        e.row_a = rmax; e.row_part = part;
+        e.exp_scale = scale * 1.4426950408889634f;   // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
+        e.D = P;
+        RC(gemm_launch(e, ns, r.st));
+        launch_row_reduce(part, inv_l, rows, np, 1, r.st);
+    }
     bf16* Vt = r.Walloc<bf16>(act_bytes(B, h, w, C));  // [B][C][tok]
     launch_transpose(qkv + 2 * C, Vt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
-    bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, C));
+    bf16* a = r.S<bf16>(rec.a);
     {
         GemmOp o;
         o.name = "attn.pv";
@@ -663,6 +688,7 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
         o.A_sW = tok; o.A_sH = (int64_t)w * tok; o.A_sB = (int64_t)tok * tok;
         o.OW = w; o.OH = h;
         o.Bm = Vt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
+        o.row_scale = inv_l;
         o.D = a; o.D_sW = C; o.D_sH = (int64_t)w * C; o.D_sB = (int64_t)tok * C; o.D_sN = 1;
         RC(gemm_launch(o, ns, r.st));
     }
@@ -673,32 +699,36 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
     return 0;
 }
 
+// Backward: dP = da V^T never leaves the tensor memory -- the epilogue of that GEMM turns it into
+// dS = P * (dP - D) * scale with P = P~ / l and D = rowsum(dP * P) = da . a (mode 3); dV = P^T da uses the
+// unnormalised P~ with the rows of da pre-scaled by 1 / l.
 static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* dout, bf16* dx) {
     const int B = r.B, h = rec.h, w = rec.w, C = p.C, ns = r.e->num_sms;
     const int tok = h * w;
+    const long long rows = (long long)B * tok;
     const float scale = 1.0f / sqrtf((float)C);
     const bf16* qkv = r.S<bf16>(rec.qkv);
     const bf16* P = r.S<bf16>(rec.P);
+    const float* inv_l = r.S<float>(rec.inv_l);
     const size_t m = r.wsa.mark();
     const size_t act = act_bytes(B, h, w, C);
     const size_t tt = (size_t)B * tok * tok;
     bf16* da = r.Walloc<bf16>(act);
     RC(gemm_launch(dense_lin_op("attn.out.dgrad", dout, B, h, w, C, p.out.bwd, C, nullptr, nullptr, da), ns, r.st));
-    bf16* daT = r.Walloc<bf16>(act);
-    launch_transpose(da, daT, B, tok, C, C, (long long)tok * C, tok, (long long)C * tok, r.st);
-    float* dP = r.Walloc<float>(tt * sizeof(float));
+    float* Drow = r.Walloc<float>((size_t)rows * sizeof(float));
+    launch_row_dot(da, r.S<bf16>(rec.a), Drow, rows, C, r.st);
+    bf16* daT = r.Walloc<bf16>(act);   // (da / l)^T
+    launch_transpose(da, daT, B, tok, C, C, (long long)tok * C, tok, (long long)C * tok, r.st, inv_l);
+    bf16* dS = r.Walloc<bf16>(tt * 2);
     {
-        GemmOp o;  // dP = da V^T
-        o.name = "attn.dP";
-        o.A = da; o.A_C = C; o.A_W = w; o.A_H = h; o.A_B = B;
-        o.A_sW = C; o.A_sH = (int64_t)w * C; o.A_sB = (int64_t)tok * C;
-        o.OW = w; o.OH = h;
-        o.Bm = qkv + 2 * C; o.N = tok; o.B_sN = 3 * C; o.B_sBatch = (int64_t)tok * 3 * C;
-        o.D = dP; o.out_fp32 = 1; o.D_sW = tok; o.D_sH = (int64_t)w * tok; o.D_sB = (int64_t)tok * tok; o.D_sN = 1;
+        GemmOp o = attn_logits_op("attn.dS", da, qkv + 2 * C, B, h, w, C, C, 3 * C);   // dP = da V^T
+        o.epi_mode = 3;
+        o.alpha = scale;
+        o.row_a = Drow; o.row_b = inv_l;
+        o.resid = P; o.R_sW = tok; o.R_sH = (int64_t)w * tok; o.R_sB = (int64_t)tok * tok;
+        o.D = dS;
         RC(gemm_launch(o, ns, r.st));
     }
-    bf16* dS = r.Walloc<bf16>(tt * 2);
-    launch_softmax_bwd_rows(P, dP, dS, scale, (long long)B * tok, tok, r.st);
     bf16* dST = r.Walloc<bf16>(tt * 2);
     launch_transpose(dS, dST, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
     bf16* PT = r.Walloc<bf16>(tt * 2);
