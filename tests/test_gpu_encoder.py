@@ -258,11 +258,35 @@ def test_512_step_runs_on_the_fast_kernels(dev, models):
 def test_cli_main_runs_small(dev, tmp_path):
     from tml_image_editing_defense_b200.main import main
     rc = main(["--num_images", "3", "--resolution", "64", "--max_train_steps", "4", "--train_batch_size", "2",
-               "--output_dir", str(tmp_path)])
+               "--images_per_pass", "2", "--output_dir", str(tmp_path)])          # two passes through the pinned loader
     assert rc == 0
     out = torch.load(tmp_path / "adversarial_rank0.pt")
     assert out["x_adv"].shape == (3, 3, 64, 64) and out["indices"] == [0, 1, 2]
     assert float(out["x_adv"].abs().max()) <= 1.0
+    noises = torch.load(tmp_path / "noise.pt")                                     # main.py:619
+    assert isinstance(noises, list) and len(noises) == 1 and noises[0].shape[1:] == (4, 8, 8)
+    # the same three images in one pass give the same result: passes are independent
+    rc = main(["--num_images", "3", "--resolution", "64", "--max_train_steps", "4", "--train_batch_size", "2",
+               "--images_per_pass", "8", "--output_dir", str(tmp_path / "one")])
+    assert rc == 0
+    one = torch.load(tmp_path / "one" / "adversarial_rank0.pt")
+    assert torch.equal(one["x_adv"][:2], out["x_adv"][:2])
+
+
+def test_cli_main_reads_a_jpeg_folder(dev, tmp_path):
+    """--train_data_dir: ImagePromptDataset (data/dataset.py:7-43) -> pinned sharded loader -> PGD."""
+    from PIL import Image
+    from tml_image_editing_defense_b200.main import main
+    rng = np.random.default_rng(1)
+    (tmp_path / "imgs").mkdir()
+    for k, (h, w) in enumerate([(80, 120), (100, 70), (64, 64)]):
+        Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(tmp_path / "imgs" / f"im{k}.jpg")
+    rc = main(["--train_data_dir", str(tmp_path / "imgs"), "--resolution", "64", "--max_train_steps", "3",
+               "--train_batch_size", "2", "--images_per_pass", "2", "--output_dir", str(tmp_path / "out")])
+    assert rc == 0
+    out = torch.load(tmp_path / "out" / "adversarial_rank0.pt")
+    assert out["x_adv"].shape == (3, 3, 64, 64) and torch.isfinite(out["x_adv"]).all()
+    assert (tmp_path / "out" / "adversarial_image_0.png").exists()                 # main.py:618
 
 
 def test_non_square_and_ragged_batch(dev, models):

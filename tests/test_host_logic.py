@@ -230,3 +230,30 @@ def test_parser_keeps_reference_flag_names():
     assert a.seed == 7 and a.max_train_steps == 3 and a.output_dir == "o"
     b = parse_args([])
     assert not b.gradient_checkpointing and not b.allow_tf32
+
+
+def test_sharded_image_loader_partitions_and_orders():
+    """The host pipeline: shards r::world cover the dataset exactly once, batches keep the shard order, the last batch
+    may be short, and shuffling permutes inside a shard only."""
+    from tml_image_editing_defense_b200.dataset import SyntheticImageDataset
+    from tml_image_editing_defense_b200.loader import ShardedImageLoader
+    ds = SyntheticImageDataset(11, resolution=8, seed=5)
+    seen = []
+    for r in range(3):
+        ld = ShardedImageLoader(ds, batch_size=2, rank=r, world_size=3, device="cpu", fetch=ds.batch)
+        assert len(ld) == (len(range(r, 11, 3)) + 1) // 2
+        got = []
+        for idx, imgs, prompts in ld:
+            assert imgs.shape == (len(idx), 3, 8, 8) and len(prompts) == len(idx)
+            for j, i in enumerate(idx):
+                assert torch.equal(imgs[j], ds.image(i))
+            got += idx
+        assert got == list(range(r, 11, 3))
+        seen += got
+    assert sorted(seen) == list(range(11))
+    a = ShardedImageLoader(ds, 4, rank=1, world_size=2, device="cpu", shuffle=True, seed=3)
+    b = ShardedImageLoader(ds, 4, rank=1, world_size=2, device="cpu", shuffle=True, seed=3)
+    assert a.indices == b.indices and sorted(a.indices) == list(range(1, 11, 2)) and a.indices != list(range(1, 11, 2))
+    per_item = ShardedImageLoader(ds, 3, device="cpu")              # the dataset[i] -> (image, prompt) path
+    assert [i for idx, _, _ in per_item for i in idx] == list(range(11))
+    assert list(ShardedImageLoader(SyntheticImageDataset(0, 8), 2, device="cpu")) == []   # empty shard

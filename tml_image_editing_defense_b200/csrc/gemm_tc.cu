@@ -358,6 +358,11 @@ __device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4&
                  : "l"(p));
 }
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -516,7 +521,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // tcgen05.ld 32 columns -> alpha / bias (from shared memory) / residual -> pack -> its own [32 rows][32 cols]
 // staging buffer (two of them) -> its own TMA store.  Only __syncwarp between the steps; ~70 instructions per chunk.
 // ------------------------------------------------------------------------------------------------
-constexpr int EPI_GENERIC = 0, EPI_LEAN_BF16 = 1, EPI_LEAN_F32 = 2;
+// EPI_LEAN_ATTN = the bf16 lean epilogue with the row-wise attention modes (GemmOp::epi_mode 1..3) compiled in; the plain
+// instantiations carry none of that code (sharing one instantiation cost the 1x1 shortcuts 27 %, measured).
+constexpr int EPI_GENERIC = 0, EPI_LEAN_BF16 = 1, EPI_LEAN_F32 = 2, EPI_LEAN_ATTN = 3;
 
 template <int EPI, bool PAIR>
 __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorMap* mapD, uint8_t* out_stage, float* bias_s,
@@ -538,7 +545,7 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
     const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
     const float alpha = p.alpha;
     const bool has_bias = p.bias != nullptr, has_res = p.resid != nullptr;
-    const int mode = EPI == EPI_LEAN_BF16 ? p.epi_mode : 0;   // 0 plain, 1 row max, 2 exp, 3 softmax backward
+    const int mode = EPI == EPI_LEAN_ATTN ? p.epi_mode : 0;   // 0 plain, 1 row max, 2 exp, 3 softmax backward
     const int htag = int(crank) * 100;
     int acc = 0, buf = 0, bias_nt = -1;
     uint32_t acc_phase = 0;
@@ -570,20 +577,14 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                 if (mode == 2) ra *= -p.exp_scale;                       // exp2(acc * c - m * c)
                 if (mode == 3) rb = alpha * __ldg(p.row_b + grow);
                 uint32_t v[32];
-                uint4 rr[4], rn[4];   // residual / P~ values of this chunk and (in flight) of the next one
-                if (ch_lo < ch_hi) {
-                    tmem_ld32(t_addr + uint32_t(ch_lo * 32), v);
-                    if (has_res) {
-                        ld_global_nc_256(rrow + ch_lo * 32, rr[0], rr[1]);
-                        ld_global_nc_256(rrow + ch_lo * 32 + 16, rr[2], rr[3]);
-                    }
-                }
+                if (ch_lo < ch_hi) tmem_ld32(t_addr + uint32_t(ch_lo * 32), v);
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
                     const int c = ch * 32;
-                    if (has_res && ch + 1 < ch_hi) {
-                        ld_global_nc_256(rrow + c + 32, rn[0], rn[1]);
-                        ld_global_nc_256(rrow + c + 48, rn[2], rn[3]);
+                    uint4 rr[4];
+                    if (has_res) {
+                        ld_global_nc_256(rrow + c, rr[0], rr[1]);
+                        ld_global_nc_256(rrow + c + 16, rr[2], rr[3]);
                     }
                     if (mode != 1) {
                         if (lane == 0) bulk_wait_group_read<1>();   // the store that last read this buffer is done with it
@@ -636,10 +637,6 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                                 f[8 * j + 6] += bf16_lo(rr[j].w); f[8 * j + 7] += bf16_hi(rr[j].w);
                             }
                         }
-                    }
-                    if (has_res) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
                     }
                     uint8_t* sb = sbase + size_t(buf) * (32 * ROWB);
                     uint8_t* rowp = sb + size_t(lane) * ROWB;
@@ -1464,6 +1461,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                 const float2 m2 = __ldg(&p.gn_mr[(size_t)img * 32 + chn / CPG]);
                 sc = s2.x; sh = s2.y; mean = m2.x; rstd = m2.y;
                 gm = __ldg(p.gn_gamma + chn);
+                if (p.gn_silu) { sc *= 0.5f; sh *= 0.5f; gm *= 0.5f; }   // the tanh form of silu' below works on u/2
             }
             __nv_bfloat16* dp = p.D + off;
             const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.resid) + off;
@@ -1492,13 +1490,16 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                     if (p.dbg_no_epi != 2) dp[(size_t)(k * STEP + j) * N] = b;
                     const float fr = __bfloat162float(b);   // reductions see the values as stored
                     if constexpr (GNB) {
-                        // GroupNorm backward: dxh = dy * act'(x*sc+sh) * gamma; sums of dxh and dxh*x
+                        // GroupNorm backward: dxh = dy * act'(x*sc+sh) * gamma; sums of dxh and dxh*x.
+                        // silu'(u) = sg + u*sg*(1-sg) with sg = (1 + t)/2, t = tanh(u/2):  silu'(u) = (1 + t + h*(1 - t*t))/2,
+                        // h = u/2 -- one MUFU and four FMAs instead of exp + rcp + six (sc, sh, gm arrive pre-halved).
                         const float xv = __uint_as_float(uint32_t(x[j]) << 16);
                         float dxh = fr * gm;
                         if (p.gn_silu) {
-                            const float u = fmaf(xv, sc, sh);
-                            const float sg = __fdividef(1.f, 1.f + __expf(-u));
-                            dxh *= sg * fmaf(u, 1.f - sg, 1.f);
+                            const float h = fmaf(xv, sc, sh);
+                            const float t = tanh_approx(h);
+                            const float z = fmaf(h, fmaf(-t, t, 1.f), t);
+                            dxh = fmaf(dxh, z, dxh);
                         }
                         s += dxh;
                         ss = fmaf(dxh, xv, ss);
@@ -1858,7 +1859,9 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, EPI_LEAN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, EPI_LEAN_ATTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, EPI_LEAN_ATTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set = true;
     }
@@ -1888,12 +1891,14 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = t.out_bytes
-            ? cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_LEAN_BF16>, mapA, mapB, mapD, p)
+        cudaError_t le = op.epi_mode != 0
+            ? cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_LEAN_ATTN>, mapA, mapB, mapD, p)
             : cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<true, EPI_GENERIC>, mapA, mapB, mapD, p);
         if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
     } else {
-        if (t.out_bytes && op.out_fp32)
+        if (op.epi_mode != 0)
+            conv_gemm_tcgen05_kernel<false, EPI_LEAN_ATTN><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
+        else if (t.out_bytes && op.out_fp32)
             conv_gemm_tcgen05_kernel<false, EPI_LEAN_F32><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);
         else if (t.out_bytes)
             conv_gemm_tcgen05_kernel<false, EPI_LEAN_BF16><<<grid, kThreads, t.smem_bytes, stream>>>(mapA, mapB, mapD, p);

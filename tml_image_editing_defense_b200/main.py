@@ -22,6 +22,7 @@ import torch.distributed as dist
 
 from .configs import TrainConfig, UniversalConfig
 from .dataset import ImagePromptDataset, SyntheticImageDataset, shard_indices
+from .loader import ShardedImageLoader
 from .parser import parse_args
 from .trainer import Trainer
 from .universal import UniversalTrainer
@@ -49,14 +50,12 @@ def main(argv=None) -> int:
 
     if args.train_data_dir:
         ds = ImagePromptDataset(args.train_data_dir, "", resolution=args.resolution)
-        n = len(ds)
-        fetch = lambda idx: torch.stack([ds[i][0] for i in idx])  # noqa: E731
+        fetch = None
     else:
-        sds = SyntheticImageDataset(args.num_images, resolution=args.resolution, seed=args.seed)
-        n = len(sds)
-        fetch = sds.batch
+        ds = SyntheticImageDataset(args.num_images, resolution=args.resolution, seed=args.seed)
+        fetch = ds.batch
+    n = len(ds)
     idx = shard_indices(n, rank, world)
-    images = fetch(idx).to(dev) if idx else torch.empty((0, 3, args.resolution, args.resolution), device=dev)
     # target latent: encoding of a fixed other image (main.py:75); synthetic: a seeded N(0,1) latent
     g = torch.Generator().manual_seed(args.seed + 17)
     lat = (1, 4, args.resolution // 8, args.resolution // 8)
@@ -64,6 +63,8 @@ def main(argv=None) -> int:
 
     t0 = time.perf_counter()
     if args.universal:
+        images = torch.cat([im for _, im, _ in ShardedImageLoader(ds, max(1, args.train_batch_size), rank, world, dev, fetch=fetch)]) \
+            if idx else torch.empty((0, 3, args.resolution, args.resolution), device=dev)
         ucfg = UniversalConfig(grad_reps=args.grad_reps, eps=args.eps, step_size=args.step_size,
                                resolution=args.resolution, latent_loss=args.latent_loss, max_steps=args.max_train_steps)
         ut = UniversalTrainer.for_b200(ucfg, vae)
@@ -88,19 +89,25 @@ def main(argv=None) -> int:
                           n_optimization_steps=args.max_train_steps, latent_loss=args.latent_loss, seed=args.seed,
                           device=dev, resolution=args.resolution, output_path=out_dir)
         tr = Trainer(cfg, vae, micro_batch=args.train_batch_size)
-        x_adv = tr.run(images, target_latent=target) if len(idx) else images
+        # the shard is attacked `--images_per_pass` images at a time; the loader stages the next pass in pinned memory and
+        # uploads it on a side stream while this one runs (run_all.py:23-93 walks its image list one by one)
+        loader = ShardedImageLoader(ds, max(1, args.images_per_pass), rank, world, dev, fetch=fetch)
+        outs, hist = [], []
+        for _, images, _ in loader:
+            outs.append(tr.run(images, target_latent=target).cpu())
+            hist = hist or list(tr.loss_history)          # the loss trajectory reported is the first pass's
+        x_adv = torch.cat(outs) if outs else torch.empty((0, 3, args.resolution, args.resolution))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        torch.save({"indices": idx, "x_adv": x_adv.cpu()}, out_dir / f"adversarial_rank{rank}.pt")
+        torch.save({"indices": idx, "x_adv": x_adv}, out_dir / f"adversarial_rank{rank}.pt")
         # main.py:619: the fixed training noises, so inference can replay them (main.py:622)
-        torch.save([n.cpu() for n in tr.noises] if tr.noises is not None else None,
+        torch.save([n_.cpu() for n_ in tr.noises] if tr.noises is not None else None,
                    out_dir / ("noise.pt" if world == 1 else f"noise_rank{rank}.pt"))
         try:
             for i, im in zip(idx[:4], Trainer.to_pil(x_adv[:4])):
                 im.save(out_dir / f"adversarial_image_{i}.png")   # main.py:618
         except Exception:
             pass
-        hist = tr.loss_history
         print(json.dumps({"rank": rank, "mode": "per-image", "steps": args.max_train_steps, "images": len(idx),
                           "seconds": dt, "image_pgd_iters_per_s": len(idx) * args.max_train_steps / dt,
                           "loss_first": hist[0] if hist else None, "loss_last": hist[-1] if hist else None}), flush=True)

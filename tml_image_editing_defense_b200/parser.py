@@ -15,6 +15,8 @@ def parse_args(input_args=None):
                    help="Path to a torch state dict (diffusers AutoencoderKL keys); random init if omitted.")
     p.add_argument("--train_data_dir", type=str, default=None, help="Folder of *.jpg images; synthetic if omitted.")
     p.add_argument("--num_images", type=int, default=64)
+    p.add_argument("--images_per_pass", type=int, default=64,
+                   help="Images of this rank's shard attacked together (one PGD run per pass; the next pass is prefetched).")
     p.add_argument("--output_dir", type=str, default="./output")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--resolution", type=int, default=512)
