@@ -167,6 +167,12 @@ def run_gemm_suite(lib, dev):
         ("halo pair 512->512 4x128 2 n-tiles", dict(B=2, H=4, W=128, Cin=512, N=512, mode=0, resid=True, bias=True, gn=1)),
         ("halo pair N=16 dgrad 8x256", dict(B=2, H=8, W=256, Cin=128, N=16, mode=1)),
         ("halo multi-wave 128->128 128x128 B=4", dict(B=4, H=128, W=128, Cin=128, N=128, mode=0, resid=True)),
+        # rows of 64 pixels: pitch-66 halo tile, 33 M tiles of 128 slots per 64 rows (pairs = same tile of two images)
+        ("h66 pair 512->512 64x64 B=2 all", dict(B=2, H=64, W=64, Cin=512, N=512, mode=0, bias=True, resid=True, gn=1)),
+        ("h66 pair dgrad 512->512 64x64 B=4 +gnbwd", dict(B=4, H=64, W=64, Cin=512, N=512, mode=1, gn=2)),
+        ("h66 single 256->256 64x64 B=3 +stats", dict(B=3, H=64, W=64, Cin=256, N=256, mode=0, bias=True, gn=1)),
+        ("h66 single 128->128 128x64 B=1 resid", dict(B=1, H=128, W=64, Cin=128, N=128, mode=0, resid=True)),
+        ("h66 pair 64->256 64x64 B=2", dict(B=2, H=64, W=64, Cin=64, N=256, mode=0)),
         # operand-swapped kernel (N = 128 output channels, rows of 256 pixels)
         ("swap 128->128 4x256 bias +stats", dict(B=2, H=4, W=256, Cin=128, N=128, mode=0, bias=True, gn=1)),
         ("swap dgrad 128->128 3x512 resid", dict(B=1, H=3, W=512, Cin=128, N=128, mode=1, resid=True)),

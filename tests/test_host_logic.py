@@ -66,7 +66,8 @@ def _conv_desc(B, H, W, Cin, N, gn, taps=9):
 def test_partial_sum_geometry_of_the_fused_reductions():
     """Host-side tiling logic (no GPU needed): how many GroupNorm partial entries per image each kernel writes.
     Operand-swapped kernel (rows of >= 128 pixels, 128/256/512 channels): one entry per 128 pixels for the statistics
-    (8 epilogue warps), per 64 pixels for the backward sums (16 warps); pixel-major kernel: one per 128-row tile."""
+    (8 epilogue warps), per 64 pixels for the backward sums (16 warps); pixel-major kernel: one per 128-row tile; 3x3
+    convolutions on rows of 64 pixels: one per 128 slots of the pitch-66 halo space (64 rows x 66 / 128 = 33)."""
     import ctypes as C
     from tml_image_editing_defense_b200 import _lib
     lib = _lib.load()
@@ -75,8 +76,11 @@ def test_partial_sum_geometry_of_the_fused_reductions():
     assert n(_conv_desc(2, 8, 512, 128, 128, 2)) == 8 * 512 // 64
     assert n(_conv_desc(2, 8, 128, 512, 512, 1)) == 8 * 128 // 128          # swapped, CTA pairs (rows of 128 pixels)
     assert n(_conv_desc(2, 8, 128, 512, 512, 2)) == 8 * 128 // 64
-    assert n(_conv_desc(2, 64, 64, 512, 512, 1)) == lib.tml_debug_gn_tiles_per_image(64, 64) == 32   # pixel-major
-    assert n(_conv_desc(2, 64, 64, 512, 512, 2)) == 32
+    assert lib.tml_debug_gn_tiles_per_image(64, 64) == 32
+    assert n(_conv_desc(2, 64, 64, 512, 512, 1)) == 33                      # 3x3 on rows of 64 pixels: pitch-66 halo tiles
+    assert n(_conv_desc(2, 64, 64, 512, 512, 2)) == 33
+    assert n(_conv_desc(2, 64, 64, 512, 512, 1, taps=1)) == 32              # 1x1 at 64^2: plain pixel-major tiles
+    assert n(_conv_desc(2, 32, 32, 512, 512, 1)) == lib.tml_debug_gn_tiles_per_image(32, 32) == 8   # rows of 32 pixels
     assert n(_conv_desc(2, 7, 128, 512, 512, 1)) == lib.tml_debug_gn_tiles_per_image(7, 128)         # odd rows: no pairs
     assert n(_conv_desc(2, 16, 16, 128, 256, 1, taps=1)) == lib.tml_debug_gn_tiles_per_image(16, 16)  # 1x1: pixel-major
 

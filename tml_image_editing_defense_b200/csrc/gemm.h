@@ -68,6 +68,7 @@ struct GemmOp {
 // Derived tiling, shared by both kernels (the debug kernel ignores the tile fields).
 struct GemmTiling {
     int TW, TH, rows_valid, tiles_w, tiles_h, BN, n_tiles, kchunks, stages, mt, stage_bytes, halo, halo_bytes, pair;
+    int h66;         // halo mode on rows of 64 pixels (pitch-66 tile, 128-slot M tiles; tiles_h = tiles per image)
     int out_bytes;   // > 0: the epilogue stages output tiles in shared memory and writes them with TMA stores
     size_t smem_bytes;
 };

@@ -149,6 +149,10 @@ int gemm_row_partials(const GemmOp& op) {
 int gemm_gn_chunks_per_image(const GemmOp& op) {
     if (op.gn_mode != 0 && gemm_swapped_shape(op))   // one entry per epilogue warp's pixel range (64 or 128 pixels)
         return op.OH * op.OW / (op.gn_mode == 2 ? sw_px_per_warp(true) : sw_px_per_warp(false));
+    GemmOp shape = op;        // the geometry does not depend on the reduction's buffers, which a caller may set later
+    shape.gn_mode = 0;
+    GemmTiling t;
+    if (gemm_plan(shape, &t) == 0 && t.h66) return t.tiles_h;   // pitch-66 tiles of 64-pixel rows: 33 per 64 rows
     return gemm_gn_tiles_per_image(op.OH, op.OW);
 }
 
@@ -186,6 +190,45 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
             seen |= 1u << ((op.dh[i] + 1) * 3 + op.dw[i] + 1);
         }
         if (seen != 0x1FFu) halo = false;
+    }
+    // Halo mode for rows of 64 pixels ("h66", the 512-channel layers at 64^2): the halo tile is {64 channels, 66 pixels
+    // (x = -1 .. 64, the two ends zero-filled by TMA), 6 rows}, i.e. the image with a row pitch of 66 in SHARED memory only.
+    // In that pitch-66 index space s = 66*y + x + 1 a tap is the affine shift 66*dh + dw, so an M tile is 128 consecutive
+    // slots starting anywhere (two of every 66 are the zero columns: junk output rows that are never stored), read through
+    // row-shifted descriptors like the 130-pixel tile.  64 rows x 66 = 33 tiles of 128 per image.  The A operand then costs
+    // 50 KB per 64-channel chunk instead of nine 16 KB tap tiles: 64 -> 40 B/clk/SM from L2, which is what bounded these layers.
+    static const bool no_h66 = getenv("TML_NO_H66") && getenv("TML_NO_H66")[0] == '1';   // tuning switch
+    bool h66 = !no_halo && !no_h66 && !halo && op.stride == 1 && op.ntaps == 9 && op.OW == 64 && op.A_W == 64 &&
+               op.OH == op.A_H && (op.OH * 66) % 128 == 0 && op.B_sBatch == 0 && op.dbg_shift == 0 && op.D_sN == 1 &&
+               !op.out_fp32 && (op.n_store == 0 || op.n_store == op.N) && op.epi_mode == 0 && op.row_scale == nullptr;
+    if (h66) {
+        unsigned seen = 0;
+        for (int i = 0; i < 9; ++i) {
+            if (op.dh[i] < -1 || op.dh[i] > 1 || op.dw[i] < -1 || op.dw[i] > 1) { h66 = false; break; }
+            seen |= 1u << ((op.dh[i] + 1) * 3 + op.dw[i] + 1);
+        }
+        if (seen != 0x1FFu) h66 = false;
+    }
+    t->h66 = h66 ? 1 : 0;
+    if (h66) {
+        t->halo = 1;
+        t->out_bytes = 0;
+        t->TW = 64; t->TH = 2; t->rows_valid = 128;
+        t->tiles_w = 1; t->tiles_h = op.OH * 66 / 128;      // tiles per image (in the pitch-66 space)
+        t->BN = BN; t->n_tiles = op.N / BN; t->kchunks = op.A_C / kBlockK;
+        t->mt = 1;
+        t->halo_bytes = ((6 * 66 * 128) + 1023) / 1024 * 1024;
+        const long cta_m_tiles = (long)op.A_B * t->tiles_h;
+        static const bool no_pair66 = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
+        // (a pair = the same tile of two consecutive images, see decode_sub: needs an even number of images)
+        t->pair = (!no_pair66 && BN == 256 && op.A_B % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
+        t->stage_bytes = (t->pair ? BN / 2 : BN) * 128;
+        int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - 2 * t->halo_bytes) / t->stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) { set_error("%s: halo tiles do not fit", op.name); return -1; }
+        t->stages = stages;
+        t->smem_bytes = size_t(2) * t->halo_bytes + size_t(stages) * t->stage_bytes + kBarrierBytes + kGnSmemBytes + 1024;
+        return 0;
     }
     if (halo) { TW = 128; TH = 1; }
     t->halo = halo ? 1 : 0;
@@ -300,6 +343,7 @@ struct TcParams {
     // halo mode (3x3 stride-1 convolutions, output rows of 128 pixels): one (mt+2) x 130-pixel halo tile per
     // 64-channel chunk serves all nine taps through row-shifted UMMA descriptors
     int halo, halo_bytes;
+    int h66;           // halo mode on rows of 64 pixels: pitch-66 tile of 6 rows, M tile = 128 consecutive slots (see gemm_plan)
     int pair;          // halo mode on CTA pairs: cta_group::2 MMA (M = 256 over two SMs), each CTA stages half of B
     volatile int* hang_where;  // mapped host word that receives the id of a wait that timed out
     int out_bytes;     // > 0: dense outputs are staged in shared memory ([2 halves][2 buffers][128 rows][32 cols]) and TMA-stored
@@ -320,7 +364,17 @@ constexpr int kHaloW = 130;  // 128 output pixels + one halo pixel on each side
 struct SubTile { int img, oh0, ow0, sub_in_img; };
 __device__ __forceinline__ SubTile decode_sub(const TcParams& p, int mtile, int sub) {
     SubTile s;
-    if (p.halo) {
+    if (p.h66) {
+        // mtile -> (image, tile k of the pitch-66 space): oh0 / ow0 carry the first slot's row and slot-in-row
+        // (CTA pairs take the same tile of two consecutive images: one descriptor offset must serve both CTAs)
+        const int mq = p.pair ? (mtile >> 1) : mtile;
+        const int k = mq % p.tiles_h;
+        s.img = p.pair ? 2 * (mq / p.tiles_h) + (mtile & 1) : mq / p.tiles_h;
+        const int s0 = k * 128;
+        s.oh0 = s0 / 66;
+        s.ow0 = s0 - s.oh0 * 66;
+        s.sub_in_img = k;
+    } else if (p.halo) {
         const int tw_i = mtile % p.tiles_w;
         const int r = mtile / p.tiles_w;
         const int hp_n = p.tiles_h / p.mt;
@@ -847,7 +901,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         if (lane == 0 && p.halo) {
             int hs = 0;
             uint32_t hphase = 0;
-            const uint32_t halo_tx = uint32_t(p.mt + 2) * kHaloW * 128u;
+            const uint32_t halo_tx = p.h66 ? 6u * 66u * 128u : uint32_t(p.mt + 2) * kHaloW * 128u;
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const SubTile s0 = decode_sub(p, PAIR ? (tile / p.n_tiles) * 2 + int(crank) : tile / p.n_tiles, 0);
                 for (int ch = 0; ch < p.kchunks; ++ch) {
@@ -860,8 +914,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             continue;
                         }
                         if (crank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], 2u * halo_tx);
-                        tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
-                                        s0.oh0 - 1, s0.img);
+                        tma_load_4d_2sm(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK,
+                                        p.h66 ? -1 : s0.ow0 - 1, p.h66 ? s0.oh0 - 2 : s0.oh0 - 1, s0.img);
                         hs ^= 1;
                         if (hs == 0) hphase ^= 1u;
                         continue;
@@ -869,8 +923,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     if (p.dbg_mma_only && (hphase != 0 || tile != tile0)) { mbar_arrive(&hfull_bar[hs]); hs ^= 1; if (hs == 0) hphase ^= 1u; continue; }
                     mbar_arrive_expect_tx(&hfull_bar[hs], halo_tx);
                     // rows oh0-1 .. oh0+mt, pixels ow0-1 .. ow0+128: out-of-range pixels arrive as zeros (= padding)
-                    tma_load_4d(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK, s0.ow0 - 1,
-                                s0.oh0 - 1, s0.img);
+                    // (h66: pixels -1 .. 64 of rows r0-2 .. r0+3, r0 = row of the tile's first slot)
+                    tma_load_4d(smem + size_t(hs) * p.halo_bytes, &mapA, &hfull_bar[hs], ch * kBlockK,
+                                p.h66 ? -1 : s0.ow0 - 1, p.h66 ? s0.oh0 - 2 : s0.oh0 - 1, s0.img);
                     hs ^= 1;
                     if (hs == 0) hphase ^= 1u;
                 }
@@ -893,6 +948,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(acc * acc_cols);
                 if (p.halo) {
+                    // h66: slot-in-row of the tile's first output slot (the same for both CTAs of a pair)
+                    const int xi0 = p.h66 ? decode_sub(p, PAIR ? (tile / p.n_tiles) * 2 : tile / p.n_tiles, 0).ow0 : 0;
                     for (int ch = 0; ch < p.kchunks; ++ch) {
                         mbar_wait(&hfull_bar[hs], hphase, hw, htag + 4);
                         tc_fence_after();
@@ -902,7 +959,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             tc_fence_after();
                             const uint64_t b_desc = umma_desc_sw128(smem_u32(ring + size_t(stage) * p.stage_bytes));
                             // operand rows = 128 consecutive halo pixels starting at (row sub+dh+1, pixel dw+1)
-                            const uint32_t row0 = uint32_t((p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
+                            // (h66: the tile holds rows r0-2 .. r0+3 at a pitch of 66 slots, slot = x + 1)
+                            const uint32_t row0 = p.h66 ? uint32_t((p.dh[tap] + 2) * 66 + xi0 + p.dw[tap])
+                                                        : uint32_t((p.dh[tap] + 1) * kHaloW + p.dw[tap] + 1);
                             const uint64_t a_desc0 = umma_desc_sw128(h_addr + row0 * 128u);
                             const uint32_t first = (ch | tap) != 0 ? 1u : 0u;
                             if (elect_one()) {
@@ -988,7 +1047,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         const int half = e >> 2;
         const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
         const int row = q * 32 + lane;
-        const bool valid = row < p.rows_valid;
+        const bool row_ok = row < p.rows_valid;
         const int r_th = row / p.TW, r_tw = row - r_th * p.TW;
         const int cpg = p.gn_cpg;
         const int nch = p.BN >> 5;                      // 32-column chunks in the tile (0 when BN == 16)
@@ -1008,7 +1067,14 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             for (int sub = 0; sub < p.mt && p.dbg_no_epi != 1; ++sub) {
                 const SubTile stl = decode_sub(p, mtile, sub);
                 const int sub_in_img = stl.sub_in_img, img = stl.img;
-                const int oh = stl.oh0 + r_th, ow = stl.ow0 + r_tw;
+                int oh = stl.oh0 + r_th, ow = stl.ow0 + r_tw;
+                bool valid = row_ok;
+                if (p.h66) {   // row = slot of the pitch-66 space: slot 0 / 65 of every row is a zero column (no output)
+                    const int sl = stl.ow0 + row;
+                    const int dr = sl / 66, xi = sl - dr * 66;
+                    oh = stl.oh0 + dr; ow = xi - 1;
+                    valid = xi >= 1 && xi <= 64;
+                }
                 const long long d_off = (long long)img * p.D_sB + (long long)oh * p.D_sH + (long long)ow * p.D_sW;
                 const long long r_off = (long long)img * p.R_sB + (long long)oh * p.R_sH + (long long)ow * p.R_sW;
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * acc_cols + sub * p.BN);
@@ -1782,6 +1848,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
         cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
         cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(t.TW + (op.dbg_shift ? 8 : 0)), (cuuint32_t)t.TH, 1};
         if (t.halo) { box[1] = 130; box[2] = (cuuint32_t)(t.mt + 2); }
+        if (t.h66) { box[1] = 66; box[2] = 6; }
         if (op.dbg_shift && (t.TH != 1 || t.TW > 64 || t.mt != 1)) { set_error("dbg_shift needs TH=1, TW<=64, mt=1"); return -1; }
         if ((rc = encode_map(&mapA, op.A, 4, dims, str, box, op.name))) return rc;
     } else {
@@ -1839,7 +1906,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
     p.dbg_shift = op.dbg_shift; p.dbg_bo = op.dbg_bo;
-    p.halo = t.halo; p.halo_bytes = t.halo_bytes;
+    p.halo = t.halo; p.halo_bytes = t.halo_bytes; p.h66 = t.h66;
     p.pair = t.pair;
     p.epi_mode = op.epi_mode; p.row_a = op.row_a; p.row_b = op.row_b; p.row_part = op.row_part; p.exp_scale = op.exp_scale;
     p.row_scale = op.row_scale;
