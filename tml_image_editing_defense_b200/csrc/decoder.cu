@@ -121,17 +121,10 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
     L.B = B; L.h = h; L.w = w;
     Arena S;
     const int Ctop = c.block_out_channels[nb - 1];
-    size_t ws_peak = 0, gmax = 0;
-    auto resnet_ws = [&](int ci, int co, int hh, int ww) {
-        const size_t f = gn_partial_bytes(B, hh * ww) + act_bytes(B, hh, ww, ci) + 2 * act_bytes(B, hh, ww, co) + 4096;
-        const size_t b = 2 * act_bytes(B, hh, ww, co) + 2 * act_bytes(B, hh, ww, ci) + gn_partial_bytes(B, hh * ww) +
-                         fused_partial_bytes(B, hh, ww) + (size_t)B * 32 * sizeof(float2) + 8192;
-        return f > b ? f : b;
-    };
+    // (the scratch size is measured by a dry run of the walks: dec_layout)
     int hh = h, ww = w;
     L.x0 = S.alloc(act_bytes(B, hh, ww, Ctop));
     size_t cur = L.x0;
-    gmax = act_bytes(B, hh, ww, Ctop);
     auto add_resnet = [&](int ci, int co) {
         ResnetRec r;
         r.h = hh; r.w = ww; r.x = cur;
@@ -139,8 +132,6 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
         r.h1 = S.alloc(act_bytes(B, hh, ww, co));
         r.g2 = alloc_gn(S, B, co);
         r.out = S.alloc(act_bytes(B, hh, ww, co));
-        ws_peak = std::max(ws_peak, resnet_ws(ci, co, hh, ww));
-        gmax = std::max(gmax, std::max(act_bytes(B, hh, ww, ci), act_bytes(B, hh, ww, co)));
         L.res.push_back(r);
         cur = r.out;
     };
@@ -169,9 +160,6 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
             u.h = hh; u.w = ww;
             hh *= 2; ww *= 2;
             u.out = S.alloc(act_bytes(B, hh, ww, cout));
-            // forward: upsampled input; backward: gradient w.r.t. the upsampled input (both [B,2h,2w,C])
-            ws_peak = std::max(ws_peak, act_bytes(B, hh, ww, cout) + 8192);
-            gmax = std::max(gmax, act_bytes(B, hh, ww, cout));
             L.ups.push_back(u);
             cur = u.out;
         }
@@ -179,12 +167,8 @@ static int build_dec_layout(TmlEncoder* e, int B, int h, int w) {
     L.gout = alloc_gn(S, B, cin);
     L.xlast = cur;
     L.Hl = hh; L.Wl = ww;
-    // head / tail: latent pack (64 ch), final norm output, d(image) pack (64 ch) + d_a + reductions
-    ws_peak = std::max(ws_peak, act_bytes(B, h, w, 64) + 4096);
-    ws_peak = std::max(ws_peak, gn_partial_bytes(B, hh * ww) + act_bytes(B, hh, ww, cin) + act_bytes(B, hh, ww, 64) +
-                                    fused_partial_bytes(B, hh, ww) + 16384);
     L.saved_bytes = S.peak + 256;
-    L.ws_bytes = ws_peak + 2 * (gmax + 256) + 3 * (fused_partial_bytes(B, hh, ww) + 256) + (64 << 10);
+    L.ws_bytes = 0;   // set by dec_layout from the dry run
     return 0;
 }
 

@@ -1,5 +1,5 @@
 // Bandwidth-bound kernels of the PGD hot path: conv_in pack (hi/lo bf16 split of the fp32 image) / col2im, GroupNorm
-// (+SiLU) forward / backward, softmax forward / backward, transposes, posterior sample + latent loss
+// (+SiLU) forward / backward, attention row helpers and transposes, posterior sample + latent loss
 // gradient, and the fused PGD updates.  All reductions are two-stage with a fixed order, so results
 // are bitwise reproducible run to run and independent of how images are sharded over GPUs.
 #include <cuda_bf16.h>
@@ -45,26 +45,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 // Block-wide sum broadcast to every thread (blockDim.x multiple of 32, <= 1024); fixed order.
-__device__ __forceinline__ float block_sum(float v, float* red /*[33]*/) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        float t = lane < nw ? red[lane] : 0.f;
-        t = warp_sum(t);
-        if (lane == 0) red[32] = t;
-    }
-    __syncthreads();
-    return red[32];
-}
 __device__ __forceinline__ double block_sum_d(double v, double* red /*[33]*/) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     v = warp_sum_d(v);
@@ -74,20 +55,6 @@ __device__ __forceinline__ double block_sum_d(double v, double* red /*[33]*/) {
     if (w == 0) {
         double t = lane < nw ? red[lane] : 0.0;
         t = warp_sum_d(t);
-        if (lane == 0) red[32] = t;
-    }
-    __syncthreads();
-    return red[32];
-}
-__device__ __forceinline__ float block_max(float v, float* red /*[33]*/) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    v = warp_max(v);
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        float t = lane < nw ? red[lane] : -INFINITY;
-        t = warp_max(t);
         if (lane == 0) red[32] = t;
     }
     __syncthreads();
@@ -505,72 +472,9 @@ void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const 
 }
 
 // ================================================================================================
-// softmax over rows of fp32 logits -> bf16 probabilities; and its backward
-//   dS = P * (dP - sum_j P*dP) * scale         (diffusers Attention)
+// Attention helpers.  (The softmax itself -- row max, exp, normalisation, backward -- runs in the epilogues of the
+// QK^T / dP GEMMs, see GemmOp::epi_mode; what is left here are the transposes and the tiny row kernels.)
 // ================================================================================================
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P,
-                                                           int cols) {
-    __shared__ float red[33];
-    const float* row = S + (size_t)blockIdx.x * cols;
-    bf16* out = P + (size_t)blockIdx.x * cols;
-    float mx = -INFINITY;
-    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
-        const float4 v = *reinterpret_cast<const float4*>(row + c);
-        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-    }
-    mx = block_max(mx, red);
-    float sum = 0.f;
-    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
-        const float4 v = *reinterpret_cast<const float4*>(row + c);
-        sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
-    }
-    sum = block_sum(sum, red);
-    const float inv = 1.f / sum;
-    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
-        const float4 v = *reinterpret_cast<const float4*>(row + c);
-        uint2 o;
-        o.x = pack2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
-        o.y = pack2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
-        *reinterpret_cast<uint2*>(out + c) = o;
-    }
-}
-
-void launch_softmax_rows(const float* S, bf16* P, long long rows, int cols, cudaStream_t s) {
-    if (g_dry_run) return;
-    softmax_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(S, P, cols);
-    COUNT_LAUNCH();
-}
-
-__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __restrict__ P, const float* __restrict__ dP,
-                                                               bf16* __restrict__ dS, float scale, int cols) {
-    __shared__ float red[33];
-    const bf16* prow = P + (size_t)blockIdx.x * cols;
-    const float* drow = dP + (size_t)blockIdx.x * cols;
-    bf16* out = dS + (size_t)blockIdx.x * cols;
-    float dot = 0.f;
-    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
-        const uint2 u = *reinterpret_cast<const uint2*>(prow + c);
-        const float4 d = *reinterpret_cast<const float4*>(drow + c);
-        dot += bf_lo(u.x) * d.x + bf_hi(u.x) * d.y + bf_lo(u.y) * d.z + bf_hi(u.y) * d.w;
-    }
-    dot = block_sum(dot, red);
-    for (int c = threadIdx.x * 4; c < cols; c += 1024) {
-        const uint2 u = *reinterpret_cast<const uint2*>(prow + c);
-        const float4 d = *reinterpret_cast<const float4*>(drow + c);
-        uint2 o;
-        o.x = pack2(bf_lo(u.x) * (d.x - dot) * scale, bf_hi(u.x) * (d.y - dot) * scale);
-        o.y = pack2(bf_lo(u.y) * (d.z - dot) * scale, bf_hi(u.y) * (d.w - dot) * scale);
-        *reinterpret_cast<uint2*>(out + c) = o;
-    }
-}
-
-void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float scale, long long rows, int cols,
-                             cudaStream_t s) {
-    if (g_dry_run) return;
-    softmax_bwd_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, dS, scale, cols);
-    COUNT_LAUNCH();
-}
-
 // out[b][c][r] = in[b][r][c].  64x64 tiles; each thread moves bf16 pairs (4-byte accesses, 128-byte
 // warp transactions on both sides); the +2 padding keeps the column reads bank-conflict free.
 // row_scale (optional): input row r of batch b is multiplied by row_scale[b * R + r] on the way.

@@ -38,9 +38,6 @@ void launch_gn_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const 
                          cudaStream_t s);
 
 // attention helpers
-void launch_softmax_rows(const float* S, bf16* P, long long rows, int cols, cudaStream_t s);
-void launch_softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, float scale, long long rows, int cols,
-                             cudaStream_t s);
 // out[b][c][r] = in[b][r][c]; in row stride ld_in, batch strides in elements
 void launch_transpose(const bf16* in, bf16* out, int batch, int R, int C, long long ld_in, long long bs_in,
                       long long ld_out, long long bs_out, cudaStream_t s, const float* row_scale = nullptr);

@@ -365,18 +365,10 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
     if ((W / down_factor) % 8) { set_error("W/%d must be a multiple of 8 (got W=%d)", down_factor, W); return -30; }
     L = Layout();
     L.B = B; L.H = H; L.W = W;
-    Arena S, WS;
+    Arena S;   // (the scratch size is measured by a dry run of the walks: enc_layout)
     int h = H, w = W;
     L.x0 = S.alloc(act_bytes(B, h, w, c.block_out_channels[0]));
     size_t cur = L.x0;
-    size_t ws_peak = 0;
-    auto resnet_ws = [&](int ci, int co, int hh, int ww) {
-        // forward: partial + a + a2 + sc ; backward: d_a2 + partial + mm + d_h1 + d_a1 + tmp
-        const size_t f = gn_partial_bytes(B, hh * ww) + act_bytes(B, hh, ww, ci) + 2 * act_bytes(B, hh, ww, co) + 4096;
-        const size_t b = 2 * act_bytes(B, hh, ww, co) + 2 * act_bytes(B, hh, ww, ci) + gn_partial_bytes(B, hh * ww) +
-                         (size_t)B * 32 * sizeof(float2) + 8192;
-        return f > b ? f : b;
-    };
     int cin = c.block_out_channels[0];
     for (int i = 0; i < nb; ++i) {
         const int cout = c.block_out_channels[i];
@@ -387,7 +379,6 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
             r.h1 = S.alloc(act_bytes(B, h, w, cout));
             r.g2 = alloc_gn(S, B, cout);
             r.out = S.alloc(act_bytes(B, h, w, cout));
-            ws_peak = std::max(ws_peak, resnet_ws(cin, cout, h, w));
             L.res.push_back(r);
             cur = r.out;
             cin = cout;
@@ -409,7 +400,6 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
         r.h1 = S.alloc(act_bytes(B, h, w, cin));
         r.g2 = alloc_gn(S, B, cin);
         r.out = S.alloc(act_bytes(B, h, w, cin));
-        ws_peak = std::max(ws_peak, resnet_ws(cin, cin, h, w));
         L.res.push_back(r);
         cur = r.out;
         if (m == 0 && c.mid_block_add_attention) {
@@ -430,20 +420,8 @@ static int build_layout(TmlEncoder* e, int B, int H, int W) {
     L.gout = alloc_gn(S, B, cin);
     L.xlast = cur;
     L.hl = h; L.wl = w;
-    // final: partial + a (fwd); dm64 + d_a + partial + mm (bwd)
-    ws_peak = std::max(ws_peak, gn_partial_bytes(B, h * w) + 2 * act_bytes(B, h, w, cin) + act_bytes(B, h, w, 64) + 16384);
-    // two ping-pong gradient buffers of the largest activation
-    size_t gmax = 0;
-    {
-        int hh = H, ww = W;
-        for (int i = 0; i < nb; ++i) {
-            gmax = std::max(gmax, act_bytes(B, hh, ww, c.block_out_channels[i]));
-            if (i) gmax = std::max(gmax, act_bytes(B, hh, ww, c.block_out_channels[i - 1]));
-            if (i != nb - 1) { hh /= 2; ww /= 2; }
-        }
-    }
     L.saved_bytes = S.peak + 256;
-    L.ws_bytes = ws_peak + 2 * (gmax + 256) + 3 * (fused_partial_bytes(B, H, W) + 256) + (64 << 10);
+    L.ws_bytes = 0;   // set by enc_layout from the dry run
     return 0;
 }
 
