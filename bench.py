@@ -381,7 +381,12 @@ def run_ours(args):
     roofline = {
         "bound": "tensor", "kernel": "conv3x3_swapped_kernel + conv_gemm_tcgen05_kernel (all tcgen05 GEMM launches)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+        "frac": (achieved_tf / peak_tf) if achieved_tf else None,
+        # dram bytes of ONE launch of the dominant instantiation (128->128 3x3 at 512^2, 16 images), ncu --set full
+        "traffic": 2.127e9 if res == 512 else None,
+        "traffic_source": "profiles/r01_prof_swap_c128_r1.txt: dram read 1.087 GB + write 1.040 GB per launch of "
+                          "conv3x3_swapped_kernel<1,0,0,0> on 16 x 512^2 x 128 ch = its algorithmic bytes (input once, "
+                          "output once: 2 x 1.074 GB); the aggregate `achieved` above covers every tcgen05 launch",
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_timed": gemm_n, "launches_dropped": gemm_drop,
         "gemm_ms_per_step": gemm_ms_step, "gemm_share_of_step": gemm_ms_step / (ms_max / args.steps),

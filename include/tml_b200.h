@@ -4,6 +4,9 @@
  * fully asynchronous (no internal synchronisation), int status (0 = ok, <0 = error, message from
  * tml_last_error()).  No C++ exceptions and no torch types cross this boundary.
  * One handle per device; a handle is not thread-safe, distinct handles are.
+ * Devices: a handle-based call (tml_encoder_*, tml_decoder_*) makes the handle's device current for its duration and
+ * restores the caller's device before it returns; the stream must belong to that device.  The pointer-only calls
+ * launch on the CURRENT device: make the buffers' device current before calling them.
  *
  * The reference (OrLichter/tml_image_editing_defense) is pure Python with no FFI of its own; each
  * entry point below names the reference call site it replaces (file:line in /root/reference).
@@ -52,7 +55,9 @@ int tml_encoder_set_weight(TmlEncoder* enc, const char* diffusers_key, const voi
 /* Repack to bf16 K-major GEMM operands (forward and input-gradient forms), fold quant_conv into
  * conv_out, upload.  Must be called once after all weights are set. */
 int tml_encoder_finalize(TmlEncoder* enc, void* stream);
-/* Bytes of scratch (`ws`) and of forward->backward state (`saved`) for a [B,3,H,W] batch. */
+/* Bytes of scratch (`ws`) and of forward->backward state (`saved`) for a [B,3,H,W] batch.  The scratch size is not an
+ * estimate: the call replays the forward and backward walks with every kernel launch disabled and reports the peak of
+ * the same arena the real walks use (so it also validates the shape: a shape the walks cannot run fails here). */
 int tml_encoder_query(TmlEncoder* enc, int B, int H, int W, size_t* workspace_bytes, size_t* saved_bytes);
 /* x: fp32 NCHW [B,3,H,W] -> moments: fp32 NCHW [B, 2*latent, H/8, W/8] (quant_conv output). */
 int tml_encoder_forward(TmlEncoder* enc, const float* x_nchw, int B, int H, int W, float* moments_nchw, void* saved,
@@ -92,7 +97,9 @@ int tml_latent_loss(int kind, const float* moments, const float* noise, const fl
 /* linf branch, main.py:272-274; in place on x_adv; bit-exact with the ATen sequence. */
 int tml_pgd_step_linf(float* x_adv, const float* grad, const float* x, float eps, float step, float lo, float hi,
                       int64_t n, void* stream);
-/* l2 branch, main.py:254-268; mask [B,1,H,W] or NULL; ws of tml_pgd_l2_workspace(B) bytes. */
+/* l2 branch, main.py:254-268; mask [B,1,H,W] or NULL; ws of tml_pgd_l2_workspace(B) bytes.  The per-image norms are
+ * reduced in a fixed order (reproducible for any batch split), not in ATen's: <= 2e-6 absolute on the result
+ * ("Stated tolerances"). */
 size_t tml_pgd_l2_workspace(int B);
 int tml_pgd_step_l2(float* x_adv, const float* grad, const float* x, const float* mask, float eps, float step,
                     float lo, float hi, int B, int C, int64_t hw, void* ws, void* stream);

@@ -429,3 +429,27 @@ def test_grad_cosine_1024_vs_oracle_on_gpu(dev, models):
     gg, l, _ = vae.attack_grad(x, t, n, 0)
     assert cosine(gg, g_ref) >= 0.999
     torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
+
+
+def test_handle_on_a_device_that_is_not_current(models):
+    """TrainConfig.device / AutoencoderKL(device=...) naming a GPU other than the current one: the C ABI
+    guards the device per call, the wrappers use the tensor's own device and stream.  Needs two GPUs."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from tml_image_editing_defense_b200 import ops
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    oracle, vae0 = models
+    assert torch.cuda.current_device() == 0
+    vae1 = AutoencoderKL(device="cuda:1").load_state_dict(oracle.state_dict())
+    g = torch.Generator().manual_seed(41)
+    x = torch.rand((2, 3, 64, 64), generator=g) * 2 - 1
+    t = torch.randn((2, 4, 8, 8), generator=g)
+    n = torch.randn((2, 4, 8, 8), generator=g)
+    g0, l0, _ = vae0.attack_grad(x.to("cuda:0"), t.to("cuda:0"), n.to("cuda:0"), 0)
+    g1, l1, _ = vae1.attack_grad(x.to("cuda:1"), t.to("cuda:1"), n.to("cuda:1"), 0)     # current device is still 0
+    assert torch.cuda.current_device() == 0
+    assert g1.device == torch.device("cuda:1")
+    assert torch.equal(g1.cpu(), g0.cpu()) and torch.equal(l1.cpu(), l0.cpu())           # same bits on either GPU
+    xa = ops.pgd_step_linf_(x.to("cuda:1").clone(), g1, x.to("cuda:1"), 32 / 255, 4 / 255, -1.0, 1.0)
+    xb = ops.pgd_step_linf_(x.to("cuda:0").clone(), g0, x.to("cuda:0"), 32 / 255, 4 / 255, -1.0, 1.0)
+    assert torch.equal(xa.cpu(), xb.cpu())
