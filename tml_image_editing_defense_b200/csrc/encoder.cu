@@ -30,7 +30,7 @@ int tml_encoder_create(const TmlEncoderCfg* cfg, int device, TmlEncoder** out) {
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return -1; }
-    CUDA_OK(cudaSetDevice(device));
+    DeviceGuard guard(device);   // the caller's current device is restored on return
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -48,7 +48,7 @@ int tml_encoder_create(const TmlEncoderCfg* cfg, int device, TmlEncoder** out) {
 
 void tml_encoder_destroy(TmlEncoder* e) {
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceGuard guard(e->device);
     for (void* p : e->dev_allocs) cudaFree(p);
     delete e;
 }
@@ -92,7 +92,7 @@ int tml_encoder_set_weight(TmlEncoder* e, const char* key, const void* ptr, int 
 int tml_encoder_finalize(TmlEncoder* e, void* stream) {
     (void)stream;
     if (!e) { set_error("null handle"); return -1; }
-    CUDA_OK(cudaSetDevice(e->device));
+    DeviceGuard guard(e->device);
     const TmlEncoderCfg& c = e->cfg;
     const int C0 = c.block_out_channels[0];
     {   // conv_in forward as a 3x3 convolution over a 64-channel image [hi(3) | lo(3) | 0(58)]: both halves see the same weights
