@@ -47,7 +47,12 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     if resid:
         ref = ref + resid_t.double()
     Ad, Wd = A.to(dev), Wm.to(torch.bfloat16).to(dev)
-    D = torch.full((B, OH, OW, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    # output with a guard band on both sides: a stray store (wrong tile decode, junk rows of the pitch-66 mode written)
+    # shows up as a changed sentinel even when the values inside happen to be right
+    GUARD = 8192
+    Dbig = torch.full((GUARD + B * OH * OW * N + GUARD,), -777.0, dtype=torch.bfloat16, device=dev)
+    D = Dbig[GUARD: GUARD + B * OH * OW * N].view(B, OH, OW, N)
+    D.fill_(float("nan"))
     d = _lib.TmlGemmDesc()
     d.A = Ad.data_ptr(); d.A_C = Cin; d.A_W = W; d.A_H = H; d.A_B = B
     d.A_sW = Cin; d.A_sH = W * Cin; d.A_sB = H * W * Cin
@@ -92,7 +97,10 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     out = D.float().cpu()
     err = rel_err(out, ref)
     nan = int(torch.isnan(out).sum())
-    ok = err < 1e-2 and nan == 0
+    guard_ok = bool((Dbig[:GUARD] == -777.0).all()) and bool((Dbig[-GUARD:] == -777.0).all())
+    if not guard_ok:
+        print(f"        {name}: stores outside the output tensor (guard band overwritten)")
+    ok = err < 1e-2 and nan == 0 and guard_ok
     if gn:
         # reference reductions over the bf16 values the kernel stored
         o64 = out.double().view(B, OH * OW, 32, N // 32)
