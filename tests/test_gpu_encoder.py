@@ -453,3 +453,37 @@ def test_handle_on_a_device_that_is_not_current(models):
     xa = ops.pgd_step_linf_(x.to("cuda:1").clone(), g1, x.to("cuda:1"), 32 / 255, 4 / 255, -1.0, 1.0)
     xb = ops.pgd_step_linf_(x.to("cuda:0").clone(), g0, x.to("cuda:0"), 32 / 255, 4 / 255, -1.0, 1.0)
     assert torch.equal(xa.cpu(), xb.cpu())
+
+
+def test_attention_with_peaked_softmax_vs_oracle(dev):
+    """The softmax lives in GEMM epilogues (row max from a first QK^T pass, exp2 + bf16 store in the second): logits far
+    from the random-init regime -- q/k projections scaled so that the rows are nearly one-hot, as trained VAEs can be --
+    must still match the fp32 oracle (no overflow, no all-zero rows, gradient parity)."""
+    from oracle.encoder_oracle import encoder_attack_grad, make_oracle, perturb_affine_params
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    oracle = make_oracle(0)
+    perturb_affine_params(oracle, 99)
+    sd = oracle.state_dict()
+    for k in list(sd):
+        if "attentions.0.to_q.weight" in k or "attentions.0.to_k.weight" in k:
+            sd[k] = sd[k] * 6.0             # logits x 36 (std ~12): softmax rows collapse onto a few keys
+    oracle.load_state_dict(sd)
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(oracle.state_dict())
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand((2, 3, 128, 128), generator=g) * 2 - 1).to(dev)
+    t = torch.randn((2, 4, 16, 16), generator=g).to(dev)
+    n = torch.randn((2, 4, 16, 16), generator=g).to(dev)
+    od = oracle.to(dev)
+    g_ref, l_ref, _ = encoder_attack_grad(od, x, t, n, 0)
+    with torch.no_grad():
+        m_ref = od.moments(x)
+    oracle.to("cpu")
+    m = vae.moments(x)
+    assert torch.isfinite(m).all()
+    assert rel_err(m, m_ref) < 5e-2
+    gg, l, _ = vae.attack_grad(x, t, n, 0)
+    assert torch.isfinite(gg).all()
+    # peaked rows amplify the bf16 rounding of q.k (a logit error of 0.03 moves a near-tie): measured 0.989 on B200;
+    # the point of this test is the absence of overflow / empty rows / NaN far from the random-init regime
+    assert cosine(gg, g_ref) >= 0.98
+    torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
