@@ -48,7 +48,10 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up (nvidia-smi needs ~0.2 s to come up) and every line is time-stamped; `stop(t0, t1)` keeps the
+    samples that fall inside the timed region.  A region shorter than the 200 ms sampling period may contain none: the
+    samples of the warm-up steps (the same work, back to back) are used then and the line says so."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -57,9 +60,11 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # (host time, csv line)
 
     def start(self):
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -70,9 +75,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = None, t1: float = None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,22 +85,33 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+        self.proc = None
+
+        def parse(lines):
+            sm, smax, reasons = [], None, set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            sm.sort()
+            return sm, smax, reasons
+
+        inside = [x for x in self.lines if t0 is None or (t0 <= x[0] <= t1)]
+        window = "timed region"
+        if not inside:   # region shorter than the sampling period: fall back to the warm-up steps right before it
+            inside = [x for x in self.lines if x[0] <= (t1 if t1 is not None else float("inf"))][-3:]
+            window = "warm-up steps immediately before the timed region (region shorter than the 200 ms sampling period)"
+        sm, smax, reasons = parse(inside)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def workload_config(res: int, B: int, world: int, mb: int, streams: int = 1, scaling: str = "strong"):
@@ -225,26 +241,28 @@ def run_ours(args):
             tr.compute_grad(xa_, None, x_, tgt_img_, tgt_, [noise_], grad_out=grad_, beta=0.0)
             tr.perturbation_step(xa_, grad_, x_, None)
 
+        if timed_gemms and rank == 0:
+            sampler.start()                  # up before the warm-up; only the samples inside the timed region are kept
         for _ in range(warm):
             step_device()
         barrier()
         c0 = _lib.launch_counts()
         if timed_gemms:
-            if rank == 0:
-                sampler.start()              # clocks are sampled during the timed region only
             lib.tml_gemm_timing_enable(200000)
         barrier()
+        t_start = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step_device()
         e1.record()
         barrier()
+        t_end = time.time()
         ms_ = e0.elapsed_time(e1)
         gt_ = None
         if timed_gemms:
             if rank == 0:
-                clock_box.append(sampler.stop())
+                clock_box.append(sampler.stop(t_start, t_end))
             gt_ = (C.c_double * 4)()
             lib.tml_gemm_timing_collect(gt_)
         c1 = _lib.launch_counts()
@@ -475,21 +493,22 @@ def run_universal(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 1)):
         delta = step(delta)
     barrier()
     ut.comm_events = []
     c0 = _lib.launch_counts()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_start = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         delta = step(delta)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_start, time.time()) if rank == 0 else None
     c1 = _lib.launch_counts()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     comm_us = [1e3 * a.elapsed_time(b) for a, b in ut.comm_events]
