@@ -142,6 +142,9 @@ typedef struct TmlGemmDesc {
     /* fused GroupNorm reductions of the output (see csrc/gemm.h): mode 1 = (sum, sumsq), 2 = backward sums */
     int gn_mode; float* gn_partial; const void* gn_x; const void* gn_ss; const void* gn_mr; const float* gn_gamma; int gn_silu;
     int dbg_shift, dbg_bo; /* hardware experiment: row-shifted UMMA descriptor (tests only) */
+    /* fused input normalisation (CTA-pair 3x3 kernel): A is the raw GroupNorm input, in_gn_ss = [A_B][A_C] float2
+     * (scale, shift); the kernel convolves silu(A * scale + shift) */
+    const void* in_gn_ss;
 } TmlGemmDesc;
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 /* entries per image of the partial buffer a gn_mode GEMM writes: [B][tiles][32][2] floats */

@@ -26,7 +26,7 @@ from tml_image_editing_defense_b200 import _lib, ops  # noqa
 IMPL = {"simt": False}
 
 
-def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid=False, alpha=1.0, seed=0, gn=0):
+def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid=False, alpha=1.0, seed=0, gn=0, xf=False):
     """conv3x3 in packing mode `mode` (0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity) or mode -1: 1x1."""
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
@@ -39,7 +39,13 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
         w = (torch.randn(co, ci, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(torch.bfloat16).float()
         Wm, dh, dw = pack_conv3x3(w, mode)
         OH, OW = (H // 2, W // 2) if mode == 2 else (H, W)
-    ref = emulate_gemm(A.float(), Wm, dh, dw, stride, OH, OW) * alpha
+    A_ref = A.float()
+    ss_in = None
+    if xf:   # fused input normalisation: the kernel convolves bf16(silu(A * scale + shift)), A = the raw GroupNorm input
+        ss_in = torch.stack([torch.rand(B, Cin, generator=g) + 0.5, torch.randn(B, Cin, generator=g) * 0.5], dim=-1).contiguous()
+        u = A.float() * ss_in[:, None, None, :, 0] + ss_in[:, None, None, :, 1]
+        A_ref = (u * torch.sigmoid(u)).to(torch.bfloat16).float()
+    ref = emulate_gemm(A_ref, Wm, dh, dw, stride, OH, OW) * alpha
     bias_t = torch.randn(N, generator=g) if bias else None
     resid_t = torch.randn(B, OH, OW, N, generator=g).to(torch.bfloat16) if resid else None
     if bias:
@@ -70,6 +76,9 @@ def gemm_case(name, lib, B, H, W, Cin, N, mode, dev, stride=1, bias=False, resid
     d.D = D.data_ptr(); d.out_fp32 = 0
     d.D_sW = N; d.D_sH = OW * N; d.D_sB = OH * OW * N; d.D_sN = 1; d.n_store = 0
     keep = []
+    if xf:
+        keep.append(ss_in.to(dev))
+        d.in_gn_ss = keep[-1].data_ptr()
     if gn and IMPL["simt"]:
         gn = 0   # the SIMT debug kernel has no fused reductions
     if gn:
@@ -192,6 +201,11 @@ def run_gemm_suite(lib, dev):
         ("swap dgrad 128->128 4x256 +gnbwd", dict(B=2, H=4, W=256, Cin=128, N=128, mode=1, gn=2)),
         ("swap 128->512 2x256 +stats", dict(B=1, H=2, W=256, Cin=128, N=512, mode=0, bias=True, gn=1)),
         ("swap dgrad 512->512 1x256 +gnbwd", dict(B=2, H=1, W=256, Cin=512, N=512, mode=1, gn=2)),
+        # CTA pairs with the GroupNorm + SiLU of the input applied on the operand path (raw input, per-image scale / shift)
+        ("swpair xf 256->256 4x128 bias +stats", dict(B=2, H=4, W=128, Cin=256, N=256, mode=0, bias=True, gn=1, xf=True)),
+        ("swpair xf 128->256 6x256 (two segments)", dict(B=2, H=6, W=256, Cin=128, N=256, mode=0, bias=True, xf=True)),
+        ("swpair xf 512->512 2x128 resid", dict(B=1, H=2, W=128, Cin=512, N=512, mode=0, resid=True, xf=True)),
+        ("swpair xf multi-wave 256->512 64x128 B=4 all", dict(B=4, H=64, W=128, Cin=256, N=512, mode=0, bias=True, resid=True, gn=1, xf=True)),
         # the same kernel on CTA pairs (rows of 128 pixels: M = 256 channels, N = 2 rows x 128 pixels)
         ("swpair 256->256 4x128 bias +stats", dict(B=2, H=4, W=128, Cin=256, N=256, mode=0, bias=True, gn=1)),
         ("swpair 512->512 2x128 resid", dict(B=1, H=2, W=128, Cin=512, N=512, mode=0, resid=True)),
@@ -200,7 +214,12 @@ def run_gemm_suite(lib, dev):
         ("swpair multi-wave 256->512 64x128 B=4 all", dict(B=4, H=64, W=128, Cin=256, N=512, mode=0, bias=True, resid=True, gn=1)),
         ("swap multi-wave 128->128 64x256 B=4 all", dict(B=4, H=64, W=256, Cin=128, N=128, mode=0, bias=True, resid=True, gn=1)),
     ]
+    import os
+    no_pairs = any(os.environ.get(k) == v for k, v in (("TML_NO_SWAP", "1"), ("TML_NO_SWAP_PAIR", "1"),
+                                                        ("TML_SWAP_PREFER_PAIR", "0")))
     for name, kw in cases:
+        if kw.get("xf") and (no_pairs or IMPL["simt"]):
+            continue   # the fused input normalisation exists on the CTA-pair form of the swapped kernel only
         try:
             ok &= gemm_case(name, lib, dev=dev, **kw)
         except Exception:

@@ -43,6 +43,7 @@ class TmlGemmDesc(C.Structure):
         ("gn_mode", C.c_int), ("gn_partial", C.c_void_p), ("gn_x", C.c_void_p), ("gn_ss", C.c_void_p),
         ("gn_mr", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_silu", C.c_int),
         ("dbg_shift", C.c_int), ("dbg_bo", C.c_int),
+        ("in_gn_ss", C.c_void_p),
     ]
 
 

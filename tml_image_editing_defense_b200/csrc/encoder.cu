@@ -472,6 +472,7 @@ static int desc_to_op(const TmlGemmDesc* d, GemmOp& o) {
     o.gn_ss = reinterpret_cast<const float2*>(d->gn_ss); o.gn_mr = reinterpret_cast<const float2*>(d->gn_mr);
     o.gn_gamma = d->gn_gamma; o.gn_silu = d->gn_silu;
     o.dbg_shift = d->dbg_shift; o.dbg_bo = d->dbg_bo;
+    o.in_gn_ss = reinterpret_cast<const float2*>(d->in_gn_ss);
     return 0;
 }
 

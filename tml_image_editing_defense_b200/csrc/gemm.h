@@ -59,6 +59,10 @@ struct GemmOp {
     float* row_part = nullptr;
     float exp_scale = 0.f;
     const float* row_scale = nullptr;
+    // Fused input normalisation (operand-swapped CTA-pair kernel only, see gemm_fuses_input_gn): A is the RAW GroupNorm
+    // input and every staged input row is rewritten in shared memory as silu(x * scale + shift) before the MMAs read it;
+    // in_gn_ss = [A_B][A_C] (scale, shift) per image and input channel (gn_finalize's output).
+    const float2* in_gn_ss = nullptr;
     // hardware experiment (tests only): A tile loaded `dbg_shift` pixels early into a (TW+8)-row box and
     // consumed through a row-shifted UMMA descriptor; dbg_bo = 1 also sets the descriptor base_offset field
     int dbg_shift = 0, dbg_bo = 0;
@@ -86,6 +90,10 @@ int gemm_row_partials(const GemmOp& op);
 // true when gemm_launch_tc runs this op on the operand-swapped 3x3 kernel (channels as M, 256 pixels of a row as N),
 // whose fused GroupNorm reductions are cheap enough to use at any K
 bool gemm_swapped_shape(const GemmOp& op);
+
+// true when this op (shape only) runs on the CTA-pair form of the operand-swapped kernel, which can apply the GroupNorm +
+// SiLU of its input on the operand path (GemmOp::in_gn_ss) instead of reading a separately normalised tensor
+bool gemm_fuses_input_gn(const GemmOp& op);
 
 // tcgen05/TMEM/TMA implicit-GEMM kernel (the product path).
 int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream);

@@ -1226,7 +1226,7 @@ template <bool PAIR> struct SwGeo {
     static constexpr int kRowBytes = PAIR ? 17 * 1024 : 33 * 1024;   // kRowPx * 128 B rounded up to the 1 KB swizzle atom
     static constexpr int kRowSlots = PAIR ? 4 : TML_SW_ROWSLOTS;
     static constexpr int kWStages = PAIR ? 8 : TML_SW_WSTAGES;
-    static constexpr int kSmem = 1024 + kRowSlots * kRowBytes + kWStages * (128 * kBlockK * 2) + 256;
+    static constexpr int kSmem = 1024 + kRowSlots * kRowBytes + kWStages * (128 * kBlockK * 2) + 512;
 };
 constexpr int kSwWBytes = 128 * kBlockK * 2;  // 16 KB: 128 output channels x 64 input channels
 static_assert(SwGeo<false>::kSmem <= kMaxSmem && SwGeo<true>::kSmem <= kMaxSmem, "swapped-conv shared memory");
@@ -1247,6 +1247,7 @@ struct SwParams {
     volatile int* hang_where;
     int dbg_no_epi, dbg_mma_only;
     int l2_prefetch;             // row producer pulls the NEXT tile's input rows into L2 while this tile runs
+    const float2* in_ss;         // XF instantiations: [nimg][64 * kchunks] (scale, shift) of the GroupNorm feeding this conv
 };
 
 // The GNB instantiations run 16 epilogue warps (64 pixels each, 8-pixel steps, <= 102 registers) because their
@@ -1299,8 +1300,16 @@ __device__ __forceinline__ SwTile sw_decode(const SwParams& p, int tile, int cra
 
 // NC: output channels = 128 * NC; RES: residual add; GNB: fused GroupNorm-backward reductions (gn_mode 2);
 // PAIR: the cta_group::2 instantiation (launched as clusters of two CTAs; the others contain no cluster instruction).
-template <int NC, bool RES, bool GNB, bool PAIR>
-__global__ void __launch_bounds__(SwCfg<GNB>::kThreadsSw, 1)
+// XF (CTA pairs, forward convolutions): the input is the RAW GroupNorm input; four extra warps rewrite every staged row
+// in shared memory as silu(x * scale + shift) between its TMA arrival and the MMAs that read it, so the normalised
+// activation never exists in HBM.  Budget on pairs: 3 x 130 x 64 elements per 64-channel chunk and CTA against 36 MMAs of
+// 128 clk = 5.4 elements/clk/SM (one tanh.approx + ~5.5 issue slots each).  Correct (kernel suite + the full parity suite
+// pass with it switched on) but slower than the separate pass it replaces: see gemm_fuses_input_gn.  Row slots then fill in two steps: TMA -> the CTA's
+// own `rland` barrier -> transform warps -> one arrival per CTA (the follower's with release.cluster) on the
+// leader's `rfull`, which the MMA warp waits on with acquire.cluster.
+constexpr int kXfThreads = 256;   // eight transform warps: two per SM sub-partition, so that one hides the other's latencies
+template <int NC, bool RES, bool GNB, bool PAIR, bool XF = false>
+__global__ void __launch_bounds__(SwCfg<GNB>::kThreadsSw + (XF ? kXfThreads : 0), 1)
 conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapRow,
                        const __grid_constant__ CUtensorMap mapTail, const SwParams p) {
     using G = SwGeo<PAIR>;
@@ -1315,7 +1324,9 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     uint64_t* rempty = rfull + 4;     // [4]
     uint64_t* tfull = rempty + 4;     // [2]
     uint64_t* tempty = tfull + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rland = tempty + 2;     // [4]  XF: "the raw row has landed in this CTA's slot"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rland + 4);
+    static_assert(!XF || (PAIR && !GNB), "the fused input normalisation exists for forward convolutions on CTA pairs");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -1332,7 +1343,7 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         // without loads).  The accumulator-empty barrier collects both epilogues.
         const uint32_t nprod = PAIR ? 2u : 1u;
         for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < kRowSlots; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 1); }
+        for (int s = 0; s < kRowSlots; ++s) { mbar_init(&rfull[s], XF ? 2 : 1); mbar_init(&rempty[s], 1); mbar_init(&rland[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], nprod * 32 * SwCfg<GNB>::kEpiWarps); }
         fence_mbar_init();
     }
@@ -1411,7 +1422,11 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                         mbar_wait(&rempty[rs], rphase ^ 1u, hw, htag + 2);
                         uint8_t* dst = rows + size_t(rs) * kRowBytes;
                         // rows or pixels outside the image arrive as zeros (= the convolution padding)
-                        if constexpr (PAIR) {
+                        if constexpr (XF) {
+                            // the raw row lands on this CTA's own barrier; the transform warps pass it on to the leader's rfull
+                            mbar_arrive_expect_tx(&rland[rs], uint32_t(G::kRowPx) * 128u);
+                            tma_load_4d(dst, &mapRow, &rland[rs], ch * kBlockK, t.bx0 - 1, t.brow + r - 1, t.img);
+                        } else if constexpr (PAIR) {
                             if ((p.dbg_mma_only == 1 || p.dbg_mma_only == 3) && !first_pass) {
                                 if (crank == 0) mbar_arrive(&rfull[rs]);
                             } else {
@@ -1444,7 +1459,8 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                 const uint32_t d = tmem_base + uint32_t(acc * 256);
                 for (int ch = 0; ch < p.kchunks; ++ch)
                     for (int r = 0; r < 3; ++r) {
-                        mbar_wait(&rfull[rs], rphase, hw, htag + 4);
+                        if constexpr (XF) mbar_wait_cluster(&rfull[rs], rphase, hw, htag + 4);   // rows rewritten by both CTAs' threads
+                        else mbar_wait(&rfull[rs], rphase, hw, htag + 4);
                         tc_fence_after();
                         const uint32_t raddr = smem_u32(rows + size_t(rs) * kRowBytes);
                         for (int c = 0; c < 3; ++c) {
@@ -1482,6 +1498,70 @@ conv3x3_swapped_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
                 __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4 + SwCfg<GNB>::kEpiWarps) {
+        // ===================================================================== input normalisation (XF: 8 warps)
+        if constexpr (XF) {
+            const int tt = int(threadIdx.x) - (128 + 32 * SwCfg<GNB>::kEpiWarps);   // 0 .. kXfThreads-1
+            const int j = tt & 7;            // this thread's 16-byte chunk of a pixel row = channels 8j .. 8j+7 of the chunk
+            const int r0 = tt >> 3;          // its pixels: r0, r0 + 32, ... (five at most of the slot's 130)
+            constexpr int PXI = kXfThreads / 8, NIT = (G::kRowPx + PXI - 1) / PXI;
+            const int C_in = p.kchunks * kBlockK;
+            int rs = 0, nslot = 0;
+            uint32_t rphase = 0;
+            for (int tile = tile0; tile < total_tiles; tile += tstep) {
+                const SwTile t = sw_decode<NC, PAIR>(p, tile, int(crank));
+                for (int ch = 0; ch < p.kchunks; ++ch) {
+                    // silu(u) = u * sigmoid(u) = h + h * tanh(h) with h = u / 2: scale and shift arrive pre-halved
+                    float sc[8], sh[8];
+                    const float2* ssp = p.in_ss + (size_t)t.img * C_in + ch * kBlockK + 8 * j;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 v = __ldg(ssp + e);
+                        sc[e] = 0.5f * v.x; sh[e] = 0.5f * v.y;
+                    }
+                    for (int r = 0; r < 3; ++r) {
+                        mbar_wait(&rland[rs], rphase, hw, htag + 7);
+                        const int yin = t.brow + r - 1;
+                        if (yin >= 0 && yin < p.H) {   // rows outside the image stay the zeros TMA wrote (= the padding)
+                            uint8_t* slot = rows + size_t(rs) * kRowBytes;
+                            uint4 u[NIT];
+                            bool ok[NIT];
+#pragma unroll
+                            for (int i = 0; i < NIT; ++i) {       // all loads first: five independent 16-byte reads in flight
+                                const int px = r0 + i * PXI, xin = t.bx0 - 1 + px;
+                                ok[i] = px < G::kRowPx && xin >= 0 && xin < p.W;   // halo pixels outside the image: padding
+                                if (ok[i]) u[i] = *reinterpret_cast<const uint4*>(slot + size_t(px) * 128 + ((j ^ (px & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int i = 0; i < NIT; ++i) {
+                                if (!ok[i]) continue;
+                                const int px = r0 + i * PXI;
+                                const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+                                uint32_t o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float h0 = fmaf(bf16_lo(w[e]), sc[2 * e], sh[2 * e]);
+                                    const float h1 = fmaf(bf16_hi(w[e]), sc[2 * e + 1], sh[2 * e + 1]);
+                                    o[e] = pack_bf16x2(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+                                }
+                                *reinterpret_cast<uint4*>(slot + size_t(px) * 128 + ((j ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                            }
+                        }
+                        fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's reads
+                        // ONE arrival per CTA and slot, issued by a different warp each time: a release.cluster arrive on
+                        // the peer's barrier stalls its thread for a cross-SM round trip (measured with four remote
+                        // arrivals per slot: 660 instead of 1450 TFLOP/s), so the cost is rotated over the four warps
+                        named_bar_sync(5, kXfThreads);
+                        if (lane == 0 && (tt >> 5) == (nslot & 7)) {
+                            if (crank != 0) mbar_arrive_remote(&rfull[rs], 0);   // release.cluster
+                            else mbar_arrive(&rfull[rs]);
+                        }
+                        ++nslot;
+                        if (++rs == kRowSlots) { rs = 0; rphase ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp >= 4) {
@@ -1719,6 +1799,14 @@ static int swapped_kind(const GemmOp& op) {
     return pair_ok ? 2 : 0;
 }
 bool gemm_swapped_shape(const GemmOp& op) { return swapped_kind(op) != 0; }
+bool gemm_fuses_input_gn(const GemmOp& op) {
+    // OFF by default.  Measured on B200 (tools/gpu_r2_q.sh .. gpu_r2_s.sh): with the transform on the operand path the pair
+    // convolutions run at 1200-1250 TFLOP/s isolated instead of 1630-1690 (eight transform warps: ~2100 warp-instructions
+    // per 130 x 64 slot = a third of the SM's issue slots, one MUFU per element) and the whole step at 372-374 instead of
+    // 386-388 image-PGD-iters/s: the separate apply pass it removes (3.5 ms per 64 images, at the HBM roofline) is cheaper.
+    static const bool on = getenv("TML_FUSE_INGN") && getenv("TML_FUSE_INGN")[0] == '1';   // experiment switch
+    return on && g_impl.load() == 0 && swapped_kind(op) == 2;
+}
 static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
     if (!gemm_swapped_shape(op) || op.gn_mode < 0 || op.gn_mode > 2) return false;
     if (op.gn_mode != 0 && !op.gn_partial) return false;
@@ -1735,6 +1823,11 @@ static bool swap_eligible(const GemmOp& op, int tap_of[3][3]) {
 static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num_sms, cudaStream_t stream) {
     int rc;
     const bool pair = swapped_kind(op) == 2;
+    const bool xf = op.in_gn_ss != nullptr;
+    if (xf && (!pair || op.gn_mode == 2)) {
+        set_error("%s: the fused input normalisation needs the CTA-pair form of a forward convolution", op.name);
+        return -1;
+    }
     CUtensorMap mapW, mapRow, mapTail;
     {
         cuuint64_t dims[3] = {(cuuint64_t)op.ntaps * op.A_C, (cuuint64_t)op.N, 1};
@@ -1761,6 +1854,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
     p.gn_partial = op.gn_partial;
     p.gn_x = reinterpret_cast<const __nv_bfloat16*>(op.gn_x);
     p.gn_ss = op.gn_ss; p.gn_mr = op.gn_mr; p.gn_gamma = op.gn_gamma; p.gn_silu = op.gn_silu;
+    p.in_ss = op.in_gn_ss;
     p.hang_where = hang_word_device();
     { static const int pf = getenv("TML_SW_PREFETCH") ? atoi(getenv("TML_SW_PREFETCH")) : 0; p.l2_prefetch = pf; }   // tuning switch
     { static const int mo = getenv("TML_DBG_MMA_ONLY") ? atoi(getenv("TML_DBG_MMA_ONLY")) : 0; p.dbg_mma_only = mo;   // 1 none, 2 no weights, 3 no rows
@@ -1774,7 +1868,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
         tl.a = take_event(); tl.b = take_event();
         tl.flops = 2.0 * (double)op.A_B * op.OH * op.OW * (double)op.N * (double)op.ntaps * op.A_C;
         snprintf(tl.key, sizeof(tl.key), "%s|%ld|%d|%d|%d", op.name, (long)op.A_B * op.OH * op.OW, op.N,
-                 op.ntaps * op.A_C, (pair ? 3000 : 2000) + op.gn_mode * 10);
+                 op.ntaps * op.A_C, (pair ? 3000 : 2000) + (xf ? 100 : 0) + op.gn_mode * 10);
         cudaEventRecord(tl.a, stream);
     } else if (g_timing) {
         ++g_timing_dropped;
@@ -1787,6 +1881,10 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
         static const SwKernel table[3][2][2] = {SW_ROW(1, false), SW_ROW(2, false), SW_ROW(4, false)};
         static const SwKernel ptable[2][2][2] = {SW_ROW(2, true), SW_ROW(4, true)};
 #undef SW_ROW
+        // [NC 2 / 4][residual]: forward convolutions on CTA pairs with the GroupNorm + SiLU of their input fused in
+        static const SwKernel xtable[2][2] = {
+            {conv3x3_swapped_kernel<2, false, false, true, true>, conv3x3_swapped_kernel<2, true, false, true, true>},
+            {conv3x3_swapped_kernel<4, false, false, true, true>, conv3x3_swapped_kernel<4, true, false, true, true>}};
         bool& attr_set = attr_flag(0);   // cudaFuncSetAttribute is per device
         if (!attr_set) {
             for (int b = 0; b < 2; ++b)
@@ -1796,11 +1894,13 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
                         e = cudaFuncSetAttribute(table[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SwGeo<false>::kSmem);
                     for (int a = 0; a < 2 && e == cudaSuccess; ++a)
                         e = cudaFuncSetAttribute(ptable[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SwGeo<true>::kSmem);
+                    for (int a = 0; a < 2 && e == cudaSuccess && c == 0; ++a)
+                        e = cudaFuncSetAttribute(xtable[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, SwGeo<true>::kSmem);
                     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
                 }
             attr_set = true;
         }
-        const int threads = op.gn_mode == 2 ? SwCfg<true>::kThreadsSw : SwCfg<false>::kThreadsSw;
+        const int threads = (op.gn_mode == 2 ? SwCfg<true>::kThreadsSw : SwCfg<false>::kThreadsSw) + (xf ? kXfThreads : 0);
         const int ri = op.resid ? 1 : 0, gi = op.gn_mode == 2 ? 1 : 0;
         if (pair) {
             cudaLaunchConfig_t cfg;
@@ -1814,7 +1914,7 @@ static int gemm_launch_swapped(const GemmOp& op, const int tap_of[3][3], int num
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            cudaError_t le = cudaLaunchKernelEx(&cfg, ptable[nc == 2 ? 0 : 1][ri][gi], mapW, mapRow, mapTail, p);
+            cudaError_t le = cudaLaunchKernelEx(&cfg, xf ? xtable[nc == 2 ? 0 : 1][ri] : ptable[nc == 2 ? 0 : 1][ri][gi], mapW, mapRow, mapTail, p);
             if (le != cudaSuccess) { set_error("%s: cluster launch failed: %s", op.name, cudaGetErrorString(le)); return -5; }
         } else {
             table[nc == 1 ? 0 : nc == 2 ? 1 : 2][ri][gi]<<<grid, threads, SwGeo<false>::kSmem, stream>>>(mapW, mapRow, mapTail, p);
@@ -1831,6 +1931,10 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     {
         int tap_of[3][3];
         if (swap_eligible(op, tap_of)) return gemm_launch_swapped(op, tap_of, num_sms, stream);
+    }
+    if (op.in_gn_ss != nullptr) {
+        set_error("%s: in_gn_ss is only implemented by the CTA-pair operand-swapped kernel (see gemm_fuses_input_gn)", op.name);
+        return -1;
     }
     GemmTiling t;
     int rc = gemm_plan(op, &t);

@@ -82,6 +82,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
 #endif
 }
 
+// The same bounded wait with acquire semantics at cluster scope: the waiter consumes shared-memory data that threads of
+// the PEER CTA wrote before they arrived on this barrier with release.cluster (mbar_arrive_remote).
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* where = nullptr, int tag = 0) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+#if TML_WAIT_TIMEOUT_NS == 0
+    (void)where; (void)tag;
+    while (!mbar_try_wait_cluster(bar, parity)) {}
+#else
+    const uint64_t t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if ((++spins & 1023u) != 0) continue;
+        if (global_timer_ns() - t0 > TML_WAIT_TIMEOUT_NS) {
+            if (where) { *where = tag; __threadfence_system(); }
+            __trap();
+        }
+    }
+#endif
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------- clusters (CTA pairs)

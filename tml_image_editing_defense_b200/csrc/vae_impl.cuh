@@ -495,7 +495,8 @@ static int gn_forward(Run& r, const bf16* x, const Norm& n, const GnSaved& g, bf
     }
     launch_gn_finalize(part, n.gamma, n.beta, r.S<float2>(g.ss), r.S<float2>(g.mr), r.B, hw, n.C, r.e->cfg.norm_eps,
                        nchunks, r.st);
-    launch_gn_apply(x, r.S<float2>(g.ss), y, r.B, hw, n.C, silu, r.st);
+    // y == nullptr: statistics only -- the consumer applies scale / shift / SiLU on its operand path (GemmOp::in_gn_ss)
+    if (y != nullptr) launch_gn_apply(x, r.S<float2>(g.ss), y, r.B, hw, n.C, silu, r.st);
     r.wsa.reset(m);
     return 0;
 }
@@ -559,21 +560,37 @@ static int resnet_forward(Run& r, const Resnet& p, const ResnetRec& rec) {
     const int ns = r.e->num_sms;
     const bf16* x = r.S<bf16>(rec.x);
     const size_t m = r.wsa.mark();
-    bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
-    RC(gn_forward(r, x, p.n1, rec.g1, a, hw, 1, r.pending));
     bf16* h1 = r.S<bf16>(rec.h1);
-    GemmOp c1 = dense_conv_op("resnet.conv1", a, B, h, w, p.ci, p.c1.fwd, p.co, 1, h, w, p.c1.bias, nullptr, h1);
+    // Where the convolution runs on the CTA-pair form of the operand-swapped kernel (the 256^2 and 128^2 stages), the
+    // GroupNorm + SiLU of its input CAN be applied on the operand path (the normalised activation is then never written);
+    // measured slower than the separate apply pass, so gemm_fuses_input_gn is off unless TML_FUSE_INGN=1.
+    GemmOp c1 = dense_conv_op("resnet.conv1", x, B, h, w, p.ci, p.c1.fwd, p.co, 1, h, w, p.c1.bias, nullptr, h1);
+    if (gemm_fuses_input_gn(c1)) {
+        RC(gn_forward(r, x, p.n1, rec.g1, nullptr, hw, 1, r.pending));
+        c1.in_gn_ss = r.S<float2>(rec.g1.ss);
+    } else {
+        bf16* a = r.Walloc<bf16>(act_bytes(B, h, w, p.ci));
+        RC(gn_forward(r, x, p.n1, rec.g1, a, hw, 1, r.pending));
+        c1.A = a;
+    }
     const Partials s1 = fuse_stats(c1, r.statbuf[0], h, w);     // statistics of h1 for norm2, from the epilogue
     RC(gemm_launch(c1, ns, r.st));
-    bf16* a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
-    RC(gn_forward(r, h1, p.n2, rec.g2, a2, hw, 1, s1));
     const bf16* resid = x;
-    if (p.has_sc) {
-        bf16* sc = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
-        RC(gemm_launch(dense_lin_op("resnet.shortcut", x, B, h, w, p.ci, p.sc.fwd, p.co, p.sc.bias, nullptr, sc), ns, r.st));
-        resid = sc;
+    bf16* sc = nullptr;
+    if (p.has_sc) sc = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+    GemmOp c2 = dense_conv_op("resnet.conv2", h1, B, h, w, p.co, p.c2.fwd, p.co, 1, h, w, p.c2.bias, resid, r.S<bf16>(rec.out));
+    if (gemm_fuses_input_gn(c2)) {
+        RC(gn_forward(r, h1, p.n2, rec.g2, nullptr, hw, 1, s1));
+        c2.in_gn_ss = r.S<float2>(rec.g2.ss);
+    } else {
+        bf16* a2 = r.Walloc<bf16>(act_bytes(B, h, w, p.co));
+        RC(gn_forward(r, h1, p.n2, rec.g2, a2, hw, 1, s1));
+        c2.A = a2;
     }
-    GemmOp c2 = dense_conv_op("resnet.conv2", a2, B, h, w, p.co, p.c2.fwd, p.co, 1, h, w, p.c2.bias, resid, r.S<bf16>(rec.out));
+    if (p.has_sc) {
+        RC(gemm_launch(dense_lin_op("resnet.shortcut", x, B, h, w, p.ci, p.sc.fwd, p.co, p.sc.bias, nullptr, sc), ns, r.st));
+        c2.resid = sc;
+    }
     r.pending = fuse_stats(c2, r.statbuf[1], h, w);             // statistics of the block output for the next norm
     RC(gemm_launch(c2, ns, r.st));
     r.wsa.reset(m);

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--k1", action="store_true", help="1x1 convolution instead of 3x3")
     ap.add_argument("--resid", action="store_true")
     ap.add_argument("--bias", action="store_true")
+    ap.add_argument("--xf", action="store_true", help="fused input GroupNorm + SiLU (CTA-pair 3x3 kernel): A is the raw input")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -47,6 +48,9 @@ def main():
         keep.append(torch.randn(B, H, W, N, device=dev).to(torch.bfloat16)); d.resid = keep[-1].data_ptr()
     d.R_sW = N; d.R_sH = W * N; d.R_sB = H * W * N
     d.D = D.data_ptr(); d.D_sW = N; d.D_sH = W * N; d.D_sB = H * W * N; d.D_sN = 1
+    if a.xf:
+        keep.append(torch.stack([torch.rand(B, Cin, device=dev) + 0.5, torch.randn(B, Cin, device=dev) * 0.5], dim=-1).contiguous())
+        d.in_gn_ss = keep[-1].data_ptr()
     if a.gn:
         d.gn_mode = a.gn
         if a.gn == 2:
