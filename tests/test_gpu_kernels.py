@@ -214,3 +214,18 @@ def test_tcgen05_gemm_suite_fallback_paths(dev):
     """The same suite with the fast paths switched off (no operand-swapped kernel, no CTA pairs, register epilogue
     instead of TMA stores): the A/B switches documented in DESIGN.md must stay correct."""
     _run_gemm_suite({"TML_NO_SWAP": "1", "TML_PAIR": "0", "TML_NO_TMA_STORE": "1"})
+
+
+def test_encoder_walk_with_fused_input_groupnorm(dev):
+    """TML_FUSE_INGN=1 (off by default): the CTA-pair 3x3 convolutions take the RAW GroupNorm input and
+    apply scale / shift / SiLU on their operand path.  The layer-by-layer comparison with the oracle (every saved
+    activation, every backward stage) at 256^2 -- where the 128^2 stage runs on pairs -- must hold with it switched on."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "tests" / "gpu_check.py"), "--skip-gemm", "--impl", "tc", "--res", "256",
+                        "--batch", "2"], env=dict(os.environ, TML_FUSE_INGN="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL OK" in r.stdout
