@@ -487,3 +487,27 @@ def test_attention_with_peaked_softmax_vs_oracle(dev):
     # the point of this test is the absence of overflow / empty rows / NaN far from the random-init regime
     assert cosine(gg, g_ref) >= 0.98
     torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
+
+
+@pytest.mark.parametrize("hw", [(384, 384), (256, 512), (320, 448)])
+def test_other_resolutions_take_the_general_paths(dev, models, hw):
+    """Sizes that are not powers of two fall off the fast geometries stage by stage (rows of 384 / 192 / 96 / 48 pixels:
+    halo mode, tap-by-tap tiles of 96 and 48 pixels, register epilogue where a warp's rows are not whole tile rows) --
+    the gradient must still match the fp32 oracle."""
+    from oracle.encoder_oracle import encoder_attack_grad
+    oracle, vae = models
+    H, W = hw
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = (torch.rand((2, 3, H, W), generator=g) * 2 - 1).to(dev)
+    t = torch.randn((2, 4, H // 8, W // 8), generator=g).to(dev)
+    n = torch.randn((2, 4, H // 8, W // 8), generator=g).to(dev)
+    od = oracle.to(dev)
+    g_ref, l_ref, _ = encoder_attack_grad(od, x, t, n, 0)
+    oracle.to("cpu")
+    torch.cuda.empty_cache()
+    gg, l, _ = vae.attack_grad(x, t, n, 0)
+    assert torch.isfinite(gg).all()
+    assert cosine(gg, g_ref) >= 0.999
+    torch.testing.assert_close(l, l_ref, rtol=2e-2, atol=0)
+    g1, l1, _ = vae.attack_grad(x[1:2].contiguous(), t[1:2].contiguous(), n[1:2].contiguous(), 0)
+    assert torch.equal(g1[0], gg[1]) and torch.equal(l1[0], l[1])       # batch-composition invariance holds here too

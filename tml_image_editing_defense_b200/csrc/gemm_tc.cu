@@ -169,7 +169,12 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     if (op.N % 256 == 0) BN = 256;
     else if (op.N % 128 == 0) BN = 128;
     else if (op.N <= 256) BN = op.N;
-    else { set_error("%s: N=%d unsupported (need N%%128==0 or N<=256)", op.name, op.N); return -1; }
+    else {
+        // any other width (e.g. 2240 attention tokens of a 320 x 448 image): the largest column tile that divides N
+        for (int d = 256; d >= 32 && BN == 0; d -= 32) if (op.N % d == 0) BN = d;
+        for (int d = 240; d >= 16 && BN == 0; d -= 16) if (op.N % d == 0) BN = d;
+        if (BN == 0) { set_error("%s: N=%d has no column tile (a multiple of 16, at most 256)", op.name, op.N); return -1; }
+    }
     if (op.resid && BN < 32) { set_error("%s: residual needs N >= 32", op.name); return -1; }
     if (op.gn_mode != 0) {
         const int cpg = op.N / 32;

@@ -630,6 +630,15 @@ static int resnet_backward(Run& r, const Resnet& p, const ResnetRec& rec, const 
 //   PV      rows scaled by 1 / sum in the epilogue               (row_scale)
 // The second QK^T costs 2*tok^2*C flops per image (0.7 % of the step at 512^2) and replaces a 4-byte-per-logit write,
 // the softmax kernel's 4-byte read and its 2-byte write.
+// The attention products see tokens, not pixels: they are tiled over a virtual [tok / gw][gw] grid (gw = 128 or 64) so that
+// every tile is 128 consecutive tokens and every epilogue warp owns 32 of them, whatever the latent's height and width.
+static int attn_grid(int tok, int* gh, int* gw) {
+    if (tok % 64 != 0) { set_error("attention needs (H/8)*(W/8) %% 64 == 0 tokens, got %d", tok); return -31; }
+    *gw = tok % 128 == 0 ? 128 : 64;
+    *gh = tok / *gw;
+    return 0;
+}
+
 static GemmOp attn_logits_op(const char* name, const bf16* A, const bf16* Bk, int B, int h, int w, int C, int ldA, int ldB) {
     const int tok = h * w;
     GemmOp o;   // D[tok, tok'] = A[tok, C] * Bk[tok', C]^T, both operands rows of a [B][tok][ld] tensor
@@ -655,8 +664,10 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
     RC(gemm_launch(dense_lin_op("attn.qkv", t, B, h, w, C, p.qkv.fwd, 3 * C, p.qkv.bias, nullptr, qkv), ns, r.st));
     bf16* P = r.S<bf16>(rec.P);
     float* inv_l = r.S<float>(rec.inv_l);
+    int gh = 0, gw = 0;
+    RC(attn_grid(tok, &gh, &gw));
     {
-        GemmOp o = attn_logits_op("attn.qk.max", qkv, qkv + C, B, h, w, C, 3 * C, 3 * C);
+        GemmOp o = attn_logits_op("attn.qk.max", qkv, qkv + C, B, gh, gw, C, 3 * C, 3 * C);
         o.epi_mode = 1;
         const int np = gemm_row_partials(o);
         if (np < 0) return np;
@@ -665,7 +676,7 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
         o.row_part = part;
         RC(gemm_launch(o, ns, r.st));
         launch_row_reduce(part, rmax, rows, np, 0, r.st);
-        GemmOp e = attn_logits_op("attn.qk.exp", qkv, qkv + C, B, h, w, C, 3 * C, 3 * C);
+        GemmOp e = attn_logits_op("attn.qk.exp", qkv, qkv + C, B, gh, gw, C, 3 * C, 3 * C);
         e.epi_mode = 2;
         e.row_a = rmax; e.row_part = part;
         e.exp_scale = scale * 1.4426950408889634f;   // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
@@ -679,12 +690,12 @@ static int attn_forward(Run& r, const Attn& p, const AttnRec& rec) {
     {
         GemmOp o;
         o.name = "attn.pv";
-        o.A = P; o.A_C = tok; o.A_W = w; o.A_H = h; o.A_B = B;
-        o.A_sW = tok; o.A_sH = (int64_t)w * tok; o.A_sB = (int64_t)tok * tok;
-        o.OW = w; o.OH = h;
+        o.A = P; o.A_C = tok; o.A_W = gw; o.A_H = gh; o.A_B = B;
+        o.A_sW = tok; o.A_sH = (int64_t)gw * tok; o.A_sB = (int64_t)tok * tok;
+        o.OW = gw; o.OH = gh;
         o.Bm = Vt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
         o.row_scale = inv_l;
-        o.D = a; o.D_sW = C; o.D_sH = (int64_t)w * C; o.D_sB = (int64_t)tok * C; o.D_sN = 1;
+        o.D = a; o.D_sW = C; o.D_sH = (int64_t)gw * C; o.D_sB = (int64_t)tok * C; o.D_sN = 1;
         RC(gemm_launch(o, ns, r.st));
     }
     GemmOp oo = dense_lin_op("attn.out", a, B, h, w, C, p.out.fwd, C, p.out.bias, x, r.S<bf16>(rec.out));
@@ -714,13 +725,15 @@ static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* 
     launch_row_dot(da, r.S<bf16>(rec.a), Drow, rows, C, r.st);
     bf16* daT = r.Walloc<bf16>(act);   // (da / l)^T
     launch_transpose(da, daT, B, tok, C, C, (long long)tok * C, tok, (long long)C * tok, r.st, inv_l);
+    int gh = 0, gw = 0;
+    RC(attn_grid(tok, &gh, &gw));
     bf16* dS = r.Walloc<bf16>(tt * 2);
     {
-        GemmOp o = attn_logits_op("attn.dS", da, qkv + 2 * C, B, h, w, C, C, 3 * C);   // dP = da V^T
+        GemmOp o = attn_logits_op("attn.dS", da, qkv + 2 * C, B, gh, gw, C, C, 3 * C);   // dP = da V^T
         o.epi_mode = 3;
         o.alpha = scale;
         o.row_a = Drow; o.row_b = inv_l;
-        o.resid = P; o.R_sW = tok; o.R_sH = (int64_t)w * tok; o.R_sB = (int64_t)tok * tok;
+        o.resid = P; o.R_sW = tok; o.R_sH = (int64_t)gw * tok; o.R_sB = (int64_t)tok * tok;
         o.D = dS;
         RC(gemm_launch(o, ns, r.st));
     }
@@ -736,11 +749,11 @@ static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* 
     auto tok_gemm = [&](const char* name, const bf16* A, const bf16* Bt, bf16* D) {
         GemmOp o;  // D[tok, C] (row stride 3C) = A[tok, tok'] * Bt[C, tok']^T
         o.name = name;
-        o.A = A; o.A_C = tok; o.A_W = w; o.A_H = h; o.A_B = B;
-        o.A_sW = tok; o.A_sH = (int64_t)w * tok; o.A_sB = (int64_t)tok * tok;
-        o.OW = w; o.OH = h;
+        o.A = A; o.A_C = tok; o.A_W = gw; o.A_H = gh; o.A_B = B;
+        o.A_sW = tok; o.A_sH = (int64_t)gw * tok; o.A_sB = (int64_t)tok * tok;
+        o.OW = gw; o.OH = gh;
         o.Bm = Bt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
-        o.D = D; o.D_sW = 3 * C; o.D_sH = (int64_t)w * 3 * C; o.D_sB = (int64_t)tok * 3 * C; o.D_sN = 1;
+        o.D = D; o.D_sW = 3 * C; o.D_sH = (int64_t)gw * 3 * C; o.D_sB = (int64_t)tok * 3 * C; o.D_sN = 1;
         return gemm_launch(o, ns, r.st);
     };
     RC(tok_gemm("attn.dQ", dS, Kt, dqkv));
