@@ -321,7 +321,7 @@ def run_ours(args):
     # Every byte is copied every step; only the order is pipelined.
     # The iterate ping-pongs between two pinned host buffers (the result of step i is the input of
     # step i+1); the step-invariant inputs (source, target, noise) are uploaded on a side stream while
-    # the previous step computes.
+    # the previous step computes, and within a step the iterate moves micro-batch by micro-batch.
     xa_bufs = [xh.clone().pin_memory(), torch.empty_like(xh).pin_memory()]
     loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
     h2d = xh.numel() * 4 + xh.numel() * 4 + th.numel() * 4 + nh.numel() * 4
@@ -338,19 +338,41 @@ def run_ours(args):
             ev.record(copy_stream)
         return x_d, t_d, n_d, ev
 
+    d2h_stream = torch.cuda.Stream(device=dev)
+    chunks = [(s_, min(B, s_ + mb)) for s_ in range(0, B, mb)]
+
     def step_e2e():
+        """Images are independent, so the step is pipelined per micro-batch: the iterate of micro-batch m+1 is uploaded
+        while m computes, the result of m is downloaded while m+1 computes.  Every byte still moves every step."""
         main = torch.cuda.current_stream()
         x_d, t_d, n_d, ev = state["pre"] if state["pre"] is not None else upload_invariants()
-        xa_d = xa_bufs[state["cur"]].to(dev, non_blocking=True)
+        src, dst = xa_bufs[state["cur"]], xa_bufs[state["cur"] ^ 1]
+        parts = []
+        with torch.cuda.stream(copy_stream):            # the iterate first, micro-batch by micro-batch ...
+            for s_, e_ in chunks:
+                xa_m = src[s_:e_].to(dev, non_blocking=True)
+                ev_m = torch.cuda.Event()
+                ev_m.record(copy_stream)
+                parts.append((xa_m, ev_m))
         main.wait_event(ev)
-        state["pre"] = upload_invariants()          # next step's uploads overlap this step's kernels
-        g_d, _, _, ld = tr.compute_grad(xa_d, None, x_d, None, t_d, [n_d])
-        xa_d = tr.perturbation_step(xa_d, g_d, x_d, None)
-        xa_bufs[state["cur"] ^ 1].copy_(xa_d, non_blocking=True)
-        loss_host.copy_(ld["per_image"], non_blocking=True)
+        state["pre"] = upload_invariants()              # ... then the next step's invariants, under this step's kernels
+        for (s_, e_), (xa_m, ev_m) in zip(chunks, parts):
+            main.wait_event(ev_m)
+            xa_m.record_stream(main)
+            g_m, _, _, ld = tr.compute_grad(xa_m, None, x_d[s_:e_], None, t_d[s_:e_], [n_d[s_:e_]])
+            xa_m = tr.perturbation_step(xa_m, g_m, x_d[s_:e_], None)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                dst[s_:e_].copy_(xa_m, non_blocking=True)
+                loss_host[s_:e_].copy_(ld["per_image"], non_blocking=True)
+            xa_m.record_stream(d2h_stream)
+            ld["per_image"].record_stream(d2h_stream)
         for t_ in (x_d, t_d, n_d):
             t_.record_stream(main)
-        main.synchronize()                          # the caller owns the result after this
+        d2h_stream.synchronize()                        # the caller owns the result after this
+        main.synchronize()
         state["cur"] ^= 1
 
     for _ in range(2):
