@@ -117,6 +117,43 @@ int tml_universal_step(float* delta, const float* grad, const float* source, flo
  * passes the per-pixel (min, max) images of the whole dataset so every replica applies the same bounds. */
 int tml_universal_project(float* delta, const float* sources, int nsrc, float lo, float hi, int64_t n, void* stream);
 
+/* ---- UNet: replaces self.pipeline.unet(latent_model_input, t, encoder_hidden_states=prompt_embeds).sample
+ *      (main.py:233-238; diffusers UNet2DConditionModel, SD-1.5 topology) and its backward w.r.t. the sample
+ *      (torch.autograd.grad(loss, [cur_image]) through the denoising loop, main.py:176,229-243). ---- */
+typedef struct TmlUnet TmlUnet;
+typedef struct TmlUnetCfg {
+    int in_channels;            /* 4 */
+    int out_channels;           /* 4 */
+    int num_blocks;             /* 4 */
+    int block_out_channels[8];  /* 320,640,1280,1280 (multiples of 64) */
+    int layers_per_block;       /* 2 */
+    int cross_attention_dim;    /* 768 */
+    int num_heads;              /* 8 (diffusers' `attention_head_dim` of SD-1.5 is the head COUNT) */
+    int norm_num_groups;        /* 32 */
+    int down_has_attn[8];       /* 1,1,1,0 */
+    int up_has_attn[8];         /* 0,1,1,1 */
+} TmlUnetCfg;
+int tml_unet_create(const TmlUnetCfg* cfg, int device, TmlUnet** out);
+void tml_unet_destroy(TmlUnet* unet);
+/* diffusers state-dict keys ("conv_in.weight", "down_blocks.0.resnets.0.norm1.weight", ...), host or device memory */
+int tml_unet_set_weight(TmlUnet* unet, const char* diffusers_key, const void* ptr, int dtype, const int64_t* shape, int ndim);
+int tml_unet_finalize(TmlUnet* unet, void* stream);
+/* scratch / forward->backward state for a [B,4,h,w] sample with ctx_tokens prompt tokens (dry run of both walks) */
+int tml_unet_query(TmlUnet* unet, int B, int h, int w, int ctx_tokens, size_t* workspace_bytes, size_t* saved_bytes);
+/* sample fp32 NCHW [B,4,h,w]; one scalar timestep for the batch (main.py:233); ctx fp32 [B,ctx_tokens,cross_attention_dim]
+ * -> out fp32 NCHW [B,4,h,w] (the predicted noise). */
+int tml_unet_forward(TmlUnet* unet, const float* sample_nchw, float timestep, const float* ctx, int B, int h, int w,
+                     int ctx_tokens, float* out_nchw, void* saved, void* ws, void* stream);
+/* dout fp32 NCHW -> dsample fp32 NCHW; `saved` from the forward of the same inputs */
+int tml_unet_backward(TmlUnet* unet, const float* dout_nchw, int B, int h, int w, int ctx_tokens, const void* saved,
+                      float* dsample_nchw, void* ws, void* stream);
+/* saved bf16 NHWC activations: "conv_in", "resnet_h1"/"resnet_out", "tf_t0"/"tf_x1"/"tf_x2"/"tf_out" (transformer index),
+ * "down_out", "up_out"; "count_resnets"/"count_tf" return the count in *offset */
+int tml_debug_unet_saved_tensor(TmlUnet* unet, const char* name, int index, size_t* offset, int dims[4]);
+/* Tests on a machine without a GPU: while on, tml_unet_create skips the device checks and finalize uploads nothing, so
+ * tml_unet_query still replays both walks as a dry run (layout, scratch size, shape validation of every GEMM). */
+void tml_debug_set_host_only(int on);
+
 /* ---- introspection / test hooks ---- */
 /* number of kernels launched by this library since load: [0] tcgen05 GEMMs, [1] all other kernels */
 void tml_launch_counts(int64_t out[2]);
@@ -159,7 +196,7 @@ int tml_debug_decoder_saved_tensor(TmlEncoder* vae, const char* name, int index,
 /* Every backward stage copies its output gradient (bf16 NHWC) into slot k of dev_buffer (NULL = off). */
 void tml_debug_set_grad_dump(void* dev_buffer, size_t slot_bytes, int slots);
 /* Host-only helpers (no CUDA calls) used by the CPU tests of the weight packing. */
-int tml_debug_pack_conv3x3(const float* w /*[Co][Ci][3][3]*/, int Co, int Ci, int mode /*0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity (ph,pw)=(0,0),(0,1),(1,0),(1,1)*/,
+int tml_debug_pack_conv3x3(const float* w /*[Co][Ci][3][3]*/, int Co, int Ci, int mode /*0 fwd s1, 1 dgrad s1, 2 fwd s2, 3..6 dgrad s2 parity (ph,pw)=(0,0),(0,1),(1,0),(1,1) for pad (0,1,0,1); 7 fwd s2 pad 1, 8..11 its parity dgrads*/,
                            uint16_t* out_bf16, int* ntaps, int* dh, int* dw);
 
 #ifdef __cplusplus

@@ -29,6 +29,15 @@ class TmlEncoderCfg(C.Structure):
     ]
 
 
+class TmlUnetCfg(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int), ("out_channels", C.c_int), ("num_blocks", C.c_int),
+        ("block_out_channels", C.c_int * 8), ("layers_per_block", C.c_int), ("cross_attention_dim", C.c_int),
+        ("num_heads", C.c_int), ("norm_num_groups", C.c_int), ("down_has_attn", C.c_int * 8),
+        ("up_has_attn", C.c_int * 8),
+    ]
+
+
 class TmlGemmDesc(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("A_C", C.c_int), ("A_W", C.c_int), ("A_H", C.c_int), ("A_B", C.c_int),
@@ -85,6 +94,19 @@ SIGNATURES = {
     "tml_universal_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_int64, C.c_void_p, C.c_void_p]),
     "tml_universal_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
+    "tml_unet_create": (C.c_int, [C.POINTER(TmlUnetCfg), C.c_int, C.POINTER(C.c_void_p)]),
+    "tml_unet_destroy": (None, [C.c_void_p]),
+    "tml_unet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "tml_unet_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tml_unet_query": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_size_t)]),
+    "tml_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tml_unet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "tml_debug_unet_saved_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t),
+                                              C.POINTER(C.c_int)]),
+    "tml_debug_set_host_only": (None, [C.c_int]),
     "tml_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "tml_gemm_timing_enable": (None, [C.c_int]),
     "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),

@@ -16,6 +16,7 @@ thread_local bool g_dry_run = false;
 static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(); }
 #define COUNT_LAUNCH() g_launches.fetch_add(1)
+void count_launch() { g_launches.fetch_add(1); }
 
 constexpr int kNumSMs = 148;
 

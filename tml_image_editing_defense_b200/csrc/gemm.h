@@ -8,6 +8,7 @@ namespace tml {
 
 constexpr int kMaxTaps = 9;
 extern thread_local bool g_dry_run;   // see kernels.h: launchers return without launching
+extern thread_local bool g_dry_validate;   // with g_dry_run: gemm_launch still plans the op and reports shape errors
 
 // D[b, oh, ow, n] = alpha * sum_t sum_c A[b, oh*stride + dh[t], ow*stride + dw[t], c] * Bm[batch][n][t*A_C + c]
 //                   + bias[n] + resid[b, oh, ow, n]

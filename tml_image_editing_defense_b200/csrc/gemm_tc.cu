@@ -2088,8 +2088,12 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     return 0;
 }
 
+thread_local bool g_dry_validate = false;   // dry runs also plan every GEMM (shape validation without a GPU)
 int gemm_launch(const GemmOp& op, int num_sms, cudaStream_t stream) {
-    if (g_dry_run) return 0;
+    if (g_dry_run) {
+        if (g_dry_validate) { GemmTiling t; return gemm_plan(op, &t); }
+        return 0;
+    }
     if (g_impl.load() == 1) return gemm_launch_simt(op, stream);
     return gemm_launch_tc(op, num_sms, stream);
 }

@@ -83,6 +83,37 @@ void launch_posterior_sample(const float* moments, const float* noise, float* z,
 void launch_posterior_sample_bwd(const float* moments, const float* noise, const float* dz, float* dmoments, int B,
                                  int hw, cudaStream_t s);
 
+// ---- UNet helpers (unet_kernels.cu; diffusion attack, main.py:229-243) ----
+// GroupNorm(32 groups) for any channel count with C % 32 == 0 and C % 8 == 0 (partials / finalize as above)
+void launch_gng_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s);
+void launch_gng_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s);
+void launch_gng_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,
+                            float* partial, int B, int HW, int C, int silu, cudaStream_t s);
+void launch_gng_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float2* mm,
+                          const bf16* resid, bf16* dx, int B, int HW, int C, int silu, cudaStream_t s);
+// LayerNorm over C of [rows][C] (C <= 2048); stats[row] = (mean, rstd)
+void launch_ln_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, long long rows, int C,
+                   float eps, cudaStream_t s);
+void launch_ln_bwd(const bf16* x, const bf16* dy, const float* gamma, const float2* stats, const bf16* resid, bf16* dx,
+                   long long rows, int C, cudaStream_t s);
+// GEGLU: h [rows][2I] = [x | gate] -> out [rows][I] = x * gelu(gate); backward dh [rows][2I]
+void launch_geglu_fwd(const bf16* h, bf16* out, long long rows, int I, cudaStream_t s);
+void launch_geglu_bwd(const bf16* h, const bf16* dout, bf16* dh, long long rows, int I, cudaStream_t s);
+// [B][tok_src][ld_in] columns col0 + h*d .. -> [(B*heads)][tok_out][dpad] (zero padded; fill 1: query slot d = 1,
+// fill 2: key slot d = -29952 on rows >= tok_valid), and the inverse
+void launch_head_split(const bf16* in, long long ld_in, long long bs_in, int col0, bf16* out, int B, int heads,
+                       int tok_src, int tok_valid, int tok_out, int d, int dpad, int fill, cudaStream_t s);
+void launch_head_merge(const bf16* in, bf16* out, long long ld_out, long long bs_out, int col0, int B, int heads,
+                       int tok, int d, int dpad, cudaStream_t s);
+void launch_copy_cols(const bf16* in, long long ld_in, int ic0, bf16* out, long long ld_out, int oc0, int ncols,
+                      long long rows, cudaStream_t s);
+void launch_add_bf16(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t s);
+void launch_timestep_embed(float t, float* out, int dim, cudaStream_t s);
+void launch_small_linear(const float* x, const float* W, const float* bias, float* y, int N, int K, int silu_in,
+                         cudaStream_t s);
+void launch_nchw_pack64(const float* x, bf16* out, int B, int C, int hw, cudaStream_t s);
+void launch_nhwc64_unpack(const bf16* in, float* out, int B, int C, int hw, cudaStream_t s);
+
 long kernel_launch_count();
 
 }  // namespace tml

@@ -111,19 +111,28 @@ static int pack_conv3x3(const float* w, int Co, int Ci, int mode, std::vector<ui
             }
         return 0;
     }
-    if (mode >= 3 && mode <= 6) {
-        const int ph = (mode - 3) >> 1, pw = (mode - 3) & 1;
+    // mode 7: forward s2, symmetric pad 1 (the UNet's Downsample2D): same matrix as mode 0, (dh,dw) = (r-1, s-1)
+    // mode 8..11: its dgrad per output parity (ph,pw): input row i = 2o + r - 1, so r = ph + 1 (mod 2) and
+    //             dY row o = i' + (ph + 1 - r)/2 for i = 2i' + ph
+    if (mode == 7) {
+        const int rc = pack_conv3x3(w, Co, Ci, 0, out, ntaps, dh, dw);
+        return rc;
+    }
+    if ((mode >= 3 && mode <= 6) || (mode >= 8 && mode <= 11)) {
+        const int pad = mode >= 8 ? 1 : 0;
+        const int q = mode >= 8 ? mode - 8 : mode - 3;
+        const int ph = q >> 1, pw = q & 1;
         int rs[2], ss[2], nr = 0, ns = 0;
-        for (int r = 0; r < 3; ++r) if ((r & 1) == ph) rs[nr++] = r;
-        for (int s = 0; s < 3; ++s) if ((s & 1) == pw) ss[ns++] = s;
+        for (int r = 0; r < 3; ++r) if ((r & 1) == ((ph + pad) & 1)) rs[nr++] = r;
+        for (int s = 0; s < 3; ++s) if ((s & 1) == ((pw + pad) & 1)) ss[ns++] = s;
         *ntaps = nr * ns;
         out.assign((size_t)Ci * (*ntaps) * Co, 0);
         int t = 0;
         for (int a = 0; a < nr; ++a)
             for (int b = 0; b < ns; ++b, ++t) {
                 const int r = rs[a], s = ss[b];
-                dh[t] = (ph - r) / 2;  // 0 or -1
-                dw[t] = (pw - s) / 2;
+                dh[t] = (ph + pad - r) / 2;  // pad 0: 0 or -1; pad 1: 0 or +1 (exact divisions)
+                dw[t] = (pw + pad - s) / 2;
                 for (int ci = 0; ci < Ci; ++ci)
                     for (int co = 0; co < Co; ++co)
                         out[(size_t)ci * (*ntaps) * Co + (size_t)t * Co + co] = f2bf(W(co, ci, r, s));
@@ -252,8 +261,12 @@ struct TmlEncoder {
 // ------------------------------------------------------------------------------------------------
 // weight upload
 // ------------------------------------------------------------------------------------------------
+// tests without a GPU (tml_debug_set_host_only): parameters keep their shapes but nothing is uploaded, so the walks
+// can be replayed as dry runs (layout, scratch size, shape validation of every GEMM) on a CPU-only machine
+inline bool g_host_only = false;
 template <typename T>
 static int upload(TmlEncoder* e, const std::vector<T>& h, T** out) {
+    if (g_host_only) { *out = nullptr; return 0; }
     void* d = nullptr;
     CUDA_OK(cudaMalloc(&d, h.size() * sizeof(T) + 256));
     CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
