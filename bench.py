@@ -278,17 +278,7 @@ def run_ours(args):
     ms_max, tensors, gt, launches = time_device(B, args.steps, n_warm, True)
     xh, th, nh, x, tgt, noise, x_adv, grad = tensors
     if args.gemm_table and rank == 0:
-        buf = C.create_string_buffer(1 << 16)
-        n = lib.tml_gemm_timing_report(buf, len(buf))
-        rows = []
-        for ln in buf.raw[:n].decode().strip().split("\n"):
-            f = ln.split("|")
-            rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), float(f[6]), float(f[7])))
-        rows.sort(key=lambda r: -r[6])
-        print(f"{'gemm':24s} {'M':>9s} {'N':>5s} {'K':>5s} {'mode':>4s} {'n':>4s} {'ms/step':>8s} {'TFLOP/s':>8s}", file=sys.stderr)
-        for r in rows:
-            print(f"{r[0]:24s} {r[1]:9d} {r[2]:5d} {r[3]:5d} {r[4]:4d} {r[5]:4d} {r[6] / args.steps:8.3f} "
-                  f"{r[7] / (r[6] * 1e-3) / 1e12:8.1f}", file=sys.stderr)
+        print_gemm_table(lib, args.steps)
     lib.tml_gemm_timing_enable(0)
     clocks = clock_box[0] if clock_box else None
     value = world * B * args.steps / (ms_max / 1e3)
@@ -571,6 +561,25 @@ def run_universal(args):
     return 0
 
 
+def print_gemm_table(lib, steps):
+    """Per-shape in-situ GEMM times of the launches recorded since tml_gemm_timing_enable (stderr)."""
+    buf = C.create_string_buffer(1 << 18)
+    n = lib.tml_gemm_timing_report(buf, len(buf))
+    rows = []
+    for ln in buf.raw[:n].decode().strip().split("\n"):
+        f = ln.split("|")
+        rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), float(f[6]), float(f[7])))
+    rows.sort(key=lambda r: -r[6])
+    tot_ms = sum(r[6] for r in rows)
+    tot_fl = sum(r[7] for r in rows)
+    print(f"{'gemm':28s} {'M':>9s} {'N':>6s} {'K':>6s} {'mode':>4s} {'n':>5s} {'ms/step':>8s} {'TFLOP/s':>8s}", file=sys.stderr)
+    for r in rows:
+        print(f"{r[0]:28s} {r[1]:9d} {r[2]:6d} {r[3]:6d} {r[4]:4d} {r[5]:5d} {r[6] / steps:8.3f} "
+              f"{r[7] / (r[6] * 1e-3) / 1e12:8.1f}", file=sys.stderr)
+    print(f"{'total':28s} {'':9s} {'':6s} {'':6s} {'':4s} {'':5s} {tot_ms / steps:8.3f} "
+          f"{tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms else 0:8.1f}", file=sys.stderr)
+
+
 def run_diffusion(args):
     """BASELINE configs[4], informational: backprop through the img2img DDIM steps of the SD-1.5 UNet at 512^2 with
     activation checkpointing.  Encoder / decoder / PGD update are this repo's kernels; the UNet is the PyTorch
@@ -586,13 +595,26 @@ def run_diffusion(args):
     torch.cuda.set_device(0)
     B, res = args.batch, args.res
     vae = AutoencoderKL(device=str(dev)).load_state_dict(random_init_state_dict(seed=0, include_decoder=True))
-    with torch.device(dev):
-        torch.manual_seed(0)
-        unet = UNet2DConditionModel().to(torch.bfloat16).requires_grad_(False)
+    native = args.unet == "native"
+    if native:
+        # random-init weights of the SD-1.5 topology, generated on the device by the PyTorch restatement and handed to
+        # the native module as a diffusers state dict
+        from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet
+        with torch.device(dev):
+            torch.manual_seed(0)
+            src = UNet2DConditionModel().requires_grad_(False)
+        unet = NativeUNet(device=str(dev), keep_activations=not args.unet_recompute).load_state_dict(src.state_dict())
+        del src
+        torch.cuda.empty_cache()
+    else:
+        with torch.device(dev):
+            torch.manual_seed(0)
+            unet = UNet2DConditionModel().to(torch.bfloat16).requires_grad_(False)
     cfg = TrainConfig(norm_type="linf", eps=EPS, step_size=STEP, grad_reps=1, override_from_norm_type=False,
                       device=str(dev), apply_loss_on_images=True, apply_loss_on_latents=False,
                       perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=4, limit_timesteps=False)
-    da = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=True, unet_dtype=torch.bfloat16)
+    da = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=not native,
+                         unet_dtype=torch.float32 if native else torch.bfloat16)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
     tgt = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
@@ -609,6 +631,8 @@ def run_diffusion(args):
         step()
     torch.cuda.synchronize()
     c0 = _lib.launch_counts()
+    if args.gemm_table:
+        _lib.load().tml_gemm_timing_enable(200000)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -617,13 +641,26 @@ def run_diffusion(args):
     torch.cuda.synchronize()
     c1 = _lib.launch_counts()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"mode": "diffusion", "metric": "image-PGD-iters/sec", "value": B * args.steps / (ms / 1e3),
+    extra = {}
+    if args.gemm_table:
+        gt = (C.c_double * 4)()
+        _lib.load().tml_gemm_timing_collect(gt)
+        extra = {"gemm_ms_per_step": gt[0] / args.steps, "gemm_tflops_in_situ": gt[1] / (gt[0] * 1e-3) / 1e12 if gt[0] else None,
+                 "gemm_launches_timed": int(gt[2])}
+        print_gemm_table(_lib.load(), args.steps)
+        _lib.load().tml_gemm_timing_enable(0)
+    unet_desc = ("this repo's native UNet (csrc/unet.cu: tcgen05 GEMMs, bf16 activations, "
+                 + ("activations recomputed per denoising step in the backward)" if args.unet_recompute else
+                    "activations of all denoising steps kept in HBM, attention probabilities recomputed)") if native else
+                 "the PyTorch library UNet (unet_torch.py: cuDNN / cuBLAS / SDPA, bf16 autocast, torch.utils.checkpoint)")
+    print(json.dumps({"mode": "diffusion", "unet": args.unet, "metric": "image-PGD-iters/sec",
+                      "value": B * args.steps / (ms / 1e3),
                       "ms_per_step": ms / args.steps, "steps": args.steps, "loss": float(loss),
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-                      "gpu_launches": (c1[0] - c0[0]) + (c1[1] - c0[1]),
-                      "config": {"workload": f"BASELINE configs[4]: diffusion attack, 4 DDIM steps of the SD-1.5 UNet (PyTorch "
-                                             f"library module, bf16, checkpointed) + encoder/decoder/update on this repo's "
-                                             f"kernels, batch {B} x {res}^2, CFG, image-space losses, random-init weights"}}),
+                      "gpu_launches": (c1[0] - c0[0]) + (c1[1] - c0[1]), **extra,
+                      "config": {"workload": f"BASELINE configs[4]: diffusion attack, 4 DDIM steps of the SD-1.5 UNet with "
+                                             f"classifier-free guidance on {unet_desc} + encoder/decoder/update on this "
+                                             f"repo's kernels, batch {B} x {res}^2, image-space losses, random-init weights"}}),
           flush=True)
     return 0
 
@@ -649,6 +686,11 @@ def main():
     ap.add_argument("--mode", default="encoder", choices=["encoder", "universal", "diffusion"],
                     help="universal: BASELINE configs[3] (shared perturbation, one NCCL all-reduce per step); "
                          "diffusion: BASELINE configs[4] (4 DDIM steps of the SD-1.5 UNet, checkpointed; informational)")
+    ap.add_argument("--unet", default="native", choices=["native", "torch"],
+                    help="--mode diffusion: this repo's UNet kernels (default) or the PyTorch library module (baseline)")
+    ap.add_argument("--unet_recompute", action="store_true",
+                    help="--mode diffusion --unet native: re-run each UNet call's forward in the backward (checkpointing) "
+                         "instead of keeping its activations (about 10 GB per call at batch 8 with guidance)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--gemm_table", action="store_true", help="print per-shape GEMM times (stderr)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")

@@ -182,6 +182,8 @@ typedef struct TmlGemmDesc {
     /* fused input normalisation (CTA-pair 3x3 kernel): A is the raw GroupNorm input, in_gn_ss = [A_B][A_C] float2
      * (scale, shift); the kernel convolves silu(A * scale + shift) */
     const void* in_gn_ss;
+    /* transposed A: stored [batch][k][m] with m = oh*OW + ow contiguous, row stride A_sK (csrc/gemm.h) */
+    int a_trans; int64_t A_sK;
 } TmlGemmDesc;
 int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 /* entries per image of the partial buffer a gn_mode GEMM writes: [B][tiles][32][2] floats */

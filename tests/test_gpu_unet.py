@@ -1,0 +1,121 @@
+"""GPU parity tests of the native UNet (csrc/unet.cu) through the C ABI, against the fp32 PyTorch restatement of
+diffusers' UNet2DConditionModel (``unet_torch.py``: the oracle of this path -- the module itself lives in the absent
+``diffusers``, so like the VAE its parity is unpinned beyond the parameter count 859 520 964 and the key set).
+
+Tolerances (bf16 activations, fp32 accumulation): stage outputs within 5e-2 relative L2, stage gradients within 1e-1,
+final prediction cosine >= 0.999, sample-gradient cosine >= 0.999 (tiny) / 0.999 (SD-1.5)."""
+import pytest
+import torch
+
+from tests.helpers import cosine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def test_unet_tiny_stagewise_vs_oracle(dev):
+    """Every resnet / transformer / sampler output and every backward stage of a 3-level UNet (64/128/128 channels,
+    8 heads of 8 and 16 channels, 5 prompt tokens padded and masked to 64) at 32 x 32 latents."""
+    from tests.gpu_check_unet import run_unet
+    ok, cy, cdx = run_unet(dev, "tiny", batch=2, size=32, tokens=5, verbose=False)
+    assert ok
+    assert cy >= 0.999 and cdx >= 0.999
+
+
+def test_unet_tiny_odd_shapes(dev):
+    """Non-square latents, a batch of 3 and 77 prompt tokens (two key tiles of 64, 51 masked slots)."""
+    from tests.gpu_check_unet import make_oracle, tiny_native_config
+    from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet
+    cfg = tiny_native_config()
+    m = make_oracle(cfg, 3, 2.0)
+    native = NativeUNet(cfg, device=str(dev)).load_state_dict(m.state_dict())
+    md = m.to(dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((3, 4, 32, 64), generator=g).to(dev)
+    ctx = torch.randn((3, 77, cfg.cross_attention_dim), generator=g).to(dev)
+    dout = (torch.randn((3, 4, 32, 64), generator=g) * 1e-2).to(dev)
+    xr = x.clone().requires_grad_(True)
+    y_ref = md(xr, torch.tensor(981.0, device=dev), ctx).sample
+    (dx_ref,) = torch.autograd.grad((y_ref * dout).sum(), [xr])
+    xn = x.clone().requires_grad_(True)
+    y = native(xn, 981.0, ctx).sample           # autograd seam: the backward recomputes the activations
+    (dx,) = torch.autograd.grad((y * dout).sum(), [xn])
+    assert cosine(y, y_ref) >= 0.999 and rel_err(y, y_ref) < 5e-2
+    assert cosine(dx, dx_ref) >= 0.999 and rel_err(dx, dx_ref) < 1e-1
+
+
+def test_unet_checkpointed_backward_is_bit_identical(dev):
+    """keep_activations (saved state kept from the forward) and the default (forward re-run in the backward) give the
+    same bits, and a sample is independent of the batch it shares (fixed-order reductions)."""
+    from tests.gpu_check_unet import make_oracle, tiny_native_config
+    from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet
+    cfg = tiny_native_config()
+    sd = make_oracle(cfg, 4, 2.0).state_dict()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((2, 4, 32, 32), generator=g).to(dev)
+    ctx = torch.randn((2, 7, cfg.cross_attention_dim), generator=g).to(dev)
+    dout = torch.randn((2, 4, 32, 32), generator=g).to(dev)
+    res = []
+    for keep in (False, True):
+        native = NativeUNet(cfg, device=str(dev), keep_activations=keep).load_state_dict(sd)
+        xn = x.clone().requires_grad_(True)
+        y = native(xn, 500, ctx).sample
+        (dx,) = torch.autograd.grad((y * dout).sum(), [xn])
+        res.append((y.detach().clone(), dx.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    native = NativeUNet(cfg, device=str(dev)).load_state_dict(sd)
+    x1 = x[1:2].clone().requires_grad_(True)
+    y1 = native(x1, 500, ctx[1:2]).sample
+    (dx1,) = torch.autograd.grad((y1 * dout[1:2]).sum(), [x1])
+    assert torch.equal(y1.detach(), res[0][0][1:2]) and torch.equal(dx1, res[0][1][1:2])
+
+
+def test_unet_sd15_vs_oracle(dev):
+    """The SD-1.5 topology itself (320/640/1280/1280 channels, 10..80 channels per GroupNorm group, heads of 40/80/160
+    channels, 77 prompt tokens) at 64 x 64 latents (512^2 images), batch 2 = one image under classifier-free guidance."""
+    from tests.gpu_check_unet import run_unet
+    ok, cy, cdx = run_unet(dev, "sd15", batch=2, size=64, tokens=77, verbose=False)
+    assert ok
+    assert cy >= 0.999 and cdx >= 0.999
+
+
+def test_diffusion_attack_native_unet_vs_oracle(dev):
+    """The reference's compute_grad (main.py:144-246) with EVERY network on this repo's kernels -- encoder, 4 DDIM steps
+    of the UNet under classifier-free guidance, decoder, image losses -- against the all-fp32 PyTorch pipeline."""
+    from oracle.decoder_oracle import make_vae_oracle
+    from tests.gpu_check_unet import make_oracle
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.diffusion import DiffusionAttack
+    from tml_image_editing_defense_b200.schedulers import DDIMScheduler
+    from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet
+    from tml_image_editing_defense_b200.unet_torch import UNetConfig
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ucfg = UNetConfig(block_out_channels=(64, 128), cross_attention_dim=64, attention_head_dim=8, norm_num_groups=32,
+                      down_has_attn=(True, False), up_has_attn=(False, True))
+    um = make_oracle(ucfg, 21, 2.0)
+    vm = make_vae_oracle(0)
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(vm.state_dict())
+    native = NativeUNet(ucfg, device=str(dev)).load_state_dict(um.state_dict())
+    cfg = TrainConfig(norm_type="linf", override_from_norm_type=False, device=str(dev), apply_loss_on_images=True,
+                      apply_loss_on_latents=False, perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=4)
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).to(dev)
+    tgt = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).to(dev)
+    pe = torch.randn(2, 7, 64, generator=g).to(dev)
+    nz = [torch.randn(2, 4, 16, 16, generator=g).to(dev)]
+    ref = DiffusionAttack(cfg, vm.to(dev), um.to(dev), DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+    g_ref, l_ref, img_ref, _ = ref.compute_grad(x, pe, x, tgt, None, nz)
+    ours = DiffusionAttack(cfg, vae, native, DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+    gg, l, img, _ = ours.compute_grad(x, pe, x, tgt, None, nz)
+    c = cosine(gg, g_ref)
+    print("native diffusion attack gradient cosine", c)
+    assert c >= 0.99
+    assert abs(float(l) - float(l_ref)) / float(l_ref) < 0.03
+    assert rel_err(img, img_ref) < 0.08

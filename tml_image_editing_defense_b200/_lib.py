@@ -53,6 +53,7 @@ class TmlGemmDesc(C.Structure):
         ("gn_mr", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_silu", C.c_int),
         ("dbg_shift", C.c_int), ("dbg_bo", C.c_int),
         ("in_gn_ss", C.c_void_p),
+        ("a_trans", C.c_int), ("A_sK", C.c_int64),
     ]
 
 

@@ -473,6 +473,7 @@ static int desc_to_op(const TmlGemmDesc* d, GemmOp& o) {
     o.gn_gamma = d->gn_gamma; o.gn_silu = d->gn_silu;
     o.dbg_shift = d->dbg_shift; o.dbg_bo = d->dbg_bo;
     o.in_gn_ss = reinterpret_cast<const float2*>(d->in_gn_ss);
+    o.a_trans = d->a_trans; o.A_sK = d->A_sK;
     return 0;
 }
 

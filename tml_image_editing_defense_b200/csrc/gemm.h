@@ -18,6 +18,11 @@ struct GemmOp {
     const void* A = nullptr;
     int A_C = 0, A_W = 0, A_H = 0, A_B = 0;
     int64_t A_sW = 0, A_sH = 0, A_sB = 0;
+    // a_trans = 1: A is stored TRANSPOSED, [batch][k][m] with the output-row index m = oh*OW + ow contiguous (row stride
+    // A_sK, batch stride A_sB; A_C = K).  The kernel reads it as an MN-major UMMA operand, so products such as dS^T Q or
+    // P^T dO need no transposed copy of the token x token matrix.  One tap, stride 1, tiles of whole rows only.
+    int a_trans = 0;
+    int64_t A_sK = 0;
     int stride = 1;  // 1 or 2
     int ntaps = 1;
     int dh[kMaxTaps] = {0}, dw[kMaxTaps] = {0};

@@ -11,7 +11,8 @@ namespace tml {
 struct SimtParams {
     const __nv_bfloat16* A;
     int A_C, A_W, A_H, A_B;
-    long long A_sW, A_sH, A_sB;
+    long long A_sW, A_sH, A_sB, A_sK;
+    int a_trans;
     int stride, ntaps;
     int dh[kMaxTaps], dw[kMaxTaps];
     int OW, OH;
@@ -41,6 +42,11 @@ __global__ void conv_gemm_simt_kernel(const SimtParams p) {
         if (n >= p.n_store) continue;
         const __nv_bfloat16* brow = p.Bm + (long long)b * p.B_sBatch + (long long)n * p.B_sN;
         float acc = 0.f;
+        if (p.a_trans) {   // A stored [batch][k][m], m = oh*OW + ow
+            const __nv_bfloat16* acol = p.A + (long long)b * p.A_sB + (long long)oh * p.OW + ow;
+            for (int c = 0; c < p.A_C; ++c)
+                acc = fmaf(__bfloat162float(acol[(long long)c * p.A_sK]), __bfloat162float(brow[c]), acc);
+        } else
         for (int t = 0; t < p.ntaps; ++t) {
             const int ih = oh * p.stride + p.dh[t], iw = ow * p.stride + p.dw[t];
             if (ih < 0 || ih >= p.A_H || iw < 0 || iw >= p.A_W) continue;
@@ -61,7 +67,7 @@ int gemm_launch_simt(const GemmOp& op, cudaStream_t stream) {
     SimtParams p;
     p.A = reinterpret_cast<const __nv_bfloat16*>(op.A);
     p.A_C = op.A_C; p.A_W = op.A_W; p.A_H = op.A_H; p.A_B = op.A_B;
-    p.A_sW = op.A_sW; p.A_sH = op.A_sH; p.A_sB = op.A_sB;
+    p.A_sW = op.A_sW; p.A_sH = op.A_sH; p.A_sB = op.A_sB; p.A_sK = op.A_sK; p.a_trans = op.a_trans;
     p.stride = op.stride; p.ntaps = op.ntaps;
     for (int i = 0; i < kMaxTaps; ++i) { p.dh[i] = op.dh[i]; p.dw[i] = op.dw[i]; }
     p.OW = op.OW; p.OH = op.OH;

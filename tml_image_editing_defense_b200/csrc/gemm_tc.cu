@@ -165,6 +165,15 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     tile_shape(op.OH, op.OW, &TW, &TH);
     if (TW == 0) { set_error("%s: output width %d has no tile width (multiple of 8, <=128)", op.name, op.OW); return -1; }
     if (op.stride == 2 && (op.A_W % 2 != 0)) { set_error("%s: stride-2 input width must be even", op.name); return -1; }
+    if (op.a_trans) {
+        // the 128 (or 64) rows of a tile must be consecutive values of m = oh*OW + ow: whole rows, or one row segment
+        if (op.ntaps != 1 || op.stride != 1 || op.dbg_shift != 0 || op.A_sK <= 0 || (op.A_sK * 2) % 16 != 0 ||
+            (TW * TH) % 64 != 0 || !(TW == op.OW || TH == 1) || op.in_gn_ss != nullptr) {
+            set_error("%s: transposed A needs one tap, stride 1 and tiles of 64/128 consecutive rows (TW=%d TH=%d OW=%d)",
+                      op.name, TW, TH, op.OW);
+            return -1;
+        }
+    }
     int BN = 0;
     if (op.N % 256 == 0) BN = 256;
     else if (op.N % 128 == 0) BN = 128;
@@ -269,7 +278,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // every B (weight) tile is then fetched from L2 once per 256 output pixels instead of once per 128.
     const long sub_tiles = (long)op.A_B * t->tiles_h * t->tiles_w;
     static const bool no_mt2 = getenv("TML_NO_MT2") && getenv("TML_NO_MT2")[0] == '1';   // tuning switch
-    t->mt = (!no_mt2 && BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
+    t->mt = (!no_mt2 && !op.a_trans && BN <= 128 && op.B_sBatch == 0 && sub_tiles % 2 == 0 && sub_tiles * t->n_tiles >= 2 * 148) ? 2 : 1;
     // CTA pairs for the weight-heavy long-K tiles (BN = 256, K >= 2048: the 512-channel convolutions at 64^2): M = 256
     // pixels over two SMs, each CTA stages its own 128 pixels and HALF of every weight tile, which cuts the L2 -> SM
     // traffic that bounds these layers by a third (48 -> 32 KB per four MMAs).
@@ -277,7 +286,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // (a per-image B operand is fine when both CTAs of a pair always work on the same image)
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
     // (the attention logits, K = 512 and a per-image B operand, are L2-bound on single CTAs: 48 KB per four MMAs)
-    t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
+    t->pair = (!no_pair && b_ok && !op.a_trans && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && (op.ntaps * op.A_C >= 2048 || op.epi_mode != 0) && sub_tiles % 2 == 0 &&
                sub_tiles * t->n_tiles >= 4) ? 1 : 0;
     // Plain dense outputs (no fused reduction) leave through shared memory and TMA stores: the per-lane
@@ -318,6 +327,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     int mode;  // 0: stride 1 (4-D map c,w,h,b)   1: stride 2 (5-D map c,wpar,w/2,h,b)
+    int a_trans;   // A stored [batch][k][m] (3-D map m,k,b; boxes of 64 m x 64 k): MN-major UMMA operand
     int TW, TH, rows_valid;
     int tiles_w, tiles_h, nimg;
     int n_tiles, BN;
@@ -886,7 +896,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                     mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     for (int sub = 0; sub < p.mt; ++sub) {
                         uint8_t* dst = sA + sub * kATileBytes;
-                        if (p.mode == 0) {
+                        if (p.a_trans) {
+                            // 64-row (m) x 64-k atoms column by column: rows m0 .. m0+63 at dst, m0+64 .. at dst + 8 KB
+                            const int m0 = sb[sub].oh0 * p.ow_full + sb[sub].ow0;
+                            for (int j = 0; j < (p.rows_valid >> 6); ++j)
+                                tma_load_3d(dst + j * 8192, &mapA, &full_bar[stage], m0 + 64 * j, c0, sb[sub].img);
+                        } else if (p.mode == 0) {
                             tma_load_4d(dst, &mapA, &full_bar[stage], c0, sb[sub].ow0 + p.dw[tap] - p.dbg_shift,
                                         sb[sub].oh0 + p.dh[tap], sb[sub].img);
                         } else {
@@ -943,7 +958,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         // from a divergent `if (lane == 0)` region costs ~16 instructions of R2UR/ELECT shuffling per MMA, which
         // made the N = 128 layers issue-bound (64 tensor cycles per MMA).
         if (crank == 0) {   // pair mode: only the leader CTA issues
-            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kUmmaM : kUmmaM, p.BN);
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kUmmaM : kUmmaM, p.BN) | (p.a_trans ? kUmmaAMajorMN : 0u);
+            // K = 16 step of the A descriptor (addr >> 4 units): 32 B inside the swizzle row, or two 1 KB K-groups
+            const uint64_t a_step = p.a_trans ? 128u : 2u;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0, hs = 0;
@@ -1004,7 +1021,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + size_t(stage) * p.stage_bytes);
                         const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
-                        uint64_t a_desc0 = umma_desc_sw128(a_addr + uint32_t(p.dbg_shift) * 128u);
+                        uint64_t a_desc0 = p.a_trans ? umma_desc_sw128_mn(a_addr, 8192u, 1024u)
+                                                     : umma_desc_sw128(a_addr + uint32_t(p.dbg_shift) * 128u);
                         if (p.dbg_bo) a_desc0 |= uint64_t(((a_addr + uint32_t(p.dbg_shift) * 128u) >> 7) & 7u) << 49;
                         const uint32_t first = kb != 0 ? 1u : 0u;
                         if (elect_one()) {
@@ -1020,9 +1038,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                     const uint32_t d = d_tmem + uint32_t(sub * p.BN);
                                     // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the addr>>4 field
                                     umma_bf16(d, a_desc, b_desc, idesc, first);
-                                    umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1u);
-                                    umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1u);
-                                    umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1u);
+                                    umma_bf16(d, a_desc + a_step, b_desc + 2, idesc, 1u);
+                                    umma_bf16(d, a_desc + 2 * a_step, b_desc + 4, idesc, 1u);
+                                    umma_bf16(d, a_desc + 3 * a_step, b_desc + 6, idesc, 1u);
                                 }
                                 umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
                             }
@@ -1952,7 +1970,12 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     }
 
     CUtensorMap mapA, mapB;
-    if (op.stride == 1) {
+    if (op.a_trans) {
+        cuuint64_t dims[3] = {(cuuint64_t)op.OH * op.OW, (cuuint64_t)op.A_C, (cuuint64_t)op.A_B};
+        cuuint64_t str[2] = {(cuuint64_t)op.A_sK * 2, (cuuint64_t)op.A_sB * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)kBlockK, 1};
+        if ((rc = encode_map(&mapA, op.A, 3, dims, str, box, op.name))) return rc;
+    } else if (op.stride == 1) {
         cuuint64_t dims[4] = {(cuuint64_t)op.A_C, (cuuint64_t)op.A_W, (cuuint64_t)op.A_H, (cuuint64_t)op.A_B};
         cuuint64_t str[3] = {(cuuint64_t)op.A_sW * 2, (cuuint64_t)op.A_sH * 2, (cuuint64_t)op.A_sB * 2};
         cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(t.TW + (op.dbg_shift ? 8 : 0)), (cuuint32_t)t.TH, 1};
@@ -1993,6 +2016,7 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     memset(&p, 0, sizeof(p));
     p.out_bytes = t.out_bytes;
     p.mode = op.stride == 2 ? 1 : 0;
+    p.a_trans = op.a_trans;
     p.TW = t.TW; p.TH = t.TH; p.rows_valid = t.rows_valid;
     p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.nimg = op.A_B;
     p.n_tiles = t.n_tiles; p.BN = t.BN; p.mt = t.mt;

@@ -314,6 +314,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
+// MN-major operand (the matrix is stored [K][MN] with MN contiguous, i.e. transposed) in 128-byte-swizzled atoms of
+// 64 MN-elements x 8 K-rows (1024 B): LBO = distance between consecutive 64-element MN atoms, SBO = distance between
+// consecutive groups of 8 K-rows.  A K = 16 MMA reads two K groups; the next one starts 2 * SBO further.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+constexpr uint32_t kUmmaAMajorMN = 1u << 15;   // instruction-descriptor bit: A operand is MN-major
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

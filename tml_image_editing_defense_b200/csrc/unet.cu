@@ -47,7 +47,7 @@ struct TfRec {
     int h = 0, w = 0;
     size_t x = 0, out = 0;
     GnSaved g;
-    size_t t0 = 0, st1 = 0, Qh = 0, Kh = 0, Vh = 0, P = 0, Oh = 0, invl = 0;
+    size_t t0 = 0, st1 = 0, Qh = 0, Kh = 0, Vh = 0, rmax = 0, Oh = 0, invl = 0;   // self attention: P~ is recomputed in the backward
     size_t x1 = 0, st2 = 0, Q2 = 0, K2 = 0, V2 = 0, P2 = 0, O2 = 0, invl2 = 0;
     size_t x2 = 0, st3 = 0, hff = 0;
 };
@@ -317,9 +317,23 @@ GemmOp mh_tok_op(const char* name, const bf16* A, const bf16* Bt, bf16* D, int n
     return o;
 }
 
-// softmax(Q K^T * scale) V for nb batches: P~ (bf16 [nb][tq][tkv]) and 1/l are kept for the backward; O dense [nb][tq][dp]
-int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, bf16* P, float* inv_l, bf16* O, int nb,
-                         int tq, int tkv, int dp, float scale) {
+// P~ = exp2((Q K^T - rowmax) * scale * log2 e) as bf16 [nb][tq][tkv] from known row maxima; `part` receives the row sums
+// per column tile (scratch of rows x gemm_row_partials floats).  Bitwise reproducible: the backward calls it again
+// instead of keeping 2 bytes per logit alive (4.3 GB per layer at 64 x 64 latents and batch 16).
+int mh_probs(URun& r, const bf16* Q, const bf16* K, const float* rmax, float* part, bf16* P, int nb, int tq, int tkv, int dp,
+             int gh, int gw, float scale, const char* name) {
+    GemmOp e = mh_logits_op(name, Q, K, nb, tq, tkv, dp, gh, gw);
+    e.epi_mode = 2;
+    e.row_a = rmax; e.row_part = part;
+    e.exp_scale = scale * 1.4426950408889634f;
+    e.D = P;
+    return gemm_launch(e, r.u->base.num_sms, r.st);
+}
+
+// softmax(Q K^T * scale) V for nb batches: the row maxima (rmax) and 1/l are kept for the backward, P~ only if the
+// caller passes a saved buffer (cross attention: 128 key slots); O dense [nb][tq][dp]
+int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, bf16* P, float* rmax, float* inv_l, bf16* O,
+                         int nb, int tq, int tkv, int dp, float scale) {
     const int ns = r.u->base.num_sms;
     const long long rows = (long long)nb * tq;
     int gh = 0, gw = 0;
@@ -330,16 +344,12 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
     const int np = gemm_row_partials(o);   // host-only planning: also valid during a dry run
     if (np < 0) return np;
     float* part = r.Walloc<float>((size_t)rows * np * sizeof(float));
-    float* rmax = r.Walloc<float>((size_t)rows * sizeof(float));
+    if (rmax == nullptr) rmax = r.Walloc<float>((size_t)rows * sizeof(float));
+    if (P == nullptr) P = r.Walloc<bf16>((size_t)rows * tkv * sizeof(bf16));
     o.row_part = part;
     RC(gemm_launch(o, ns, r.st));
     launch_row_reduce(part, rmax, rows, np, 0, r.st);
-    GemmOp e = mh_logits_op("unet.attn.qk.exp", Q, K, nb, tq, tkv, dp, gh, gw);
-    e.epi_mode = 2;
-    e.row_a = rmax; e.row_part = part;
-    e.exp_scale = scale * 1.4426950408889634f;
-    e.D = P;
-    RC(gemm_launch(e, ns, r.st));
+    RC(mh_probs(r, Q, K, rmax, part, P, nb, tq, tkv, dp, gh, gw, scale, "unet.attn.qk.exp"));
     launch_row_reduce(part, inv_l, rows, np, 1, r.st);
     bf16* Vt = r.Walloc<bf16>((size_t)nb * tkv * dp * sizeof(bf16));   // [nb][dp][tkv]
     launch_transpose(V, Vt, nb, tkv, dp, dp, (long long)tkv * dp, tkv, (long long)dp * tkv, r.st);
@@ -351,14 +361,24 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
 }
 
 // dO [nb][tq][dp] -> dQ (always), dK / dV (self attention only; null for cross attention)
-int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, const bf16* P, const float* inv_l,
-                          const bf16* O, const bf16* dO, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv, int dp,
-                          float scale) {
+int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, const bf16* P, const float* rmax,
+                          const float* inv_l, const bf16* O, const bf16* dO, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq,
+                          int tkv, int dp, float scale) {
     const int ns = r.u->base.num_sms;
     const long long rows = (long long)nb * tq;
     int gh = 0, gw = 0;
     RC(attn_grid(tq, &gh, &gw));
     const size_t m = r.wsa.mark();
+    if (P == nullptr) {   // not kept by the forward: the same GEMM + epilogue gives the same bits again
+        GemmOp o = mh_logits_op("unet.attn.qk.exp", Q, K, nb, tq, tkv, dp, gh, gw);
+        o.epi_mode = 2;
+        const int np = gemm_row_partials(o);
+        if (np < 0) return np;
+        bf16* Pn = r.Walloc<bf16>((size_t)rows * tkv * sizeof(bf16));
+        float* part = r.Walloc<float>((size_t)rows * np * sizeof(float));
+        RC(mh_probs(r, Q, K, rmax, part, Pn, nb, tq, tkv, dp, gh, gw, scale, "unet.attn.qk.exp.recompute"));
+        P = Pn;
+    }
     float* Drow = r.Walloc<float>((size_t)rows * sizeof(float));
     launch_row_dot(dO, O, Drow, rows, dp, r.st);
     bf16* dS = r.Walloc<bf16>((size_t)nb * tq * tkv * sizeof(bf16));
@@ -375,18 +395,21 @@ int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, 
     launch_transpose(K, Kt, nb, tkv, dp, dp, (long long)tkv * dp, tkv, (long long)dp * tkv, r.st);
     RC(gemm_launch(mh_tok_op("unet.attn.dQ", dS, Kt, dQ, nb, tq, tkv, dp, gh, gw), ns, r.st));
     if (dK != nullptr && dV != nullptr) {
+        // dK = dS^T Q and dV = P~^T (dO / l): the token x token matrices are read TRANSPOSED by the tensor cores
+        // (GemmOp::a_trans, MN-major operand), so no transposed copy of dS or P~ is ever written
         int kh = 0, kw = 0;
         RC(attn_grid(tkv, &kh, &kw));
-        bf16* dST = r.Walloc<bf16>((size_t)nb * tq * tkv * sizeof(bf16));
-        launch_transpose(dS, dST, nb, tq, tkv, tkv, (long long)tq * tkv, tq, (long long)tq * tkv, r.st);
         bf16* Qt = r.Walloc<bf16>((size_t)nb * tq * dp * sizeof(bf16));
         launch_transpose(Q, Qt, nb, tq, dp, dp, (long long)tq * dp, tq, (long long)dp * tq, r.st);
-        RC(gemm_launch(mh_tok_op("unet.attn.dK", dST, Qt, dK, nb, tkv, tq, dp, kh, kw), ns, r.st));
-        bf16* PT = dST;   // reuse: dS^T has been consumed by the launch above (same stream)
-        launch_transpose(P, PT, nb, tq, tkv, tkv, (long long)tq * tkv, tq, (long long)tq * tkv, r.st);
-        bf16* dOT = Qt;   // (dO / l)^T
+        auto trans_op = [&](const char* name, const bf16* A, const bf16* Bt, bf16* D) {
+            GemmOp o = mh_tok_op(name, A, Bt, D, nb, tkv, tq, dp, kh, kw);
+            o.a_trans = 1; o.A_sK = tkv; o.A_sB = (int64_t)tq * tkv;   // A[b][k = query][m = key]
+            return gemm_launch(o, ns, r.st);
+        };
+        RC(trans_op("unet.attn.dK", dS, Qt, dK));
+        bf16* dOT = Qt;   // (dO / l)^T (Qt has been consumed by the launch above, same stream)
         launch_transpose(dO, dOT, nb, tq, dp, dp, (long long)tq * dp, tq, (long long)dp * tq, r.st, inv_l);
-        RC(gemm_launch(mh_tok_op("unet.attn.dV", PT, dOT, dV, nb, tkv, tq, dp, kh, kw), ns, r.st));
+        RC(trans_op("unet.attn.dV", P, dOT, dV));
     }
     r.wsa.reset(m);
     return 0;
@@ -408,7 +431,7 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
     rec.Qh = r.sva.alloc((size_t)nb * tok * dp * sizeof(bf16));
     rec.Kh = r.sva.alloc((size_t)nb * tok * dp * sizeof(bf16));
     rec.Vh = r.sva.alloc((size_t)nb * tok * dp * sizeof(bf16));
-    rec.P = r.sva.alloc((size_t)nb * tok * tok * sizeof(bf16));
+    rec.rmax = r.sva.alloc((size_t)nb * tok * sizeof(float));
     rec.Oh = r.sva.alloc((size_t)nb * tok * dp * sizeof(bf16));
     rec.invl = r.sva.alloc((size_t)nb * tok * sizeof(float));
     rec.x1 = r.sva.alloc(act);
@@ -442,7 +465,7 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
         launch_head_split(qkv, 3 * C, bs, 2 * C, r.S<bf16>(rec.Vh), B, H, tok, tok, tok, d, dp, 0, r.st);
         r.wsa.reset(m2);
     }
-    RC(mh_attention_forward(r, r.S<bf16>(rec.Qh), r.S<bf16>(rec.Kh), r.S<bf16>(rec.Vh), r.S<bf16>(rec.P),
+    RC(mh_attention_forward(r, r.S<bf16>(rec.Qh), r.S<bf16>(rec.Kh), r.S<bf16>(rec.Vh), nullptr, r.S<float>(rec.rmax),
                             r.S<float>(rec.invl), r.S<bf16>(rec.Oh), nb, tok, tok, dp, scale));
     launch_head_merge(r.S<bf16>(rec.Oh), a, C, (long long)tok * C, 0, B, H, tok, d, dp, r.st);
     bf16* x1 = r.S<bf16>(rec.x1);
@@ -460,7 +483,7 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
         launch_head_split(kv, 2 * C, (long long)Tp * 2 * C, C, r.S<bf16>(rec.V2), B, H, Tp, T, Tp, d, dp2, 0, r.st);
         r.wsa.reset(m2);
     }
-    RC(mh_attention_forward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2),
+    RC(mh_attention_forward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2), nullptr,
                             r.S<float>(rec.invl2), r.S<bf16>(rec.O2), nb, tok, Tp, dp2, scale));
     launch_head_merge(r.S<bf16>(rec.O2), a, C, (long long)tok * C, 0, B, H, tok, d, dp2, r.st);
     bf16* x2 = r.S<bf16>(rec.x2);
@@ -512,7 +535,7 @@ int utf_backward(URun& r, const UTf& p, const TfRec& rec, const bf16* dout, bf16
         bf16* dO = r.Walloc<bf16>((size_t)nb * tok * dp2 * sizeof(bf16));
         launch_head_split(da, C, (long long)tok * C, 0, dO, B, H, tok, tok, tok, d, dp2, 0, r.st);
         bf16* dQ = r.Walloc<bf16>((size_t)nb * tok * dp2 * sizeof(bf16));
-        RC(mh_attention_backward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2),
+        RC(mh_attention_backward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2), nullptr,
                                  r.S<float>(rec.invl2), r.S<bf16>(rec.O2), dO, dQ, nullptr, nullptr, nb, tok, Tp, dp2, scale));
         launch_head_merge(dQ, da, C, (long long)tok * C, 0, B, H, tok, d, dp2, r.st);
         bf16* dn = r.Walloc<bf16>(act);
@@ -531,7 +554,7 @@ int utf_backward(URun& r, const UTf& p, const TfRec& rec, const bf16* dout, bf16
         bf16* dQ = r.Walloc<bf16>(hb);
         bf16* dK = r.Walloc<bf16>(hb);
         bf16* dV = r.Walloc<bf16>(hb);
-        RC(mh_attention_backward(r, r.S<bf16>(rec.Qh), r.S<bf16>(rec.Kh), r.S<bf16>(rec.Vh), r.S<bf16>(rec.P),
+        RC(mh_attention_backward(r, r.S<bf16>(rec.Qh), r.S<bf16>(rec.Kh), r.S<bf16>(rec.Vh), nullptr, r.S<float>(rec.rmax),
                                  r.S<float>(rec.invl), r.S<bf16>(rec.Oh), dO, dQ, dK, dV, nb, tok, tok, dp, scale));
         bf16* dqkv = r.Walloc<bf16>(3 * act);
         const long long bs = (long long)tok * 3 * C;

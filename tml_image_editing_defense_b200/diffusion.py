@@ -3,10 +3,12 @@ classifier-free guidance -> decode -> image-space losses -> gradient w.r.t. the 
 configs[4]).
 
 Encoder and decoder (forward and backward) run on this repo's sm_100a kernels through their autograd seams
-(``vae.encode(x).latent_dist`` / ``vae.decode(z).sample``), the PGD update on the fused kernel; the UNet is the
-PyTorch library module of ``unet_torch.py`` (cuDNN / cuBLAS / SDPA), re-run under activation checkpointing per
-denoising step so that only the latents between steps stay alive (the reference keeps everything; checkpointing
-is BASELINE configs[4]'s addition).  No CLIP weights exist offline: prompt embeddings are passed in as tensors."""
+(``vae.encode(x).latent_dist`` / ``vae.decode(z).sample``), the PGD update on the fused kernel.  The UNet is either
+this repo's native module (``unet.py`` -> ``csrc/unet.cu``: pass ``unet_dtype=torch.float32, use_checkpointing=False``,
+it recomputes its own activations in the backward) or the PyTorch library module of ``unet_torch.py`` (cuDNN / cuBLAS /
+SDPA; the oracle and the library baseline), re-run under ``torch.utils.checkpoint`` per denoising step.  Either way only
+the latents between steps stay alive (the reference keeps everything; checkpointing is BASELINE configs[4]'s addition).
+No CLIP weights exist offline: prompt embeddings are passed in as tensors."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -47,8 +49,9 @@ class DiffusionAttack:
         def one_step(lat, t):
             inp = self.scheduler.scale_model_input(torch.cat([lat] * 2), t)       # :230-231
             with torch.autocast("cuda", dtype=self.unet_dtype, enabled=lat.is_cuda and self.unet_dtype != torch.float32):
-                pred = self.unet(inp.to(self.unet_dtype) if lat.is_cuda else inp, torch.tensor(t, device=lat.device),
-                                 encoder_hidden_states=ctx).sample
+                # (the native UNet takes the scalar timestep as a host number: no device round trip per step)
+                tt = t if getattr(self.unet, "native", False) else torch.tensor(t, device=lat.device)
+                pred = self.unet(inp.to(self.unet_dtype) if lat.is_cuda else inp, tt, encoder_hidden_states=ctx).sample
             pred = pred.float()
             uncond, text = pred.chunk(2)
             return uncond + c.guidance_scale * (text - uncond)                    # :240-241

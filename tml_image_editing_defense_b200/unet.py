@@ -53,6 +53,7 @@ class _UNetFn(torch.autograd.Function):
 
 class UNet2DConditionModel:
     """B200-native denoiser with the reference-facing surface of diffusers' module (``__call__`` -> ``.sample``)."""
+    native = True   # DiffusionAttack passes the timestep as a host scalar
 
     def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda:0", keep_activations: bool = False):
         self.config = config or UNetConfig()
