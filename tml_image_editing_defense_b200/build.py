@@ -15,7 +15,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libtml_b200.so"
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "encoder.cu", "decoder.cu", "unet.cu", "unet_kernels.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "encoder.cu", "decoder.cu", "unet.cu", "unet_kernels.cu", "attn_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

@@ -1,0 +1,285 @@
+// Fused multi-head attention forward for the UNet's self-attention layers (diffusers Attention / SDPA call reached from
+// main.py:233-238): one kernel per layer computes O = softmax(Q K^T * scale) V for every (image, head) without the
+// token x token matrix ever leaving the SM.
+//
+//   CTA = one (image, head) x 128 query rows, looping over key tiles of 128:
+//     warp 0   TMA producer: Q once, then K and V tiles into a two-stage ring (128-byte swizzle)
+//     warp 1   tcgen05.mma issuer: S = Q K^T into one of two TMEM buffers (128 columns each), and, one tile behind,
+//              O += P~ V with P~ read from shared memory and V read as an MN-major operand (no transposed copy)
+//     warps 2-5  softmax, thread = query row: tcgen05.ld of S, P~ = exp2((s - rowmax) * scale * log2 e) with the row
+//              maxima of the preceding max pass (so no accumulator rescaling is ever needed), bf16 P~ written into the
+//              swizzled K-major operand tile the PV MMA reads, row sums of the values as stored
+//   TMEM: S[0] | S[1] | O (DP columns); epilogue: O / l -> bf16, 1 / l -> fp32 (kept for the backward).
+//
+// The numbers are those of the unfused path (same MMA shapes for S, same exp2 form, same bf16 rounding of P~), which
+// stays the verified baseline and still serves head widths above 128 and the cross attention.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gemm.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tml {
+
+void count_launch();
+int encode_map_bf16_sw128(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                          const cuuint32_t* box, const char* what);   // gemm_tc.cu
+
+namespace {
+
+constexpr int kFaThreads = 192;
+constexpr uint32_t kUmmaBMajorMN = 1u << 16;
+
+struct FaParams {
+    const float* rmax;    // [nb][tq]
+    float* inv_l;         // [nb][tq]
+    __nv_bfloat16* O;     // [nb][tq][DP]
+    int tq, tkv;
+    float exp_scale;      // scale * log2(e)
+};
+
+__device__ __forceinline__ float fa_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t fa_pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float fa_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float fa_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+template <int DP>
+__global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                   const __grid_constant__ CUtensorMap mapK,
+                                                                   const __grid_constant__ CUtensorMap mapV,
+                                                                   const FaParams p) {
+    constexpr int NC = DP / 64;                 // 64-channel chunks of the head width
+    constexpr int kChunk = 128 * 128;           // [128 rows][128 B] = 16 KB
+    constexpr int kQBytes = NC * kChunk, kKBytes = NC * kChunk, kVBytes = NC * kChunk, kPBytes = 2 * kChunk;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kQBytes;                 // 2 stages
+    uint8_t* sV = sK + 2 * kKBytes;             // 2 stages
+    uint8_t* sP = sV + 2 * kVBytes;             // 2 buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;               // [2]
+    uint64_t* kv_empty = bars + 3;              // [2]
+    uint64_t* s_full = bars + 5;                // [2]
+    uint64_t* s_empty = bars + 7;               // [2]
+    uint64_t* p_full = bars + 9;                // [2]
+    uint64_t* p_empty = bars + 11;              // [2]
+    uint64_t* o_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, batch = blockIdx.y;
+    const int ntiles = p.tkv / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_empty[i], 1);
+        }
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kOCol = 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kQBytes);
+            for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * kChunk, &mapQ, q_full, c * 64, q0, batch);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&kv_full[s], kKBytes + kVBytes);
+                for (int c = 0; c < NC; ++c) {
+                    tma_load_3d(sK + s * kKBytes + c * kChunk, &mapK, &kv_full[s], c * 64, j * 128, batch);
+                    tma_load_3d(sV + s * kVBytes + c * kChunk, &mapV, &kv_full[s], c * 64, j * 128, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // S = Q K^T: M = 128 queries, N = 128 keys, K = DP (both operands K-major)
+        const uint32_t idesc_s = umma_idesc_bf16(128, 128);
+        // O += P V: M = 128 queries, N = DP channels, K = 128 keys; V tile [key][channel] is the MN-major B operand
+        const uint32_t idesc_o = umma_idesc_bf16(128, DP) | kUmmaBMajorMN;
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        auto issue_pv = [&](int j) {
+            const int s = j & 1, b = j & 1;
+            mbar_wait(&p_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + b * kPBytes), va = smem_u32(sV + s * kVBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {   // 8 x 16 keys
+                    const uint64_t a_desc = umma_desc_sw128(pa + (kk >> 2) * kChunk) + uint64_t((kk & 3) * 2);
+                    // MN-major: channel atoms (64) kChunk apart, groups of 8 keys 1 KB apart; 16 keys = 2 KB per step
+                    const uint64_t b_desc = umma_desc_sw128_mn(va + kk * 2048, kChunk, 1024);
+                    umma_bf16(tmem_base + kOCol, a_desc, b_desc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(&p_empty[b]);
+            }
+            __syncwarp();
+        };
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j & 1, b = j & 1;
+            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            mbar_wait(&s_empty[b], (((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + s * kKBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(qa + c * kChunk) + uint64_t(kk * 2),
+                                  umma_desc_sw128(ka + c * kChunk) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                umma_commit(&s_full[b]);
+            }
+            __syncwarp();
+            if (j > 0) issue_pv(j - 1);
+        }
+        issue_pv(ntiles - 1);
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
+    } else {
+        // ===================================================================== softmax warps (thread = query row)
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const long long grow = (long long)batch * p.tq + q0 + row;
+        const float c = p.exp_scale;
+        const float ra = -__ldg(p.rmax + grow) * c;
+        const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
+        float l = 0.f;
+        for (int j = 0; j < ntiles; ++j) {
+            const int b = j & 1;
+            mbar_wait(&s_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            mbar_wait(&p_empty[b], (((j >> 1) & 1) ^ 1));
+            uint8_t* prow = sP + b * kPBytes + row * 128;
+            uint32_t v[32];
+            tmem_ld32(t_row + uint32_t(b * 128), v);
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fa_ex2(fmaf(__uint_as_float(v[i]), c, ra));
+                if (ch < 3) tmem_ld32(t_row + uint32_t(b * 128 + (ch + 1) * 32), v);
+                uint8_t* dst = prow + (ch >> 1) * kChunk;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint4 o = make_uint4(fa_pack(f[8 * u], f[8 * u + 1]), fa_pack(f[8 * u + 2], f[8 * u + 3]),
+                                               fa_pack(f[8 * u + 4], f[8 * u + 5]), fa_pack(f[8 * u + 6], f[8 * u + 7]));
+                    const int unit = (ch & 1) * 4 + u;
+                    *reinterpret_cast<uint4*>(dst + ((unit ^ (row & 7)) << 4)) = o;
+                    l += ((fa_lo(o.x) + fa_hi(o.x)) + (fa_lo(o.y) + fa_hi(o.y))) +
+                         ((fa_lo(o.z) + fa_hi(o.z)) + (fa_lo(o.w) + fa_hi(o.w)));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&s_empty[b]);
+            fence_proxy_async();
+            mbar_arrive(&p_full[b]);
+        }
+        const float il = 1.f / l;
+        p.inv_l[grow] = il;
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.O + grow * DP;
+#pragma unroll 1
+        for (int ch = 0; ch < DP / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(t_row + kOCol + uint32_t(ch * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 o = make_uint4(fa_pack(__uint_as_float(v[8 * u]) * il, __uint_as_float(v[8 * u + 1]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 2]) * il, __uint_as_float(v[8 * u + 3]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 4]) * il, __uint_as_float(v[8 * u + 5]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 6]) * il, __uint_as_float(v[8 * u + 7]) * il));
+                *reinterpret_cast<uint4*>(orow + ch * 32 + u * 8) = o;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int DP>
+int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const float* rmax, float* inv_l,
+              __nv_bfloat16* O, int nb, int tq, int tkv, float scale, cudaStream_t st) {
+    CUtensorMap mq, mk, mv;
+    int rc;
+    cuuint32_t box[3] = {64, 128, 1};
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)DP, (cuuint64_t)tq, (cuuint64_t)nb};
+        cuuint64_t str[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tq * DP * 2};
+        if ((rc = encode_map_bf16_sw128(&mq, Q, 3, dims, str, box, "attn.fused.Q"))) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)DP, (cuuint64_t)tkv, (cuuint64_t)nb};
+        cuuint64_t str[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tkv * DP * 2};
+        if ((rc = encode_map_bf16_sw128(&mk, K, 3, dims, str, box, "attn.fused.K"))) return rc;
+        if ((rc = encode_map_bf16_sw128(&mv, V, 3, dims, str, box, "attn.fused.V"))) return rc;
+    }
+    constexpr int kChunk = 128 * 128;
+    constexpr size_t smem = size_t(DP / 64) * kChunk * 5 + 4 * kChunk + 256 + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(mh_attn_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("attn.fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+        attr_set[dev & 63] = true;
+    }
+    FaParams p;
+    p.rmax = rmax; p.inv_l = inv_l; p.O = O; p.tq = tq; p.tkv = tkv;
+    p.exp_scale = scale * 1.4426950408889634f;
+    mh_attn_fwd_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem, st>>>(mq, mk, mv, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("attn.fused: launch failed: %s", cudaGetErrorString(e)); return -5; }
+    count_launch();
+    return 0;
+}
+
+}  // namespace
+
+bool attn_fused_supported(int tq, int tkv, int dp) {
+    static const bool off = getenv("TML_NO_FUSED_ATTN") && getenv("TML_NO_FUSED_ATTN")[0] == '1';   // A/B switch
+    return !off && (dp == 64 || dp == 128) && tq % 128 == 0 && tkv % 128 == 0 && tkv >= 128;
+}
+
+// O[nb][tq][dp] = softmax(Q K^T * scale) V given the row maxima of Q K^T; inv_l[nb][tq] = 1 / row sums of P~
+int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
+                          int tq, int tkv, int dp, float scale, cudaStream_t st) {
+    if (g_dry_run) return 0;
+    if (!attn_fused_supported(tq, tkv, dp)) { set_error("attn.fused: unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
+    if (dp == 64) return launch_fa<64>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
+    return launch_fa<128>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
+}
+
+}  // namespace tml

@@ -1771,6 +1771,12 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     return 0;
 }
 
+// (attn_fused.cu) bf16 / SWIZZLE_128B tensor map through the same driver entry point
+int encode_map_bf16_sw128(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                          const cuuint32_t* box, const char* what) {
+    return encode_map(m, base, rank, dims, strides_b, box, what);
+}
+
 // "dynamic shared memory limit raised" flags, one per (device, kernel family): the attribute is per device
 static bool& attr_flag(int family) {
     static bool flags[2][64] = {};

@@ -114,6 +114,12 @@ void launch_small_linear(const float* x, const float* W, const float* bias, floa
 void launch_nchw_pack64(const float* x, bf16* out, int B, int C, int hw, cudaStream_t s);
 void launch_nhwc64_unpack(const bf16* in, float* out, int B, int C, int hw, cudaStream_t s);
 
+// fused attention forward (attn_fused.cu): O = softmax(Q K^T * scale) V per batch given the row maxima of Q K^T;
+// Q [nb][tq][dp], K / V [nb][tkv][dp] dense bf16, dp in {64, 128}, tq and tkv multiples of 128
+bool attn_fused_supported(int tq, int tkv, int dp);
+int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
+                          int tq, int tkv, int dp, float scale, cudaStream_t s);
+
 long kernel_launch_count();
 
 }  // namespace tml

@@ -345,10 +345,16 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
     if (np < 0) return np;
     float* part = r.Walloc<float>((size_t)rows * np * sizeof(float));
     if (rmax == nullptr) rmax = r.Walloc<float>((size_t)rows * sizeof(float));
-    if (P == nullptr) P = r.Walloc<bf16>((size_t)rows * tkv * sizeof(bf16));
     o.row_part = part;
     RC(gemm_launch(o, ns, r.st));
     launch_row_reduce(part, rmax, rows, np, 0, r.st);
+    if (P == nullptr && attn_fused_supported(tq, tkv, dp)) {
+        // fused: S, P~ and O never leave the SM (attn_fused.cu); the backward recomputes P~ from rmax
+        RC(launch_attn_fused_fwd(Q, K, V, rmax, inv_l, O, nb, tq, tkv, dp, scale, r.st));
+        r.wsa.reset(m);
+        return 0;
+    }
+    if (P == nullptr) P = r.Walloc<bf16>((size_t)rows * tkv * sizeof(bf16));
     RC(mh_probs(r, Q, K, rmax, part, P, nb, tq, tkv, dp, gh, gw, scale, "unet.attn.qk.exp"));
     launch_row_reduce(part, inv_l, rows, np, 1, r.st);
     bf16* Vt = r.Walloc<bf16>((size_t)nb * tkv * dp * sizeof(bf16));   // [nb][dp][tkv]
