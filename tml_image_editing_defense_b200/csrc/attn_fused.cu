@@ -266,6 +266,455 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     return 0;
 }
 
+
+// ================================================================================================
+// Fused backward.  Inputs: Q, K, V [nb][tok][DP]; dO' = dO / l (rows pre-scaled, bf16) and D' = (dO . O) / l from
+// attn_bwd_prep_kernel; the saved row maxima.  With P~ = exp2((s - m) * scale * log2 e) rounded to bf16 as in the forward:
+//     dP' = dO' V^T,   dS = P~ * (dP' - D') * scale,   dQ = dS K,   dK = dS^T Q,   dV = P~^T dO'
+// Two kernels, each recomputing S and dP' on the tensor cores so that nothing token x token is ever written:
+//   attn_bwd_dq_kernel   CTA = 128 query rows, loop over 64-key tiles:   S | dP' -> dS (smem) -> dQ += dS K
+//   attn_bwd_dkv_kernel  CTA = 128 key rows, loop over 64-query tiles:   S^T | dP'^T -> P~^T, dS^T (smem)
+//                                                                         -> dV += P~^T dO',  dK += dS^T Q
+// The K (resp. Q, dO') tile that serves as the K-major B operand of the logits is read a second time as the MN-major
+// B operand of the accumulating product: same bytes in shared memory, two descriptors.
+// ================================================================================================
+struct FbParams {
+    const float* rmax;    // [nb][tq]
+    const float* Dp;      // [nb][tq]  D' = (dO . O) / l
+    __nv_bfloat16* dQ;    // [nb][tq][DP]            (dq kernel)
+    __nv_bfloat16* dK;    // [nb][tkv][DP]           (dkv kernel)
+    __nv_bfloat16* dV;
+    int tq, tkv;
+    float exp_scale, scale;
+};
+
+// one warp per row: D'[row] = il * sum_c dO[row][c] * O[row][c];  dOs[row][c] = dO[row][c] * il
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO,
+                                                            const __nv_bfloat16* __restrict__ O,
+                                                            const float* __restrict__ inv_l, __nv_bfloat16* __restrict__ dOs,
+                                                            float* __restrict__ Dp, long long rows, int DP) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float il = __ldg(inv_l + row);
+    float acc = 0.f;
+    for (int o = lane; o < (DP >> 3); o += 32) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + row * DP) + o);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(O + row * DP) + o);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc = fmaf(fa_lo(aw[k]), fa_lo(bw[k]), acc);
+            acc = fmaf(fa_hi(aw[k]), fa_hi(bw[k]), acc);
+            ow[k] = fa_pack(fa_lo(aw[k]) * il, fa_hi(aw[k]) * il);
+        }
+        reinterpret_cast<uint4*>(dOs + row * DP)[o] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) Dp[row] = acc * il;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                   const __grid_constant__ CUtensorMap mapDO,
+                                                                   const __grid_constant__ CUtensorMap mapK,
+                                                                   const __grid_constant__ CUtensorMap mapV,
+                                                                   const FbParams p) {
+    constexpr int NC = DP / 64;
+    constexpr int kBig = 128 * 128, kSmall = 64 * 128;    // [128 rows][128 B], [64 rows][128 B]
+    constexpr int kQBytes = NC * kBig, kKBytes = NC * kSmall;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sDO = sQ + kQBytes;
+    uint8_t* sK = sDO + kQBytes;                // 2 stages
+    uint8_t* sV = sK + 2 * kKBytes;             // 2 stages
+    uint8_t* sDS = sV + 2 * kKBytes;            // 2 buffers of [128 rows][64 keys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBig);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 3;
+    uint64_t* sd_full = bars + 5;
+    uint64_t* sd_empty = bars + 7;
+    uint64_t* ds_full = bars + 9;
+    uint64_t* ds_empty = bars + 11;
+    uint64_t* acc_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, batch = blockIdx.y;
+    const int ntiles = p.tkv / 64;
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], 128);
+            mbar_init(&ds_full[i], 128); mbar_init(&ds_empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kAccCol = 256;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * kQBytes);
+            for (int c = 0; c < NC; ++c) {
+                tma_load_3d(sQ + c * kBig, &mapQ, q_full, c * 64, q0, batch);
+                tma_load_3d(sDO + c * kBig, &mapDO, q_full, c * 64, q0, batch);
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&kv_full[s], 2 * kKBytes);
+                for (int c = 0; c < NC; ++c) {
+                    tma_load_3d(sK + s * kKBytes + c * kSmall, &mapK, &kv_full[s], c * 64, j * 64, batch);
+                    tma_load_3d(sV + s * kKBytes + c * kSmall, &mapV, &kv_full[s], c * 64, j * 64, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, 64);
+        const uint32_t idesc_a = umma_idesc_bf16(128, DP) | kUmmaBMajorMN;
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        auto issue_acc = [&](int j) {
+            const int s = j & 1, b = j & 1;
+            mbar_wait(&ds_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t da = smem_u32(sDS + b * kBig), ka = smem_u32(sK + s * kKBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)   // dQ += dS K: 4 x 16 keys; K tile [key][channel] read MN-major
+                    umma_bf16(tmem_base + kAccCol, umma_desc_sw128(da) + uint64_t(kk * 2),
+                              umma_desc_sw128_mn(ka + kk * 2048, kSmall, 1024), idesc_a, (j | kk) != 0 ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                umma_commit(&ds_empty[b]);
+            }
+            __syncwarp();
+        };
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j & 1, b = j & 1;
+            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            mbar_wait(&sd_empty[b], (((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), oa = smem_u32(sDO), ka = smem_u32(sK + s * kKBytes), va = smem_u32(sV + s * kKBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(qa + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(ka + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + uint32_t(b * 128 + 64), umma_desc_sw128(oa + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(va + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                    }
+                umma_commit(&sd_full[b]);
+            }
+            __syncwarp();
+            if (j > 0) issue_acc(j - 1);
+        }
+        issue_acc(ntiles - 1);
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const long long grow = (long long)batch * p.tq + q0 + row;
+        const float c = p.exp_scale, sc = p.scale;
+        const float ra = -__ldg(p.rmax + grow) * c;
+        const float dpr = __ldg(p.Dp + grow);
+        const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
+        for (int j = 0; j < ntiles; ++j) {
+            const int b = j & 1;
+            mbar_wait(&sd_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            mbar_wait(&ds_empty[b], (((j >> 1) & 1) ^ 1));
+            uint8_t* drow = sDS + b * kBig + row * 128;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t vs[32], vd[32];
+                tmem_ld32(t_row + uint32_t(b * 128 + ch * 32), vs);
+                tmem_ld32(t_row + uint32_t(b * 128 + 64 + ch * 32), vd);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = 8 * u + 2 * k;
+                        const uint32_t pp = fa_pack(fa_ex2(fmaf(__uint_as_float(vs[i]), c, ra)),
+                                                    fa_ex2(fmaf(__uint_as_float(vs[i + 1]), c, ra)));
+                        w[k] = fa_pack(fa_lo(pp) * ((__uint_as_float(vd[i]) - dpr) * sc),
+                                       fa_hi(pp) * ((__uint_as_float(vd[i + 1]) - dpr) * sc));
+                    }
+                    const int unit = ch * 4 + u;
+                    *reinterpret_cast<uint4*>(drow + ((unit ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sd_empty[b]);
+            fence_proxy_async();
+            mbar_arrive(&ds_full[b]);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.dQ + grow * DP;
+#pragma unroll 1
+        for (int ch = 0; ch < DP / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(t_row + kAccCol + uint32_t(ch * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(orow + ch * 32 + u * 8) =
+                    make_uint4(fa_pack(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                               fa_pack(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                               fa_pack(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                               fa_pack(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK,
+                                                                    const __grid_constant__ CUtensorMap mapV,
+                                                                    const __grid_constant__ CUtensorMap mapQ,
+                                                                    const __grid_constant__ CUtensorMap mapDO,
+                                                                    const FbParams p) {
+    constexpr int NC = DP / 64;
+    constexpr int kBig = 128 * 128, kSmall = 64 * 128;
+    constexpr int kKBytes = NC * kBig, kQBytes = NC * kSmall;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + kKBytes;
+    uint8_t* sQ = sV + kKBytes;                 // 2 stages of [64 queries][DP]
+    uint8_t* sDO = sQ + 2 * kQBytes;            // 2 stages
+    uint8_t* sPT = sDO + 2 * kQBytes;           // 2 buffers of [128 keys][64 queries]
+    uint8_t* sDST = sPT + 2 * kBig;             // 2 buffers
+    float2* cvec = reinterpret_cast<float2*>(sDST + 2 * kBig);   // [2][64] (-m*c, D') of the tile's queries
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + 128);
+    uint64_t* kv_full = bars;
+    uint64_t* qd_full = bars + 1;
+    uint64_t* qd_empty = bars + 3;
+    uint64_t* sd_full = bars + 5;
+    uint64_t* sd_empty = bars + 7;
+    uint64_t* pd_full = bars + 9;
+    uint64_t* pd_empty = bars + 11;
+    uint64_t* acc_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, batch = blockIdx.y;
+    const int ntiles = p.tq / 64;
+    if (threadIdx.x == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
+            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], 128);
+            mbar_init(&pd_full[i], 128); mbar_init(&pd_empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kDvCol = 256, kDkCol = 256 + DP;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * kKBytes);
+            for (int c = 0; c < NC; ++c) {
+                tma_load_3d(sK + c * kBig, &mapK, kv_full, c * 64, k0, batch);
+                tma_load_3d(sV + c * kBig, &mapV, kv_full, c * 64, k0, batch);
+            }
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1;
+                mbar_wait(&qd_empty[s], (((i >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&qd_full[s], 2 * kQBytes);
+                for (int c = 0; c < NC; ++c) {
+                    tma_load_3d(sQ + s * kQBytes + c * kSmall, &mapQ, &qd_full[s], c * 64, i * 64, batch);
+                    tma_load_3d(sDO + s * kQBytes + c * kSmall, &mapDO, &qd_full[s], c * 64, i * 64, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, 64);
+        const uint32_t idesc_a = umma_idesc_bf16(128, DP) | kUmmaBMajorMN;
+        mbar_wait(kv_full, 0);
+        tc_fence_after();
+        auto issue_acc = [&](int i) {
+            const int s = i & 1, b = i & 1;
+            mbar_wait(&pd_full[b], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sPT + b * kBig), da = smem_u32(sDST + b * kBig);
+            const uint32_t qa = smem_u32(sQ + s * kQBytes), oa = smem_u32(sDO + s * kQBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {   // 4 x 16 queries; dO' and Q tiles [query][channel] read MN-major
+                    umma_bf16(tmem_base + kDvCol, umma_desc_sw128(pa) + uint64_t(kk * 2),
+                              umma_desc_sw128_mn(oa + kk * 2048, kSmall, 1024), idesc_a, (i | kk) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base + kDkCol, umma_desc_sw128(da) + uint64_t(kk * 2),
+                              umma_desc_sw128_mn(qa + kk * 2048, kSmall, 1024), idesc_a, (i | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&qd_empty[s]);
+                umma_commit(&pd_empty[b]);
+            }
+            __syncwarp();
+        };
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i & 1, b = i & 1;
+            mbar_wait(&qd_full[s], (i >> 1) & 1);
+            mbar_wait(&sd_empty[b], (((i >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQ + s * kQBytes), oa = smem_u32(sDO + s * kQBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // S^T = K Q^T and dP'^T = V dO'^T: 128 keys x 64 queries
+                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(ka + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(qa + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + uint32_t(b * 128 + 64), umma_desc_sw128(va + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(oa + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                    }
+                umma_commit(&sd_full[b]);
+            }
+            __syncwarp();
+            if (i > 0) issue_acc(i - 1);
+        }
+        issue_acc(ntiles - 1);
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;          // key row of this thread
+        const int st = threadIdx.x - 64;           // 0..127 among the softmax threads
+        const long long gkey = (long long)batch * p.tkv + k0 + row;
+        const float c = p.exp_scale, sc = p.scale;
+        const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            if (st < 64) {   // this tile's per-query constants (buffer b was last read two tiles ago, before a barrier)
+                const long long gq = (long long)batch * p.tq + i * 64 + st;
+                cvec[b * 64 + st] = make_float2(-__ldg(p.rmax + gq) * c, __ldg(p.Dp + gq));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&sd_full[b], (i >> 1) & 1);
+            tc_fence_after();
+            mbar_wait(&pd_empty[b], (((i >> 1) & 1) ^ 1));
+            uint8_t* prow = sPT + b * kBig + row * 128;
+            uint8_t* drow = sDST + b * kBig + row * 128;
+            const float2* cv = cvec + b * 64;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t vs[32], vd[32];
+                tmem_ld32(t_row + uint32_t(b * 128 + ch * 32), vs);
+                tmem_ld32(t_row + uint32_t(b * 128 + 64 + ch * 32), vd);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t wp[4], wd[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i2 = 8 * u + 2 * k;
+                        const float2 c0 = cv[ch * 32 + i2], c1 = cv[ch * 32 + i2 + 1];
+                        const uint32_t pp = fa_pack(fa_ex2(fmaf(__uint_as_float(vs[i2]), c, c0.x)),
+                                                    fa_ex2(fmaf(__uint_as_float(vs[i2 + 1]), c, c1.x)));
+                        wp[k] = pp;
+                        wd[k] = fa_pack(fa_lo(pp) * ((__uint_as_float(vd[i2]) - c0.y) * sc),
+                                        fa_hi(pp) * ((__uint_as_float(vd[i2 + 1]) - c1.y) * sc));
+                    }
+                    const int unit = ch * 4 + u;
+                    const int off = (unit ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+                    *reinterpret_cast<uint4*>(drow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sd_empty[b]);
+            fence_proxy_async();
+            mbar_arrive(&pd_full[b]);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            __nv_bfloat16* orow = (which ? p.dK : p.dV) + gkey * DP;
+            const uint32_t col0 = which ? kDkCol : kDvCol;
+#pragma unroll 1
+            for (int ch = 0; ch < DP / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(t_row + col0 + uint32_t(ch * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(orow + ch * 32 + u * 8) =
+                        make_uint4(fa_pack(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                                   fa_pack(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                                   fa_pack(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                                   fa_pack(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int DP>
+int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const __nv_bfloat16* dOs,
+              const float* rmax, const float* Dp, __nv_bfloat16* dQ, __nv_bfloat16* dK, __nv_bfloat16* dV, int nb, int tq,
+              int tkv, float scale, cudaStream_t st) {
+    CUtensorMap mq128, mo128, mk64, mv64, mk128, mv128, mq64, mo64;
+    int rc;
+    cuuint32_t box128[3] = {64, 128, 1}, box64[3] = {64, 64, 1};
+    cuuint64_t dq[3] = {(cuuint64_t)DP, (cuuint64_t)tq, (cuuint64_t)nb}, sq[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tq * DP * 2};
+    cuuint64_t dk[3] = {(cuuint64_t)DP, (cuuint64_t)tkv, (cuuint64_t)nb}, sk[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tkv * DP * 2};
+    if ((rc = encode_map_bf16_sw128(&mq128, Q, 3, dq, sq, box128, "attn.bwd.Q"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mo128, dOs, 3, dq, sq, box128, "attn.bwd.dO"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mq64, Q, 3, dq, sq, box64, "attn.bwd.Q64"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mo64, dOs, 3, dq, sq, box64, "attn.bwd.dO64"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mk128, K, 3, dk, sk, box128, "attn.bwd.K"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mv128, V, 3, dk, sk, box128, "attn.bwd.V"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mk64, K, 3, dk, sk, box64, "attn.bwd.K64"))) return rc;
+    if ((rc = encode_map_bf16_sw128(&mv64, V, 3, dk, sk, box64, "attn.bwd.V64"))) return rc;
+    constexpr int NC = DP / 64, kBig = 128 * 128, kSmall = 64 * 128;
+    constexpr size_t smem_dq = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 256 + 1024;
+    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 4 * kBig + 1024 + 256 + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv);
+        if (e != cudaSuccess) { set_error("attn.bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
+        attr_set[dev & 63] = true;
+    }
+    FbParams p;
+    p.rmax = rmax; p.Dp = Dp; p.dQ = dQ; p.dK = dK; p.dV = dV; p.tq = tq; p.tkv = tkv;
+    p.scale = scale; p.exp_scale = scale * 1.4426950408889634f;
+    attn_bwd_dq_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem_dq, st>>>(mq128, mo128, mk64, mv64, p);
+    attn_bwd_dkv_kernel<DP><<<dim3(tkv / 128, nb), kFaThreads, smem_dkv, st>>>(mk128, mv128, mq64, mo64, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("attn.bwd: launch failed: %s", cudaGetErrorString(e)); return -5; }
+    count_launch();
+    count_launch();
+    return 0;
+}
+
 }  // namespace
 
 bool attn_fused_supported(int tq, int tkv, int dp) {
@@ -280,6 +729,20 @@ int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const flo
     if (!attn_fused_supported(tq, tkv, dp)) { set_error("attn.fused: unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
     if (dp == 64) return launch_fa<64>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
     return launch_fa<128>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
+}
+
+// Fused backward of the same attention: dO [nb][tq][dp], O, inv_l, rmax from the forward; dOs (bf16 [nb][tq][dp]) and
+// Dp (fp32 [nb][tq]) are scratch.  Writes dQ [nb][tq][dp], dK and dV [nb][tkv][dp].
+int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf16* O, const bf16* dO, const float* rmax,
+                          const float* inv_l, bf16* dOs, float* Dp, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv,
+                          int dp, float scale, cudaStream_t st) {
+    if (g_dry_run) return 0;
+    if (!attn_fused_supported(tq, tkv, dp)) { set_error("attn.bwd: unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
+    const long long rows = (long long)nb * tq;
+    attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dO, O, inv_l, dOs, Dp, rows, dp);
+    count_launch();
+    if (dp == 64) return launch_fb<64>(Q, K, V, dOs, rmax, Dp, dQ, dK, dV, nb, tq, tkv, scale, st);
+    return launch_fb<128>(Q, K, V, dOs, rmax, Dp, dQ, dK, dV, nb, tq, tkv, scale, st);
 }
 
 }  // namespace tml

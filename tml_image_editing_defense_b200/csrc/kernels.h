@@ -120,6 +120,10 @@ bool attn_fused_supported(int tq, int tkv, int dp);
 int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
                           int tq, int tkv, int dp, float scale, cudaStream_t s);
 
+int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf16* O, const bf16* dO, const float* rmax,
+                          const float* inv_l, bf16* dOs, float* Dp, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv,
+                          int dp, float scale, cudaStream_t s);
+
 long kernel_launch_count();
 
 }  // namespace tml

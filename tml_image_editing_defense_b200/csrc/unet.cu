@@ -375,6 +375,15 @@ int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, 
     int gh = 0, gw = 0;
     RC(attn_grid(tq, &gh, &gw));
     const size_t m = r.wsa.mark();
+    static const bool no_fused_bwd = getenv("TML_NO_FUSED_ATTN_BWD") && getenv("TML_NO_FUSED_ATTN_BWD")[0] == '1';   // A/B switch
+    if (P == nullptr && dK != nullptr && dV != nullptr && !no_fused_bwd && attn_fused_supported(tq, tkv, dp)) {
+        // fused (attn_fused.cu): S and dP are recomputed on the tensor cores inside the two backward kernels
+        bf16* dOs = r.Walloc<bf16>((size_t)rows * dp * sizeof(bf16));
+        float* Dp = r.Walloc<float>((size_t)rows * sizeof(float));
+        RC(launch_attn_fused_bwd(Q, K, V, O, dO, rmax, inv_l, dOs, Dp, dQ, dK, dV, nb, tq, tkv, dp, scale, r.st));
+        r.wsa.reset(m);
+        return 0;
+    }
     if (P == nullptr) {   // not kept by the forward: the same GEMM + epilogue gives the same bits again
         GemmOp o = mh_logits_op("unet.attn.qk.exp", Q, K, nb, tq, tkv, dp, gh, gw);
         o.epi_mode = 2;
