@@ -6,9 +6,10 @@
 //     warp 0   TMA producer: Q once, then K and V tiles into a two-stage ring (128-byte swizzle)
 //     warp 1   tcgen05.mma issuer: S = Q K^T into one of two TMEM buffers (128 columns each), and, one tile behind,
 //              O += P~ V with P~ read from shared memory and V read as an MN-major operand (no transposed copy)
-//     warps 2-5  softmax, thread = query row: tcgen05.ld of S, P~ = exp2((s - rowmax) * scale * log2 e) with the row
-//              maxima of the preceding max pass (so no accumulator rescaling is ever needed), bf16 P~ written into the
-//              swizzled K-major operand tile the PV MMA reads, row sums of the values as stored
+//     warps 2-9  softmax, thread = (query row, half of the tile's keys; two warps per SM sub-partition -- with one the
+//              exp / pack chain is latency-bound): tcgen05.ld of S, P~ = exp2((s - rowmax) * scale * log2 e) with the
+//              row maxima of the preceding max pass (so no accumulator rescaling is ever needed), bf16 P~ written into
+//              the swizzled K-major operand tile the PV MMA reads, row sums of the values as stored
 //   TMEM: S[0] | S[1] | O (DP columns); epilogue: O / l -> bf16, 1 / l -> fp32 (kept for the backward).
 //
 // The numbers are those of the unfused path (same MMA shapes for S, same exp2 form, same bf16 rounding of P~), which
@@ -32,7 +33,8 @@ int encode_map_bf16_sw128(CUtensorMap* m, const void* base, int rank, const cuui
 
 namespace {
 
-constexpr int kFaThreads = 192;
+constexpr int kFaThreads = 320;   // TMA warp, MMA warp, 8 softmax warps (two per SM sub-partition: column halves of a row)
+constexpr int kSmThreads = 256;
 constexpr uint32_t kUmmaBMajorMN = 1u << 16;
 
 struct FaParams {
@@ -40,6 +42,7 @@ struct FaParams {
     float* inv_l;         // [nb][tq]
     __nv_bfloat16* O;     // [nb][tq][DP]
     int tq, tkv;
+    int lcol;             // channel of V that holds 1.0 for every key: O[:, lcol] accumulates the softmax denominator
     float exp_scale;      // scale * log2(e)
 };
 
@@ -56,25 +59,25 @@ __device__ __forceinline__ float fa_lo(uint32_t u) { return __uint_as_float(u <<
 __device__ __forceinline__ float fa_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 template <int DP>
-__global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ,
+__global__ void __launch_bounds__(kFaThreads, 2) mh_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ,
                                                                    const __grid_constant__ CUtensorMap mapK,
                                                                    const __grid_constant__ CUtensorMap mapV,
                                                                    const FaParams p) {
     constexpr int NC = DP / 64;                 // 64-channel chunks of the head width
-    constexpr int kChunk = 128 * 128;           // [128 rows][128 B] = 16 KB
-    constexpr int kQBytes = NC * kChunk, kKBytes = NC * kChunk, kVBytes = NC * kChunk, kPBytes = 2 * kChunk;
+    constexpr int kBig = 128 * 128, kSmall = 64 * 128;   // [128 rows][128 B], [64 rows][128 B]
+    constexpr int kQBytes = NC * kBig, kKBytes = NC * kSmall;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + kQBytes;                 // 2 stages
+    uint8_t* sK = sQ + kQBytes;                 // 2 stages of [64 keys][DP]
     uint8_t* sV = sK + 2 * kKBytes;             // 2 stages
-    uint8_t* sP = sV + 2 * kVBytes;             // 2 buffers
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint8_t* sP = sV + 2 * kKBytes;             // 2 buffers of [128 rows][64 keys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kBig);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;               // [2]
     uint64_t* kv_empty = bars + 3;              // [2]
-    uint64_t* s_full = bars + 5;                // [2]
-    uint64_t* s_empty = bars + 7;               // [2]
+    uint64_t* s_full = bars + 5;                // [1]
+    uint64_t* s_empty = bars + 7;               // [1]
     uint64_t* p_full = bars + 9;                // [2]
     uint64_t* p_empty = bars + 11;              // [2]
     uint64_t* o_full = bars + 13;
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, batch = blockIdx.y;
-    const int ntiles = p.tkv / 128;
+    const int ntiles = p.tkv / 64;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -90,38 +93,40 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 128);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&s_empty[i], kSmThreads);
+            mbar_init(&p_full[i], kSmThreads);
             mbar_init(&p_empty[i], 1);
         }
         mbar_init(o_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    // 256 TMEM columns (S: 64, freed by the softmax warps as soon as it is in registers; O: DP) and 80 KB of shared
+    // memory at DP = 64: two CTAs share an SM and fill each other's pipeline bubbles (prologue, barrier round trips)
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kOCol = 256;
+    constexpr uint32_t kOCol = 64;
 
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, kQBytes);
-            for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * kChunk, &mapQ, q_full, c * 64, q0, batch);
+            for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * kBig, &mapQ, q_full, c * 64, q0, batch);
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j & 1;
                 mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
-                mbar_arrive_expect_tx(&kv_full[s], kKBytes + kVBytes);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * kKBytes);
                 for (int c = 0; c < NC; ++c) {
-                    tma_load_3d(sK + s * kKBytes + c * kChunk, &mapK, &kv_full[s], c * 64, j * 128, batch);
-                    tma_load_3d(sV + s * kVBytes + c * kChunk, &mapV, &kv_full[s], c * 64, j * 128, batch);
+                    tma_load_3d(sK + s * kKBytes + c * kSmall, &mapK, &kv_full[s], c * 64, j * 64, batch);
+                    tma_load_3d(sV + s * kKBytes + c * kSmall, &mapV, &kv_full[s], c * 64, j * 64, batch);
                 }
             }
         }
     } else if (warp == 1) {
-        // S = Q K^T: M = 128 queries, N = 128 keys, K = DP (both operands K-major)
-        const uint32_t idesc_s = umma_idesc_bf16(128, 128);
-        // O += P V: M = 128 queries, N = DP channels, K = 128 keys; V tile [key][channel] is the MN-major B operand
+        // S = Q K^T: M = 128 queries, N = 64 keys, K = DP (both operands K-major)
+        const uint32_t idesc_s = umma_idesc_bf16(128, 64);
+        // O += P V: M = 128 queries, N = DP channels, K = 64 keys; V tile [key][channel] is the MN-major B operand
         const uint32_t idesc_o = umma_idesc_bf16(128, DP) | kUmmaBMajorMN;
         mbar_wait(q_full, 0);
         tc_fence_after();
@@ -129,24 +134,22 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
             const int s = j & 1, b = j & 1;
             mbar_wait(&p_full[b], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP + b * kPBytes), va = smem_u32(sV + s * kVBytes);
+            const uint32_t pa = smem_u32(sP + b * kBig), va = smem_u32(sV + s * kKBytes);
             if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {   // 8 x 16 keys
-                    const uint64_t a_desc = umma_desc_sw128(pa + (kk >> 2) * kChunk) + uint64_t((kk & 3) * 2);
-                    // MN-major: channel atoms (64) kChunk apart, groups of 8 keys 1 KB apart; 16 keys = 2 KB per step
-                    const uint64_t b_desc = umma_desc_sw128_mn(va + kk * 2048, kChunk, 1024);
-                    umma_bf16(tmem_base + kOCol, a_desc, b_desc, idesc_o, (j | kk) != 0 ? 1u : 0u);
-                }
+                for (int kk = 0; kk < 4; ++kk)   // 4 x 16 keys
+                    // MN-major: channel atoms (64) kSmall apart, groups of 8 keys 1 KB apart; 16 keys = 2 KB per step
+                    umma_bf16(tmem_base + kOCol, umma_desc_sw128(pa) + uint64_t(kk * 2),
+                              umma_desc_sw128_mn(va + kk * 2048, kSmall, 1024), idesc_o, (j | kk) != 0 ? 1u : 0u);
                 umma_commit(&kv_empty[s]);
                 umma_commit(&p_empty[b]);
             }
             __syncwarp();
         };
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j & 1, b = j & 1;
+            const int s = j & 1;
             mbar_wait(&kv_full[s], (j >> 1) & 1);
-            mbar_wait(&s_empty[b], (((j >> 1) & 1) ^ 1));
+            mbar_wait(&s_empty[0], ((j & 1) ^ 1));
             tc_fence_after();
             const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + s * kKBytes);
             if (elect_one()) {
@@ -154,9 +157,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(qa + c * kChunk) + uint64_t(kk * 2),
-                                  umma_desc_sw128(ka + c * kChunk) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
-                umma_commit(&s_full[b]);
+                        umma_bf16(tmem_base, umma_desc_sw128(qa + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(ka + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                umma_commit(&s_full[0]);
             }
             __syncwarp();
             if (j > 0) issue_pv(j - 1);
@@ -165,52 +168,54 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
         if (elect_one()) umma_commit(o_full);
         __syncwarp();
     } else {
-        // ===================================================================== softmax warps (thread = query row)
-        const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+        // ===================================================================== softmax warps
+        // thread = (query row, 32-key half of the tile): warps w and w + 4 share a TMEM lane quadrant
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const long long grow = (long long)batch * p.tq + q0 + row;
         const float c = p.exp_scale;
         const float ra = -__ldg(p.rmax + grow) * c;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
-        float l = 0.f;
         for (int j = 0; j < ntiles; ++j) {
             const int b = j & 1;
-            mbar_wait(&s_full[b], (j >> 1) & 1);
+            mbar_wait(&s_full[0], j & 1);
             tc_fence_after();
-            mbar_wait(&p_empty[b], (((j >> 1) & 1) ^ 1));
-            uint8_t* prow = sP + b * kPBytes + row * 128;
             uint32_t v[32];
-            tmem_ld32(t_row + uint32_t(b * 128), v);
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                tmem_ld_wait();
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = fa_ex2(fmaf(__uint_as_float(v[i]), c, ra));
-                if (ch < 3) tmem_ld32(t_row + uint32_t(b * 128 + (ch + 1) * 32), v);
-                uint8_t* dst = prow + (ch >> 1) * kChunk;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 o = make_uint4(fa_pack(f[8 * u], f[8 * u + 1]), fa_pack(f[8 * u + 2], f[8 * u + 3]),
-                                               fa_pack(f[8 * u + 4], f[8 * u + 5]), fa_pack(f[8 * u + 6], f[8 * u + 7]));
-                    const int unit = (ch & 1) * 4 + u;
-                    *reinterpret_cast<uint4*>(dst + ((unit ^ (row & 7)) << 4)) = o;
-                    l += ((fa_lo(o.x) + fa_hi(o.x)) + (fa_lo(o.y) + fa_hi(o.y))) +
-                         ((fa_lo(o.z) + fa_hi(o.z)) + (fa_lo(o.w) + fa_hi(o.w)));
-                }
-            }
+            tmem_ld32(t_row + uint32_t(half * 32), v);
+            tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&s_empty[b]);
+            mbar_arrive(&s_empty[0]);   // S is in registers: the next tile's logits may overwrite it
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fa_ex2(fmaf(__uint_as_float(v[i]), c, ra));
+            mbar_wait(&p_empty[b], (((j >> 1) & 1) ^ 1));
+            uint8_t* dst = sP + b * kBig + row * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 o = make_uint4(fa_pack(f[8 * u], f[8 * u + 1]), fa_pack(f[8 * u + 2], f[8 * u + 3]),
+                                           fa_pack(f[8 * u + 4], f[8 * u + 5]), fa_pack(f[8 * u + 6], f[8 * u + 7]));
+                const int unit = half * 4 + u;
+                *reinterpret_cast<uint4*>(dst + ((unit ^ (row & 7)) << 4)) = o;
+            }
             fence_proxy_async();
             mbar_arrive(&p_full[b]);
         }
-        const float il = 1.f / l;
-        p.inv_l[grow] = il;
+        // The softmax denominator is a column of O: channel `lcol` of V is 1.0 for every key (a padding channel of the
+        // head), so the tensor cores sum the probabilities exactly as they are stored (bf16), in fp32, for free.
         mbar_wait(o_full, 0);
         tc_fence_after();
+        float l;
+        {
+            uint32_t v8[8];
+            tmem_ld8(t_row + kOCol + uint32_t(p.lcol & ~7), v8);
+            tmem_ld_wait();
+            l = __uint_as_float(v8[p.lcol & 7]);
+        }
+        const float il = 1.f / l;
+        if (half == 0) p.inv_l[grow] = il;
         __nv_bfloat16* orow = p.O + grow * DP;
 #pragma unroll 1
-        for (int ch = 0; ch < DP / 32; ++ch) {
+        for (int ch = half * (DP / 64); ch < (half + 1) * (DP / 64); ++ch) {
             uint32_t v[32];
             tmem_ld32(t_row + kOCol + uint32_t(ch * 32), v);
             tmem_ld_wait();
@@ -226,15 +231,15 @@ __global__ void __launch_bounds__(kFaThreads, 1) mh_attn_fwd_kernel(const __grid
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 template <int DP>
 int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const float* rmax, float* inv_l,
-              __nv_bfloat16* O, int nb, int tq, int tkv, float scale, cudaStream_t st) {
+              __nv_bfloat16* O, int nb, int tq, int tkv, int lcol, float scale, cudaStream_t st) {
     CUtensorMap mq, mk, mv;
     int rc;
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, 128, 1}, box64[3] = {64, 64, 1};
     {
         cuuint64_t dims[3] = {(cuuint64_t)DP, (cuuint64_t)tq, (cuuint64_t)nb};
         cuuint64_t str[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tq * DP * 2};
@@ -243,11 +248,11 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     {
         cuuint64_t dims[3] = {(cuuint64_t)DP, (cuuint64_t)tkv, (cuuint64_t)nb};
         cuuint64_t str[2] = {(cuuint64_t)DP * 2, (cuuint64_t)tkv * DP * 2};
-        if ((rc = encode_map_bf16_sw128(&mk, K, 3, dims, str, box, "attn.fused.K"))) return rc;
-        if ((rc = encode_map_bf16_sw128(&mv, V, 3, dims, str, box, "attn.fused.V"))) return rc;
+        if ((rc = encode_map_bf16_sw128(&mk, K, 3, dims, str, box64, "attn.fused.K"))) return rc;
+        if ((rc = encode_map_bf16_sw128(&mv, V, 3, dims, str, box64, "attn.fused.V"))) return rc;
     }
-    constexpr int kChunk = 128 * 128;
-    constexpr size_t smem = size_t(DP / 64) * kChunk * 5 + 4 * kChunk + 256 + 1024;
+    constexpr int kBig = 128 * 128, kSmall = 64 * 128;
+    constexpr size_t smem = size_t(DP / 64) * (kBig + 4 * kSmall) + 2 * kBig + 256 + 1024;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -257,7 +262,7 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
         attr_set[dev & 63] = true;
     }
     FaParams p;
-    p.rmax = rmax; p.inv_l = inv_l; p.O = O; p.tq = tq; p.tkv = tkv;
+    p.rmax = rmax; p.inv_l = inv_l; p.O = O; p.tq = tq; p.tkv = tkv; p.lcol = lcol;
     p.exp_scale = scale * 1.4426950408889634f;
     mh_attn_fwd_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem, st>>>(mq, mk, mv, p);
     cudaError_t e = cudaGetLastError();
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
 }
 
 template <int DP>
-__global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ,
+__global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ,
                                                                    const __grid_constant__ CUtensorMap mapDO,
                                                                    const __grid_constant__ CUtensorMap mapK,
                                                                    const __grid_constant__ CUtensorMap mapV,
@@ -349,18 +354,20 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], 128);
-            mbar_init(&ds_full[i], 128); mbar_init(&ds_empty[i], 1);
+            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], kSmThreads);
+            mbar_init(&ds_full[i], kSmThreads); mbar_init(&ds_empty[i], 1);
         }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    // 256 TMEM columns (S | dP' single-buffered: the softmax warps free them as soon as they are in registers, + dQ) and
+    // ~100 KB of shared memory: two CTAs share an SM and fill each other's pipeline bubbles
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kAccCol = 256;
+    constexpr uint32_t kAccCol = 128;
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, 2 * kQBytes);
@@ -399,9 +406,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
             __syncwarp();
         };
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j & 1, b = j & 1;
+            const int s = j & 1;
             mbar_wait(&kv_full[s], (j >> 1) & 1);
-            mbar_wait(&sd_empty[b], (((j >> 1) & 1) ^ 1));
+            mbar_wait(&sd_empty[0], ((j & 1) ^ 1));
             tc_fence_after();
             const uint32_t qa = smem_u32(sQ), oa = smem_u32(sDO), ka = smem_u32(sK + s * kKBytes), va = smem_u32(sV + s * kKBytes);
             if (elect_one()) {
@@ -409,12 +416,12 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(qa + c * kBig) + uint64_t(kk * 2),
+                        umma_bf16(tmem_base, umma_desc_sw128(qa + c * kBig) + uint64_t(kk * 2),
                                   umma_desc_sw128(ka + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
-                        umma_bf16(tmem_base + uint32_t(b * 128 + 64), umma_desc_sw128(oa + c * kBig) + uint64_t(kk * 2),
+                        umma_bf16(tmem_base + 64u, umma_desc_sw128(oa + c * kBig) + uint64_t(kk * 2),
                                   umma_desc_sw128(va + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
                     }
-                umma_commit(&sd_full[b]);
+                umma_commit(&sd_full[0]);
             }
             __syncwarp();
             if (j > 0) issue_acc(j - 1);
@@ -423,42 +430,37 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
         if (elect_one()) umma_commit(acc_full);
         __syncwarp();
     } else {
-        const int quad = warp & 3;
+        const int quad = warp & 3, half = (warp - 2) >> 2;   // thread = (query row, 32-key half of the tile)
         const int row = quad * 32 + lane;
         const long long grow = (long long)batch * p.tq + q0 + row;
         const float c = p.exp_scale, sc = p.scale;
         const float ra = -__ldg(p.rmax + grow) * c;
-        const float dpr = __ldg(p.Dp + grow);
+        const float dpr = -__ldg(p.Dp + grow) * sc;   // dS = P~ * (dP' * scale - D' * scale)
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
         for (int j = 0; j < ntiles; ++j) {
             const int b = j & 1;
-            mbar_wait(&sd_full[b], (j >> 1) & 1);
+            mbar_wait(&sd_full[0], j & 1);
             tc_fence_after();
-            mbar_wait(&ds_empty[b], (((j >> 1) & 1) ^ 1));
             uint8_t* drow = sDS + b * kBig + row * 128;
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t vs[32], vd[32];
-                tmem_ld32(t_row + uint32_t(b * 128 + ch * 32), vs);
-                tmem_ld32(t_row + uint32_t(b * 128 + 64 + ch * 32), vd);
-                tmem_ld_wait();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = 8 * u + 2 * k;
-                        const uint32_t pp = fa_pack(fa_ex2(fmaf(__uint_as_float(vs[i]), c, ra)),
-                                                    fa_ex2(fmaf(__uint_as_float(vs[i + 1]), c, ra)));
-                        w[k] = fa_pack(fa_lo(pp) * ((__uint_as_float(vd[i]) - dpr) * sc),
-                                       fa_hi(pp) * ((__uint_as_float(vd[i + 1]) - dpr) * sc));
-                    }
-                    const int unit = ch * 4 + u;
-                    *reinterpret_cast<uint4*>(drow + ((unit ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
+            uint32_t vs[32], vd[32];
+            tmem_ld32(t_row + uint32_t(half * 32), vs);
+            tmem_ld32(t_row + uint32_t(64 + half * 32), vd);
+            tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&sd_empty[b]);
+            mbar_arrive(&sd_empty[0]);   // the accumulators are in registers: the next S | dP' may overwrite them
+            mbar_wait(&ds_empty[b], (((j >> 1) & 1) ^ 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 8 * u + 2 * k;
+                    w[k] = fa_pack(fa_ex2(fmaf(__uint_as_float(vs[i]), c, ra)) * fmaf(__uint_as_float(vd[i]), sc, dpr),
+                                   fa_ex2(fmaf(__uint_as_float(vs[i + 1]), c, ra)) * fmaf(__uint_as_float(vd[i + 1]), sc, dpr));
+                }
+                const int unit = half * 4 + u;
+                *reinterpret_cast<uint4*>(drow + ((unit ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
             fence_proxy_async();
             mbar_arrive(&ds_full[b]);
         }
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
         tc_fence_after();
         __nv_bfloat16* orow = p.dQ + grow * DP;
 #pragma unroll 1
-        for (int ch = 0; ch < DP / 32; ++ch) {
+        for (int ch = half * (DP / 64); ch < (half + 1) * (DP / 64); ++ch) {
             uint32_t v[32];
             tmem_ld32(t_row + kAccCol + uint32_t(ch * 32), v);
             tmem_ld_wait();
@@ -481,11 +483,11 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dq_kernel(const __grid
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 template <int DP>
-__global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK,
+__global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK,
                                                                     const __grid_constant__ CUtensorMap mapV,
                                                                     const __grid_constant__ CUtensorMap mapQ,
                                                                     const __grid_constant__ CUtensorMap mapDO,
@@ -499,9 +501,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
     uint8_t* sV = sK + kKBytes;
     uint8_t* sQ = sV + kKBytes;                 // 2 stages of [64 queries][DP]
     uint8_t* sDO = sQ + 2 * kQBytes;            // 2 stages
-    uint8_t* sPT = sDO + 2 * kQBytes;           // 2 buffers of [128 keys][64 queries]
-    uint8_t* sDST = sPT + 2 * kBig;             // 2 buffers
-    float2* cvec = reinterpret_cast<float2*>(sDST + 2 * kBig);   // [2][64] (-m*c, D') of the tile's queries
+    uint8_t* sPT = sDO + 2 * kQBytes;           // [128 keys][64 queries]
+    uint8_t* sDST = sPT + kBig;
+    float2* cvec = reinterpret_cast<float2*>(sDST + kBig);   // [2][64] (-m*c, D') of the tile's queries
     uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + 128);
     uint64_t* kv_full = bars;
     uint64_t* qd_full = bars + 1;
@@ -519,18 +521,20 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
-            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], 128);
-            mbar_init(&pd_full[i], 128); mbar_init(&pd_empty[i], 1);
+            mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], kSmThreads);
+            mbar_init(&pd_full[i], kSmThreads); mbar_init(&pd_empty[i], 1);
         }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    // DP = 64: 256 TMEM columns (S^T | dP'^T single-buffered + dV + dK) and 96 KB of shared memory -> two CTAs per SM
+    constexpr uint32_t kTmemCols = DP == 64 ? 256 : 512;
+    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kDvCol = 256, kDkCol = 256 + DP;
+    constexpr uint32_t kDvCol = 128, kDkCol = 128 + DP;
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(kv_full, 2 * kKBytes);
@@ -554,10 +558,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
         mbar_wait(kv_full, 0);
         tc_fence_after();
         auto issue_acc = [&](int i) {
-            const int s = i & 1, b = i & 1;
-            mbar_wait(&pd_full[b], (i >> 1) & 1);
+            const int s = i & 1;
+            mbar_wait(&pd_full[0], i & 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sPT + b * kBig), da = smem_u32(sDST + b * kBig);
+            const uint32_t pa = smem_u32(sPT), da = smem_u32(sDST);
             const uint32_t qa = smem_u32(sQ + s * kQBytes), oa = smem_u32(sDO + s * kQBytes);
             if (elect_one()) {
 #pragma unroll
@@ -568,14 +572,14 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
                               umma_desc_sw128_mn(qa + kk * 2048, kSmall, 1024), idesc_a, (i | kk) != 0 ? 1u : 0u);
                 }
                 umma_commit(&qd_empty[s]);
-                umma_commit(&pd_empty[b]);
+                umma_commit(&pd_empty[0]);
             }
             __syncwarp();
         };
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i & 1, b = i & 1;
+            const int s = i & 1;
             mbar_wait(&qd_full[s], (i >> 1) & 1);
-            mbar_wait(&sd_empty[b], (((i >> 1) & 1) ^ 1));
+            mbar_wait(&sd_empty[0], ((i & 1) ^ 1));
             tc_fence_after();
             const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQ + s * kQBytes), oa = smem_u32(sDO + s * kQBytes);
             if (elect_one()) {
@@ -584,12 +588,12 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         // S^T = K Q^T and dP'^T = V dO'^T: 128 keys x 64 queries
-                        umma_bf16(tmem_base + uint32_t(b * 128), umma_desc_sw128(ka + c * kBig) + uint64_t(kk * 2),
+                        umma_bf16(tmem_base, umma_desc_sw128(ka + c * kBig) + uint64_t(kk * 2),
                                   umma_desc_sw128(qa + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
-                        umma_bf16(tmem_base + uint32_t(b * 128 + 64), umma_desc_sw128(va + c * kBig) + uint64_t(kk * 2),
+                        umma_bf16(tmem_base + 64u, umma_desc_sw128(va + c * kBig) + uint64_t(kk * 2),
                                   umma_desc_sw128(oa + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
                     }
-                umma_commit(&sd_full[b]);
+                umma_commit(&sd_full[0]);
             }
             __syncwarp();
             if (i > 0) issue_acc(i - 1);
@@ -598,9 +602,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
         if (elect_one()) umma_commit(acc_full);
         __syncwarp();
     } else {
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;          // key row of this thread
-        const int st = threadIdx.x - 64;           // 0..127 among the softmax threads
+        const int quad = warp & 3, half = (warp - 2) >> 2;   // thread = (key row, 32-query half of the tile)
+        const int row = quad * 32 + lane;
+        const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
         const long long gkey = (long long)batch * p.tkv + k0 + row;
         const float c = p.exp_scale, sc = p.scale;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
@@ -608,51 +612,46 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
             const int b = i & 1;
             if (st < 64) {   // this tile's per-query constants (buffer b was last read two tiles ago, before a barrier)
                 const long long gq = (long long)batch * p.tq + i * 64 + st;
-                cvec[b * 64 + st] = make_float2(-__ldg(p.rmax + gq) * c, __ldg(p.Dp + gq));
+                cvec[b * 64 + st] = make_float2(-__ldg(p.rmax + gq) * c, -__ldg(p.Dp + gq) * sc);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&sd_full[b], (i >> 1) & 1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&sd_full[0], i & 1);
             tc_fence_after();
-            mbar_wait(&pd_empty[b], (((i >> 1) & 1) ^ 1));
-            uint8_t* prow = sPT + b * kBig + row * 128;
-            uint8_t* drow = sDST + b * kBig + row * 128;
-            const float2* cv = cvec + b * 64;
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t vs[32], vd[32];
-                tmem_ld32(t_row + uint32_t(b * 128 + ch * 32), vs);
-                tmem_ld32(t_row + uint32_t(b * 128 + 64 + ch * 32), vd);
-                tmem_ld_wait();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t wp[4], wd[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i2 = 8 * u + 2 * k;
-                        const float2 c0 = cv[ch * 32 + i2], c1 = cv[ch * 32 + i2 + 1];
-                        const uint32_t pp = fa_pack(fa_ex2(fmaf(__uint_as_float(vs[i2]), c, c0.x)),
-                                                    fa_ex2(fmaf(__uint_as_float(vs[i2 + 1]), c, c1.x)));
-                        wp[k] = pp;
-                        wd[k] = fa_pack(fa_lo(pp) * ((__uint_as_float(vd[i2]) - c0.y) * sc),
-                                        fa_hi(pp) * ((__uint_as_float(vd[i2 + 1]) - c1.y) * sc));
-                    }
-                    const int unit = ch * 4 + u;
-                    const int off = (unit ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-                    *reinterpret_cast<uint4*>(drow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-                }
-            }
+            uint8_t* prow = sPT + row * 128;
+            uint8_t* drow = sDST + row * 128;
+            const float2* cv = cvec + b * 64 + half * 32;
+            uint32_t vs[32], vd[32];
+            tmem_ld32(t_row + uint32_t(half * 32), vs);
+            tmem_ld32(t_row + uint32_t(64 + half * 32), vd);
+            tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&sd_empty[b]);
+            mbar_arrive(&sd_empty[0]);
+            mbar_wait(&pd_empty[0], ((i & 1) ^ 1));   // the previous tile's dV / dK products have read the operand tiles
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t wp[4], wd[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i2 = 8 * u + 2 * k;
+                    const float2 c0 = cv[i2], c1 = cv[i2 + 1];
+                    const float p0 = fa_ex2(fmaf(__uint_as_float(vs[i2]), c, c0.x));
+                    const float p1 = fa_ex2(fmaf(__uint_as_float(vs[i2 + 1]), c, c1.x));
+                    wp[k] = fa_pack(p0, p1);
+                    wd[k] = fa_pack(p0 * fmaf(__uint_as_float(vd[i2]), sc, c0.y), p1 * fmaf(__uint_as_float(vd[i2 + 1]), sc, c1.y));
+                }
+                const int unit = half * 4 + u;
+                const int off = (unit ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+                *reinterpret_cast<uint4*>(drow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
             fence_proxy_async();
-            mbar_arrive(&pd_full[b]);
+            mbar_arrive(&pd_full[0]);
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-            __nv_bfloat16* orow = (which ? p.dK : p.dV) + gkey * DP;
-            const uint32_t col0 = which ? kDkCol : kDvCol;
+        {   // half 0 writes dV, half 1 writes dK
+            __nv_bfloat16* orow = (half ? p.dK : p.dV) + gkey * DP;
+            const uint32_t col0 = half ? kDkCol : kDvCol;
 #pragma unroll 1
             for (int ch = 0; ch < DP / 32; ++ch) {
                 uint32_t v[32];
@@ -670,7 +669,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_bwd_dkv_kernel(const __gri
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
 template <int DP>
@@ -692,7 +691,7 @@ int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     if ((rc = encode_map_bf16_sw128(&mv64, V, 3, dk, sk, box64, "attn.bwd.V64"))) return rc;
     constexpr int NC = DP / 64, kBig = 128 * 128, kSmall = 64 * 128;
     constexpr size_t smem_dq = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 256 + 1024;
-    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 4 * kBig + 1024 + 256 + 1024;
+    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 1024 + 256 + 1024;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -722,13 +721,17 @@ bool attn_fused_supported(int tq, int tkv, int dp) {
     return !off && (dp == 64 || dp == 128) && tq % 128 == 0 && tkv % 128 == 0 && tkv >= 128;
 }
 
-// O[nb][tq][dp] = softmax(Q K^T * scale) V given the row maxima of Q K^T; inv_l[nb][tq] = 1 / row sums of P~
+// O[nb][tq][dp] = softmax(Q K^T * scale) V given the row maxima of Q K^T; inv_l[nb][tq] = 1 / row sums of P~.
+// Channel `lcol` (< dp) of V must hold 1.0 for every key (a padding channel of the head): O[:, lcol] is then the row sum.
 int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
-                          int tq, int tkv, int dp, float scale, cudaStream_t st) {
+                          int tq, int tkv, int dp, int lcol, float scale, cudaStream_t st) {
     if (g_dry_run) return 0;
-    if (!attn_fused_supported(tq, tkv, dp)) { set_error("attn.fused: unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
-    if (dp == 64) return launch_fa<64>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
-    return launch_fa<128>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, scale, st);
+    if (!attn_fused_supported(tq, tkv, dp) || lcol < 0 || lcol >= dp) {
+        set_error("attn.fused: unsupported shape tq=%d tkv=%d dp=%d lcol=%d", tq, tkv, dp, lcol);
+        return -1;
+    }
+    if (dp == 64) return launch_fa<64>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, lcol, scale, st);
+    return launch_fa<128>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, lcol, scale, st);
 }
 
 // Fused backward of the same attention: dO [nb][tq][dp], O, inv_l, rmax from the forward; dOs (bf16 [nb][tq][dp]) and

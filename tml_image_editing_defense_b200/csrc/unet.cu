@@ -333,7 +333,7 @@ int mh_probs(URun& r, const bf16* Q, const bf16* K, const float* rmax, float* pa
 // softmax(Q K^T * scale) V for nb batches: the row maxima (rmax) and 1/l are kept for the backward, P~ only if the
 // caller passes a saved buffer (cross attention: 128 key slots); O dense [nb][tq][dp]
 int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, bf16* P, float* rmax, float* inv_l, bf16* O,
-                         int nb, int tq, int tkv, int dp, float scale) {
+                         int nb, int tq, int tkv, int dp, float scale, int lcol = -1) {
     const int ns = r.u->base.num_sms;
     const long long rows = (long long)nb * tq;
     int gh = 0, gw = 0;
@@ -348,9 +348,9 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
     o.row_part = part;
     RC(gemm_launch(o, ns, r.st));
     launch_row_reduce(part, rmax, rows, np, 0, r.st);
-    if (P == nullptr && attn_fused_supported(tq, tkv, dp)) {
+    if (P == nullptr && lcol >= 0 && attn_fused_supported(tq, tkv, dp)) {
         // fused: S, P~ and O never leave the SM (attn_fused.cu); the backward recomputes P~ from rmax
-        RC(launch_attn_fused_fwd(Q, K, V, rmax, inv_l, O, nb, tq, tkv, dp, scale, r.st));
+        RC(launch_attn_fused_fwd(Q, K, V, rmax, inv_l, O, nb, tq, tkv, dp, lcol, scale, r.st));
         r.wsa.reset(m);
         return 0;
     }
@@ -477,11 +477,12 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
         const long long bs = (long long)tok * 3 * C;
         launch_head_split(qkv, 3 * C, bs, 0, r.S<bf16>(rec.Qh), B, H, tok, tok, tok, d, dp, 0, r.st);
         launch_head_split(qkv, 3 * C, bs, C, r.S<bf16>(rec.Kh), B, H, tok, tok, tok, d, dp, 0, r.st);
-        launch_head_split(qkv, 3 * C, bs, 2 * C, r.S<bf16>(rec.Vh), B, H, tok, tok, tok, d, dp, 0, r.st);
+        // (V's first padding channel is 1.0: the fused attention reads the softmax denominator off that column of O)
+        launch_head_split(qkv, 3 * C, bs, 2 * C, r.S<bf16>(rec.Vh), B, H, tok, tok, tok, d, dp, 1, r.st);
         r.wsa.reset(m2);
     }
     RC(mh_attention_forward(r, r.S<bf16>(rec.Qh), r.S<bf16>(rec.Kh), r.S<bf16>(rec.Vh), nullptr, r.S<float>(rec.rmax),
-                            r.S<float>(rec.invl), r.S<bf16>(rec.Oh), nb, tok, tok, dp, scale));
+                            r.S<float>(rec.invl), r.S<bf16>(rec.Oh), nb, tok, tok, dp, scale, d < dp ? d : -1));
     launch_head_merge(r.S<bf16>(rec.Oh), a, C, (long long)tok * C, 0, B, H, tok, d, dp, r.st);
     bf16* x1 = r.S<bf16>(rec.x1);
     RC(gemm_launch(lin_op("unet.attn1.out", a, B, h, w, C, p.out1.fwd, C, p.out1.bias, t0, x1), ns, r.st));
