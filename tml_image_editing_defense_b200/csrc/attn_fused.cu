@@ -1,19 +1,22 @@
-// Fused multi-head attention forward for the UNet's self-attention layers (diffusers Attention / SDPA call reached from
-// main.py:233-238): one kernel per layer computes O = softmax(Q K^T * scale) V for every (image, head) without the
-// token x token matrix ever leaving the SM.
+// Fused multi-head attention for the UNet's self-attention layers (diffusers Attention / SDPA call reached from
+// main.py:233-238, and its backward through torch.autograd.grad at main.py:176): O = softmax(Q K^T * scale) V for every
+// (sample, head) without the token x token matrix ever leaving the SM.
 //
-//   CTA = one (image, head) x 128 query rows, looping over key tiles of 128:
+// Forward, mh_attn_fwd_kernel: CTA = one (sample, head) x 128 query rows, looping over key tiles of 64:
 //     warp 0   TMA producer: Q once, then K and V tiles into a two-stage ring (128-byte swizzle)
-//     warp 1   tcgen05.mma issuer: S = Q K^T into one of two TMEM buffers (128 columns each), and, one tile behind,
-//              O += P~ V with P~ read from shared memory and V read as an MN-major operand (no transposed copy)
-//     warps 2-9  softmax, thread = (query row, half of the tile's keys; two warps per SM sub-partition -- with one the
-//              exp / pack chain is latency-bound): tcgen05.ld of S, P~ = exp2((s - rowmax) * scale * log2 e) with the
-//              row maxima of the preceding max pass (so no accumulator rescaling is ever needed), bf16 P~ written into
-//              the swizzled K-major operand tile the PV MMA reads, row sums of the values as stored
-//   TMEM: S[0] | S[1] | O (DP columns); epilogue: O / l -> bf16, 1 / l -> fp32 (kept for the backward).
+//     warp 1   tcgen05.mma issuer: S = Q K^T into 64 TMEM columns, and, one tile behind, O += P~ V with P~ read from
+//              shared memory and the V tile [key][channel] read as an MN-major operand (no transposed copy)
+//     warps 2-9  softmax, thread = (query row, 32-key half): tcgen05.ld of S into registers (S is released at once, so one
+//              TMEM buffer suffices), P~ = exp2((s - rowmax) * scale * log2 e) with the row maxima of the preceding max
+//              pass (no accumulator rescaling is ever needed), bf16 P~ into the swizzled K-major operand tile of the PV MMA
+//   TMEM: S (64 columns) | O (DP columns) = one 256-column allocation; with 80 KB of shared memory two CTAs share an SM
+//   and fill each other's pipeline bubbles (measured: 1 CTA/SM with 128-key tiles 1.20 ms per layer, this form 1.01 ms).
+//   The softmax denominator is a column of O: V carries 1.0 in its first padding channel.
+//   Epilogue: O / l -> bf16, 1 / l -> fp32 (kept for the backward).
+// Backward: attn_bwd_dq_kernel / attn_bwd_dkv_kernel, see the comment above them.
 //
-// The numbers are those of the unfused path (same MMA shapes for S, same exp2 form, same bf16 rounding of P~), which
-// stays the verified baseline and still serves head widths above 128 and the cross attention.
+// The unfused GEMM-epilogue path of unet.cu stays the verified baseline (TML_NO_FUSED_ATTN=1) and still serves head widths
+// above 128 and the cross attention.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
