@@ -709,7 +709,8 @@ int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     p.rmax = rmax; p.Dp = Dp; p.dQ = dQ; p.dK = dK; p.dV = dV; p.tq = tq; p.tkv = tkv;
     p.scale = scale; p.exp_scale = scale * 1.4426950408889634f;
     attn_bwd_dq_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem_dq, st>>>(mq128, mo128, mk64, mv64, p);
-    attn_bwd_dkv_kernel<DP><<<dim3(tkv / 128, nb), kFaThreads, smem_dkv, st>>>(mk128, mv128, mq64, mo64, p);
+    if (dK != nullptr && dV != nullptr)   // (cross attention: keys / values are constants of the attack)
+        attn_bwd_dkv_kernel<DP><<<dim3(tkv / 128, nb), kFaThreads, smem_dkv, st>>>(mk128, mv128, mq64, mo64, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("attn.bwd: launch failed: %s", cudaGetErrorString(e)); return -5; }
     count_launch();
@@ -738,7 +739,7 @@ int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const flo
 }
 
 // Fused backward of the same attention: dO [nb][tq][dp], O, inv_l, rmax from the forward; dOs (bf16 [nb][tq][dp]) and
-// Dp (fp32 [nb][tq]) are scratch.  Writes dQ [nb][tq][dp], dK and dV [nb][tkv][dp].
+// Dp (fp32 [nb][tq]) are scratch.  Writes dQ [nb][tq][dp], dK and dV [nb][tkv][dp] (both null: dQ only).
 int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf16* O, const bf16* dO, const float* rmax,
                           const float* inv_l, bf16* dOs, float* Dp, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv,
                           int dp, float scale, cudaStream_t st) {

@@ -48,7 +48,7 @@ struct TfRec {
     size_t x = 0, out = 0;
     GnSaved g;
     size_t t0 = 0, st1 = 0, Qh = 0, Kh = 0, Vh = 0, rmax = 0, Oh = 0, invl = 0;   // self attention: P~ is recomputed in the backward
-    size_t x1 = 0, st2 = 0, Q2 = 0, K2 = 0, V2 = 0, P2 = 0, O2 = 0, invl2 = 0;
+    size_t x1 = 0, st2 = 0, Q2 = 0, K2 = 0, V2 = 0, P2 = 0, rmax2 = 0, O2 = 0, invl2 = 0;   // P2 only on the unfused path
     size_t x2 = 0, st3 = 0, hff = 0;
 };
 struct SampRec { size_t x = 0, out = 0; int h = 0, w = 0; };   // down / up sampler: (h, w) = input size
@@ -376,7 +376,7 @@ int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, 
     RC(attn_grid(tq, &gh, &gw));
     const size_t m = r.wsa.mark();
     static const bool no_fused_bwd = getenv("TML_NO_FUSED_ATTN_BWD") && getenv("TML_NO_FUSED_ATTN_BWD")[0] == '1';   // A/B switch
-    if (P == nullptr && dK != nullptr && dV != nullptr && !no_fused_bwd && attn_fused_supported(tq, tkv, dp)) {
+    if (P == nullptr && !no_fused_bwd && attn_fused_supported(tq, tkv, dp)) {
         // fused (attn_fused.cu): S and dP are recomputed on the tensor cores inside the two backward kernels
         bf16* dOs = r.Walloc<bf16>((size_t)rows * dp * sizeof(bf16));
         float* Dp = r.Walloc<float>((size_t)rows * sizeof(float));
@@ -454,7 +454,9 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
     rec.Q2 = r.sva.alloc((size_t)nb * tok * dp2 * sizeof(bf16));
     rec.K2 = r.sva.alloc((size_t)nb * Tp * dp2 * sizeof(bf16));
     rec.V2 = r.sva.alloc((size_t)nb * Tp * dp2 * sizeof(bf16));
-    rec.P2 = r.sva.alloc((size_t)nb * tok * Tp * sizeof(bf16));
+    const bool fused2 = attn_fused_supported(tok, Tp, dp2);   // cross attention on the fused kernels: P~ is never stored
+    if (!fused2) rec.P2 = r.sva.alloc((size_t)nb * tok * Tp * sizeof(bf16));
+    rec.rmax2 = r.sva.alloc((size_t)nb * tok * sizeof(float));
     rec.O2 = r.sva.alloc((size_t)nb * tok * dp2 * sizeof(bf16));
     rec.invl2 = r.sva.alloc((size_t)nb * tok * sizeof(float));
     rec.x2 = r.sva.alloc(act);
@@ -496,11 +498,13 @@ int utf_forward(URun& r, const UTf& p, TfRec& rec, size_t x_off, int h, int w, c
         bf16* kv = r.Walloc<bf16>((size_t)B * Tp * 2 * C * sizeof(bf16));
         RC(gemm_launch(lin_op("unet.attn2.kv", ctxp, B, 1, Tp, p.kv2.ci, p.kv2.fwd, 2 * C, nullptr, nullptr, kv), ns, r.st));
         launch_head_split(kv, 2 * C, (long long)Tp * 2 * C, 0, r.S<bf16>(rec.K2), B, H, Tp, T, Tp, d, dp2, 2, r.st);
-        launch_head_split(kv, 2 * C, (long long)Tp * 2 * C, C, r.S<bf16>(rec.V2), B, H, Tp, T, Tp, d, dp2, 0, r.st);
+        // (V's padding channel d = 1.0 on every row: the fused kernel's denominator column; padded keys have P~ = 0)
+        launch_head_split(kv, 2 * C, (long long)Tp * 2 * C, C, r.S<bf16>(rec.V2), B, H, Tp, Tp, Tp, d, dp2, 1, r.st);
         r.wsa.reset(m2);
     }
-    RC(mh_attention_forward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2), nullptr,
-                            r.S<float>(rec.invl2), r.S<bf16>(rec.O2), nb, tok, Tp, dp2, scale));
+    RC(mh_attention_forward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), fused2 ? nullptr : r.S<bf16>(rec.P2),
+                            r.S<float>(rec.rmax2), r.S<float>(rec.invl2), r.S<bf16>(rec.O2), nb, tok, Tp, dp2, scale,
+                            fused2 ? d : -1));
     launch_head_merge(r.S<bf16>(rec.O2), a, C, (long long)tok * C, 0, B, H, tok, d, dp2, r.st);
     bf16* x2 = r.S<bf16>(rec.x2);
     RC(gemm_launch(lin_op("unet.attn2.out", a, B, h, w, C, p.out2.fwd, C, p.out2.bias, x1, x2), ns, r.st));
@@ -551,8 +555,10 @@ int utf_backward(URun& r, const UTf& p, const TfRec& rec, const bf16* dout, bf16
         bf16* dO = r.Walloc<bf16>((size_t)nb * tok * dp2 * sizeof(bf16));
         launch_head_split(da, C, (long long)tok * C, 0, dO, B, H, tok, tok, tok, d, dp2, 0, r.st);
         bf16* dQ = r.Walloc<bf16>((size_t)nb * tok * dp2 * sizeof(bf16));
-        RC(mh_attention_backward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2), r.S<bf16>(rec.P2), nullptr,
-                                 r.S<float>(rec.invl2), r.S<bf16>(rec.O2), dO, dQ, nullptr, nullptr, nb, tok, Tp, dp2, scale));
+        const bool fused2 = attn_fused_supported(tok, Tp, dp2);
+        RC(mh_attention_backward(r, r.S<bf16>(rec.Q2), r.S<bf16>(rec.K2), r.S<bf16>(rec.V2),
+                                 fused2 ? nullptr : r.S<bf16>(rec.P2), r.S<float>(rec.rmax2), r.S<float>(rec.invl2),
+                                 r.S<bf16>(rec.O2), dO, dQ, nullptr, nullptr, nb, tok, Tp, dp2, scale));
         launch_head_merge(dQ, da, C, (long long)tok * C, 0, B, H, tok, d, dp2, r.st);
         bf16* dn = r.Walloc<bf16>(act);
         RC(gemm_launch(lin_op("unet.attn2.q.dgrad", da, B, h, w, C, p.q2.bwd, C, nullptr, nullptr, dn), ns, r.st));
