@@ -41,7 +41,8 @@ constexpr int kSmThreads = 256;
 constexpr uint32_t kUmmaBMajorMN = 1u << 16;
 
 struct FaParams {
-    const float* rmax;    // [nb][tq]
+    const float* rmax;    // [nb][tq]  known row maxima (mh_attn_fwd_kernel)
+    float* rmax_out;      // [nb][tq]  reference maxima chosen by the online kernel (kept for the backward)
     float* inv_l;         // [nb][tq]
     __nv_bfloat16* O;     // [nb][tq][DP]
     int tq, tkv;
@@ -237,9 +238,210 @@ __global__ void __launch_bounds__(kFaThreads, 2) mh_attn_fwd_kernel(const __grid
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
+// The same forward with an ONLINE softmax: no preceding row-max pass over Q K^T.  Thread = query row (four softmax warps,
+// 64 keys per tile).  The exponent reference m_ref of a row only moves when a tile's maximum exceeds it by more than 8 in
+// log2 units, so stored probabilities stay below 2^8 (bf16 keeps its relative precision there) and the accumulator --
+// including its denominator column -- is rescaled in TMEM (tcgen05.ld / st) only on those rare tiles, after the previous
+// tile's P V product has retired.  The final m_ref is written out: the backward recomputes P~ against it.
 template <int DP>
-int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const float* rmax, float* inv_l,
-              __nv_bfloat16* O, int nb, int tq, int tkv, int lcol, float scale, cudaStream_t st) {
+__global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                    const __grid_constant__ CUtensorMap mapK,
+                                                                    const __grid_constant__ CUtensorMap mapV,
+                                                                    const FaParams p) {
+    constexpr int NC = DP / 64;
+    constexpr int kBig = 128 * 128, kSmall = 64 * 128;
+    constexpr int kQBytes = NC * kBig, kKBytes = NC * kSmall;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kQBytes;
+    uint8_t* sV = sK + 2 * kKBytes;
+    uint8_t* sP = sV + 2 * kKBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kBig);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 3;
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 7;
+    uint64_t* p_full = bars + 9;
+    uint64_t* p_empty = bars + 11;
+    uint64_t* o_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, batch = blockIdx.y;
+    const int ntiles = p.tkv / 64;
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_empty[i], 1);
+        }
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kOCol = 64;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kQBytes);
+            for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * kBig, &mapQ, q_full, c * 64, q0, batch);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&kv_full[s], 2 * kKBytes);
+                for (int c = 0; c < NC; ++c) {
+                    tma_load_3d(sK + s * kKBytes + c * kSmall, &mapK, &kv_full[s], c * 64, j * 64, batch);
+                    tma_load_3d(sV + s * kKBytes + c * kSmall, &mapV, &kv_full[s], c * 64, j * 64, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, 64);
+        const uint32_t idesc_o = umma_idesc_bf16(128, DP) | kUmmaBMajorMN;
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        auto issue_pv = [&](int j) {
+            const int s = j & 1, b = j & 1;
+            mbar_wait(&p_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + b * kBig), va = smem_u32(sV + s * kKBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem_base + kOCol, umma_desc_sw128(pa) + uint64_t(kk * 2),
+                              umma_desc_sw128_mn(va + kk * 2048, kSmall, 1024), idesc_o, (j | kk) != 0 ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                umma_commit(&p_empty[b]);
+            }
+            __syncwarp();
+        };
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j & 1;
+            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            mbar_wait(&s_empty[0], ((j & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + s * kKBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base, umma_desc_sw128(qa + c * kBig) + uint64_t(kk * 2),
+                                  umma_desc_sw128(ka + c * kSmall) + uint64_t(kk * 2), idesc_s, (c | kk) != 0 ? 1u : 0u);
+                umma_commit(&s_full[0]);
+            }
+            __syncwarp();
+            if (j > 0) issue_pv(j - 1);
+        }
+        issue_pv(ntiles - 1);
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const long long grow = (long long)batch * p.tq + q0 + row;
+        const float c = p.exp_scale;
+        const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
+        float m_ref = 0.f;
+        for (int j = 0; j < ntiles; ++j) {
+            const int b = j & 1;
+            mbar_wait(&s_full[0], j & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_row, v0);
+            tmem_ld32(t_row + 32u, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_empty[0]);
+            float mt = __uint_as_float(v0[0]);
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v0[i]));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v1[i]));
+            if (j == 0) {
+                m_ref = mt;
+            } else {
+                const bool need = (mt - m_ref) * c > 8.f;
+                if (__any_sync(0xffffffffu, need)) {
+                    // rescale this warp's 32 accumulator rows once the previous tile's P V has retired
+                    mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
+                    const float alpha = need ? fa_ex2((m_ref - mt) * c) : 1.f;
+                    if (need) m_ref = mt;
+#pragma unroll 1
+                    for (int ch = 0; ch < DP / 32; ++ch) {
+                        uint32_t o[32];
+                        tmem_ld32(t_row + kOCol + uint32_t(ch * 32), o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_row + kOCol + uint32_t(ch * 32), o);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+            }
+            const float ra = -m_ref * c;
+            mbar_wait(&p_empty[b], (((j >> 1) & 1) ^ 1));
+            uint8_t* dst = sP + b * kBig + row * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t* vv = u < 4 ? v0 : v1;
+                const int k = (u & 3) * 8;
+                const uint4 o = make_uint4(
+                    fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 1]), c, ra))),
+                    fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 2]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 3]), c, ra))),
+                    fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 4]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 5]), c, ra))),
+                    fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 6]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 7]), c, ra))));
+                *reinterpret_cast<uint4*>(dst + ((u ^ (row & 7)) << 4)) = o;
+            }
+            fence_proxy_async();
+            mbar_arrive(&p_full[b]);
+        }
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        float l;
+        {
+            uint32_t v8[8];
+            tmem_ld8(t_row + kOCol + uint32_t(p.lcol & ~7), v8);
+            tmem_ld_wait();
+            l = __uint_as_float(v8[p.lcol & 7]);
+        }
+        const float il = 1.f / l;
+        p.inv_l[grow] = il;
+        p.rmax_out[grow] = m_ref;
+        __nv_bfloat16* orow = p.O + grow * DP;
+#pragma unroll 1
+        for (int ch = 0; ch < DP / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(t_row + kOCol + uint32_t(ch * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 o = make_uint4(fa_pack(__uint_as_float(v[8 * u]) * il, __uint_as_float(v[8 * u + 1]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 2]) * il, __uint_as_float(v[8 * u + 3]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 4]) * il, __uint_as_float(v[8 * u + 5]) * il),
+                                           fa_pack(__uint_as_float(v[8 * u + 6]) * il, __uint_as_float(v[8 * u + 7]) * il));
+                *reinterpret_cast<uint4*>(orow + ch * 32 + u * 8) = o;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+template <int DP>
+int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const float* rmax, float* rmax_out,
+              float* inv_l, __nv_bfloat16* O, int nb, int tq, int tkv, int lcol, float scale, cudaStream_t st) {
     CUtensorMap mq, mk, mv;
     int rc;
     cuuint32_t box[3] = {64, 128, 1}, box64[3] = {64, 64, 1};
@@ -261,13 +463,16 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(mh_attn_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mh_attn_fwd_online_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("attn.fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -4; }
         attr_set[dev & 63] = true;
     }
     FaParams p;
-    p.rmax = rmax; p.inv_l = inv_l; p.O = O; p.tq = tq; p.tkv = tkv; p.lcol = lcol;
+    p.rmax = rmax; p.rmax_out = rmax_out; p.inv_l = inv_l; p.O = O; p.tq = tq; p.tkv = tkv; p.lcol = lcol;
     p.exp_scale = scale * 1.4426950408889634f;
-    mh_attn_fwd_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem, st>>>(mq, mk, mv, p);
+    if (rmax == nullptr) mh_attn_fwd_online_kernel<DP><<<dim3(tq / 128, nb), 192, smem, st>>>(mq, mk, mv, p);
+    else mh_attn_fwd_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem, st>>>(mq, mk, mv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("attn.fused: launch failed: %s", cudaGetErrorString(e)); return -5; }
     count_launch();
@@ -727,15 +932,18 @@ bool attn_fused_supported(int tq, int tkv, int dp) {
 
 // O[nb][tq][dp] = softmax(Q K^T * scale) V given the row maxima of Q K^T; inv_l[nb][tq] = 1 / row sums of P~.
 // Channel `lcol` (< dp) of V must hold 1.0 for every key (a padding channel of the head): O[:, lcol] is then the row sum.
-int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
-                          int tq, int tkv, int dp, int lcol, float scale, cudaStream_t st) {
+// rmax != null: known row maxima (a preceding max pass); rmax == null: online softmax, the reference maxima the kernel
+// settled on are written to rmax_out (what the backward must recompute P~ against).
+int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* rmax_out, float* inv_l,
+                          bf16* O, int nb, int tq, int tkv, int dp, int lcol, float scale, cudaStream_t st) {
     if (g_dry_run) return 0;
     if (!attn_fused_supported(tq, tkv, dp) || lcol < 0 || lcol >= dp) {
         set_error("attn.fused: unsupported shape tq=%d tkv=%d dp=%d lcol=%d", tq, tkv, dp, lcol);
         return -1;
     }
-    if (dp == 64) return launch_fa<64>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, lcol, scale, st);
-    return launch_fa<128>(Q, K, V, rmax, inv_l, O, nb, tq, tkv, lcol, scale, st);
+    if (rmax == nullptr && rmax_out == nullptr) { set_error("attn.fused: no row-maximum buffer"); return -1; }
+    if (dp == 64) return launch_fa<64>(Q, K, V, rmax, rmax_out, inv_l, O, nb, tq, tkv, lcol, scale, st);
+    return launch_fa<128>(Q, K, V, rmax, rmax_out, inv_l, O, nb, tq, tkv, lcol, scale, st);
 }
 
 // Fused backward of the same attention: dO [nb][tq][dp], O, inv_l, rmax from the forward; dOs (bf16 [nb][tq][dp]) and

@@ -117,8 +117,10 @@ void launch_nhwc64_unpack(const bf16* in, float* out, int B, int C, int hw, cuda
 // fused attention forward (attn_fused.cu): O = softmax(Q K^T * scale) V per batch given the row maxima of Q K^T;
 // Q [nb][tq][dp], K / V [nb][tkv][dp] dense bf16, dp in {64, 128}, tq and tkv multiples of 128
 bool attn_fused_supported(int tq, int tkv, int dp);
-int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* inv_l, bf16* O, int nb,
-                          int tq, int tkv, int dp, int lcol /* channel of V holding 1.0 */, float scale, cudaStream_t s);
+// rmax: known row maxima, or null = online softmax (the reference maxima it settles on go to rmax_out)
+int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const float* rmax, float* rmax_out, float* inv_l,
+                          bf16* O, int nb, int tq, int tkv, int dp, int lcol /* channel of V holding 1.0 */, float scale,
+                          cudaStream_t s);
 
 int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf16* O, const bf16* dO, const float* rmax,
                           const float* inv_l, bf16* dOs, float* Dp, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv,

@@ -339,6 +339,14 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
     int gh = 0, gw = 0;
     RC(attn_grid(tq, &gh, &gw));
     const size_t m = r.wsa.mark();
+    static const bool known_max = getenv("TML_ATTN_KNOWN_MAX") && getenv("TML_ATTN_KNOWN_MAX")[0] == '1';   // A/B switch
+    const bool fused = P == nullptr && lcol >= 0 && attn_fused_supported(tq, tkv, dp);
+    if (fused && !known_max && rmax != nullptr) {
+        // fused, online softmax (attn_fused.cu): no max pass; S, P~ and O never leave the SM
+        RC(launch_attn_fused_fwd(Q, K, V, nullptr, rmax, inv_l, O, nb, tq, tkv, dp, lcol, scale, r.st));
+        r.wsa.reset(m);
+        return 0;
+    }
     GemmOp o = mh_logits_op("unet.attn.qk.max", Q, K, nb, tq, tkv, dp, gh, gw);
     o.epi_mode = 1;
     const int np = gemm_row_partials(o);   // host-only planning: also valid during a dry run
@@ -348,9 +356,9 @@ int mh_attention_forward(URun& r, const bf16* Q, const bf16* K, const bf16* V, b
     o.row_part = part;
     RC(gemm_launch(o, ns, r.st));
     launch_row_reduce(part, rmax, rows, np, 0, r.st);
-    if (P == nullptr && lcol >= 0 && attn_fused_supported(tq, tkv, dp)) {
-        // fused: S, P~ and O never leave the SM (attn_fused.cu); the backward recomputes P~ from rmax
-        RC(launch_attn_fused_fwd(Q, K, V, rmax, inv_l, O, nb, tq, tkv, dp, lcol, scale, r.st));
+    if (fused) {
+        // fused with the row maxima of the pass above
+        RC(launch_attn_fused_fwd(Q, K, V, rmax, nullptr, inv_l, O, nb, tq, tkv, dp, lcol, scale, r.st));
         r.wsa.reset(m);
         return 0;
     }
