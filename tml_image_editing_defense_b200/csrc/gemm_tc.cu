@@ -286,7 +286,7 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // (a per-image B operand is fine when both CTAs of a pair always work on the same image)
     const bool b_ok = op.B_sBatch == 0 || (t->tiles_h * t->tiles_w) % 2 == 0;
     // (the attention logits, K = 512 and a per-image B operand, are L2-bound on single CTAs: 48 KB per four MMAs)
-    t->pair = (!no_pair && b_ok && !op.a_trans && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
+    t->pair = (!no_pair && b_ok && op.dbg_shift == 0 && BN == 256 && t->mt == 1 &&
                t->rows_valid == 128 && (op.ntaps * op.A_C >= 2048 || op.epi_mode != 0) && sub_tiles % 2 == 0 &&
                sub_tiles * t->n_tiles >= 4) ? 1 : 0;
     // Plain dense outputs (no fused reduction) leave through shared memory and TMA stores: the per-lane
@@ -878,7 +878,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                             if (crank == 0) mbar_arrive(&full_bar[stage]);
                         } else {
                             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * uint32_t(p.rows_valid) * 128u + uint32_t(p.BN) * 128u);
-                            if (p.mode == 0) {
+                            if (p.a_trans) {
+                                // this CTA's 128 rows of the transposed operand: two 64-row x 64-k atoms
+                                const int m0 = sb[0].oh0 * p.ow_full + sb[0].ow0;
+                                tma_load_3d_2sm(sA, &mapA, &full_bar[stage], m0, c0, sb[0].img);
+                                tma_load_3d_2sm(sA + 8192, &mapA, &full_bar[stage], m0 + 64, c0, sb[0].img);
+                            } else if (p.mode == 0) {
                                 tma_load_4d_2sm(sA, &mapA, &full_bar[stage], c0, sb[0].ow0 + p.dw[tap], sb[0].oh0 + p.dh[tap], sb[0].img);
                             } else {
                                 const int dw = p.dw[tap], dh = p.dh[tap];
@@ -1028,9 +1033,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                         if (elect_one()) {
                             if constexpr (PAIR) {
                                 umma_bf16_2sm(d_tmem, a_desc0, b_desc, idesc, first);
-                                umma_bf16_2sm(d_tmem, a_desc0 + 2, b_desc + 2, idesc, 1u);
-                                umma_bf16_2sm(d_tmem, a_desc0 + 4, b_desc + 4, idesc, 1u);
-                                umma_bf16_2sm(d_tmem, a_desc0 + 6, b_desc + 6, idesc, 1u);
+                                umma_bf16_2sm(d_tmem, a_desc0 + a_step, b_desc + 2, idesc, 1u);
+                                umma_bf16_2sm(d_tmem, a_desc0 + 2 * a_step, b_desc + 4, idesc, 1u);
+                                umma_bf16_2sm(d_tmem, a_desc0 + 3 * a_step, b_desc + 6, idesc, 1u);
                                 umma_commit_2sm(&empty_bar[stage], 3);
                             } else {
                                 for (int sub = 0; sub < p.mt; ++sub) {

@@ -750,28 +750,37 @@ static int attn_backward(Run& r, const Attn& p, const AttnRec& rec, const bf16* 
         o.D = dS;
         RC(gemm_launch(o, ns, r.st));
     }
-    bf16* dST = r.Walloc<bf16>(tt * 2);
-    launch_transpose(dS, dST, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
-    bf16* PT = r.Walloc<bf16>(tt * 2);
-    launch_transpose(P, PT, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
     bf16* Kt = r.Walloc<bf16>(act);
     launch_transpose(qkv + C, Kt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
     bf16* Qt = r.Walloc<bf16>(act);
     launch_transpose(qkv, Qt, B, tok, C, 3 * C, (long long)tok * 3 * C, tok, (long long)C * tok, r.st);
     bf16* dqkv = r.Walloc<bf16>(3 * act);
-    auto tok_gemm = [&](const char* name, const bf16* A, const bf16* Bt, bf16* D) {
-        GemmOp o;  // D[tok, C] (row stride 3C) = A[tok, tok'] * Bt[C, tok']^T
+    // D[tok, C] (row stride 3C) = A[tok, tok'] * Bt[C, tok']^T; transposed = true reads A[tok', tok] (the stored dS / P~)
+    // as an MN-major operand instead (GemmOp::a_trans): dK = dS^T Q and dV = P~^T (da / l) without a transposed copy
+    auto tok_gemm = [&](const char* name, const bf16* A, const bf16* Bt, bf16* D, bool transposed) {
+        GemmOp o;
         o.name = name;
         o.A = A; o.A_C = tok; o.A_W = gw; o.A_H = gh; o.A_B = B;
         o.A_sW = tok; o.A_sH = (int64_t)gw * tok; o.A_sB = (int64_t)tok * tok;
+        if (transposed) { o.a_trans = 1; o.A_sK = tok; }
         o.OW = gw; o.OH = gh;
         o.Bm = Bt; o.N = C; o.B_sN = tok; o.B_sBatch = (int64_t)C * tok;
         o.D = D; o.D_sW = 3 * C; o.D_sH = (int64_t)gw * 3 * C; o.D_sB = (int64_t)tok * 3 * C; o.D_sN = 1;
         return gemm_launch(o, ns, r.st);
     };
-    RC(tok_gemm("attn.dQ", dS, Kt, dqkv));
-    RC(tok_gemm("attn.dK", dST, Qt, dqkv + C));
-    RC(tok_gemm("attn.dV", PT, daT, dqkv + 2 * C));
+    static const bool no_atrans = env_off("TML_NO_ATRANS");   // A/B switch: transposed copies of dS and P~ as in round 1
+    RC(tok_gemm("attn.dQ", dS, Kt, dqkv, false));
+    if (no_atrans || gemm_get_impl() != 0) {
+        bf16* dST = r.Walloc<bf16>(tt * 2);
+        launch_transpose(dS, dST, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
+        bf16* PT = r.Walloc<bf16>(tt * 2);
+        launch_transpose(P, PT, B, tok, tok, tok, (long long)tok * tok, tok, (long long)tok * tok, r.st);
+        RC(tok_gemm("attn.dK", dST, Qt, dqkv + C, false));
+        RC(tok_gemm("attn.dV", PT, daT, dqkv + 2 * C, false));
+    } else {
+        RC(tok_gemm("attn.dK", dS, Qt, dqkv + C, true));
+        RC(tok_gemm("attn.dV", P, daT, dqkv + 2 * C, true));
+    }
     bf16* dt = r.Walloc<bf16>(act);
     GemmOp gq = dense_lin_op("attn.qkv.dgrad", dqkv, B, h, w, 3 * C, p.qkv.bwd, C, nullptr, nullptr, dt);
     float* pbuf = r.Walloc<float>(fused_partial_bytes(B, h, w));
