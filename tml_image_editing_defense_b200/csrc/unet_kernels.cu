@@ -318,9 +318,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
         if (o < C8) {
             float f[8];
             u_unpack8(v[i], f);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + o * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + o * 8) + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                f[j] = fmaf((f[j] - mean) * rstd, __ldg(&gamma[o * 8 + j]), __ldg(&beta[o * 8 + j]));
+            for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mean) * rstd, gg[j], bb[j]);
             *reinterpret_cast<uint4*>(y + (size_t)row * C + (size_t)o * 8) = u_pack8(f);
         }
     }
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
     if (row >= rows) return;
     const int C8 = C >> 3;
     const float2 st = stats[row];
+    // x and dy stay packed in registers between the two passes (gamma is re-read as two float4 per octet: L1 hits)
     uint4 vx[kLnMaxOct], vd[kLnMaxOct];
     float a = 0.f, b = 0.f;
 #pragma unroll
@@ -351,12 +355,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
         if (o < C8) {
             vx[i] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + (size_t)o * 8));
             vd[i] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * C + (size_t)o * 8));
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8) + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             float fx[8], fd[8];
             u_unpack8(vx[i], fx);
             u_unpack8(vd[i], fd);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float g = fd[j] * __ldg(&gamma[o * 8 + j]);
+                const float g = fd[j] * gg[j];
                 a += g;
                 b = fmaf(g, (fx[j] - st.x) * st.y, b);
             }
@@ -374,9 +380,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
                 const uint4 ur = __ldg(reinterpret_cast<const uint4*>(resid + (size_t)row * C + (size_t)o * 8));
                 u_unpack8(ur, fr);
             }
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8) + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float g = fd[j] * __ldg(&gamma[o * 8 + j]);
+                const float g = fd[j] * gg[j];
                 float v = st.y * (g - m1 - (fx[j] - st.x) * st.y * m2);
                 if (resid != nullptr) v += fr[j];
                 out[j] = v;
