@@ -43,14 +43,14 @@ def test_unet_tiny_odd_shapes(dev):
     y_ref = md(xr, torch.tensor(981.0, device=dev), ctx).sample
     (dx_ref,) = torch.autograd.grad((y_ref * dout).sum(), [xr])
     xn = x.clone().requires_grad_(True)
-    y = native(xn, 981.0, ctx).sample           # autograd seam: the backward recomputes the activations
+    y = native(xn, 981.0, ctx).sample           # autograd seam
     (dx,) = torch.autograd.grad((y * dout).sum(), [xn])
     assert cosine(y, y_ref) >= 0.999 and rel_err(y, y_ref) < 5e-2
     assert cosine(dx, dx_ref) >= 0.999 and rel_err(dx, dx_ref) < 1e-1
 
 
 def test_unet_checkpointed_backward_is_bit_identical(dev):
-    """keep_activations (saved state kept from the forward) and the default (forward re-run in the backward) give the
+    """keep_activations (the default: saved state kept from the forward) and the forward re-run in the backward give the
     same bits, and a sample is independent of the batch it shares (fixed-order reductions)."""
     from tests.gpu_check_unet import make_oracle, tiny_native_config
     from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet

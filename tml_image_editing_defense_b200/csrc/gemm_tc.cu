@@ -184,6 +184,30 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
         for (int d = 240; d >= 16 && BN == 0; d -= 16) if (op.N % d == 0) BN = d;
         if (BN == 0) { set_error("%s: N=%d has no column tile (a multiple of 16, at most 256)", op.name, op.N); return -1; }
     }
+    // Small problems (a few tile waves): a narrower column tile can fill the last wave better than the widest one, e.g.
+    // 4096 x 1280 (the UNet's 16 x 16 level) is 80 CTA-pair tiles of 256 columns = 2 waves of 74 pairs, but 256 tiles of
+    // 160 columns = 2 waves of 148 CTAs at 0.62 of the work per tile.  Cost model: waves x (columns + fixed per-tile cost).
+    static const bool no_bn_heur = getenv("TML_NO_BN_HEUR") && getenv("TML_NO_BN_HEUR")[0] == '1';   // A/B switch
+    if (!no_bn_heur && op.N > 256 && op.epi_mode == 0 && op.gn_mode == 0 && !op.a_trans && TW * TH > 0 &&
+        !(op.stride == 1 && op.ntaps == 9 && (op.OW % 128 == 0 || op.OW == 64))) {   // (halo modes keep their geometry)
+        const long sub = (long)op.A_B * (op.OH / TH) * (op.OW / TW);
+        const int rows_valid = TW * TH;
+        auto cost = [&](int bn) -> double {
+            const long nt = op.N / bn;
+            const bool pair = bn == 256 && rows_valid == 128 && op.ntaps * op.A_C >= 2048 && sub % 2 == 0 && sub * nt >= 4;
+            if (pair) return 0.9 * (double)((sub / 2 * nt + 73) / 74) * (bn + 48);
+            const bool mt2 = bn <= 128 && op.B_sBatch == 0 && sub % 2 == 0 && sub * nt >= 2 * 148;
+            if (mt2) return (double)((sub / 2 * nt + 147) / 148) * (2 * bn + 48);
+            return (double)((sub * nt + 147) / 148) * (bn + 48);
+        };
+        double best = cost(BN);
+        const double def = best;
+        int best_bn = BN;
+        const int cands[3] = {192, 160, 128};
+        for (int c : cands)
+            if (c < BN && op.N % c == 0 && cost(c) < best) { best = cost(c); best_bn = c; }
+        if (best < 0.85 * def) BN = best_bn;
+    }
     if (op.resid && BN < 32) { set_error("%s: residual needs N >= 32", op.name); return -1; }
     if (op.gn_mode != 0) {
         const int cpg = op.N / 32;

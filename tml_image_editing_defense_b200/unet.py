@@ -3,9 +3,11 @@
 
 Forward and the gradient w.r.t. the sample (``torch.autograd.grad(loss, [cur_image])`` through the denoising loop,
 main.py:176,229-243) run in ``csrc/unet.cu`` through the C ABI (``tml_unet_*``).  Timestep, prompt embeddings and
-weights are constants of the attack, so no other gradient exists.  The backward re-runs the forward (activation
-checkpointing per UNet call, BASELINE configs[4]) unless ``keep_activations`` is set, so only the sample, the timestep
-and the prompt embeddings stay alive between the denoising steps.
+weights are constants of the attack, so no other gradient exists.  By default the activations of every call whose sample
+requires a gradient stay in HBM until its backward (as in the reference, which keeps everything; ~10 GB per call at 16
+samples of 64 x 64 latents -- the attention probabilities are recomputed, not kept); ``keep_activations=False`` re-runs
+the forward in the backward instead (activation checkpointing per UNet call, BASELINE configs[4]), so only the sample, the
+timestep and the prompt embeddings stay alive between the denoising steps.
 
 There is no fallback: without the CUDA library or an sm_100a device construction raises.  ``unet_torch.py`` is the
 PyTorch restatement of the same module (the oracle of the tests and the library baseline), not a code path of this one.
@@ -55,7 +57,7 @@ class UNet2DConditionModel:
     """B200-native denoiser with the reference-facing surface of diffusers' module (``__call__`` -> ``.sample``)."""
     native = True   # DiffusionAttack passes the timestep as a host scalar
 
-    def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda:0", keep_activations: bool = False):
+    def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda:0", keep_activations: bool = True):
         self.config = config or UNetConfig()
         self.device = torch.device(device)
         if self.device.type != "cuda":
