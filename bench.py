@@ -591,9 +591,16 @@ def run_diffusion(args):
     from tml_image_editing_defense_b200.unet_torch import UNet2DConditionModel
     from tml_image_editing_defense_b200.vae import AutoencoderKL
     from tml_image_editing_defense_b200.weights import random_init_state_dict
-    dev = torch.device("cuda:0")
-    torch.cuda.set_device(0)
-    B, res = args.batch, args.res
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:   # images shard r::world with no data-path collective, exactly like the encoder attack
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, res = args.batch, args.res   # images per GPU (weak scaling: the step of one image is what the memory bounds)
     vae = AutoencoderKL(device=str(dev)).load_state_dict(random_init_state_dict(seed=0, include_decoder=True))
     native = args.unet == "native"
     if native:
@@ -615,7 +622,7 @@ def run_diffusion(args):
                       perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=4, limit_timesteps=False)
     da = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=not native,
                          unet_dtype=torch.float32 if native else torch.bfloat16)
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator().manual_seed(rank)
     x = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
     tgt = (torch.rand((B, 3, res, res), generator=g) * 2 - 1).to(dev)
     pe = torch.randn((2, 77, 768), generator=g).to(dev)
@@ -627,9 +634,14 @@ def run_diffusion(args):
         ops.pgd_step_linf_(x_adv, grad.contiguous(), x, EPS, STEP, LO, HI)
         return loss
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):   # (0 is allowed: profiler runs)
         step()
-    torch.cuda.synchronize()
+    barrier()
     c0 = _lib.launch_counts()
     if args.gemm_table:
         _lib.load().tml_gemm_timing_enable(200000)
@@ -638,9 +650,13 @@ def run_diffusion(args):
     for _ in range(args.steps):
         loss = step()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     c1 = _lib.launch_counts()
     ms = e0.elapsed_time(e1)
+    if world > 1:   # device time, max over ranks
+        t_ = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms = float(t_.item())
     extra = {}
     if args.gemm_table:
         gt = (C.c_double * 4)()
@@ -653,8 +669,14 @@ def run_diffusion(args):
                  + ("activations recomputed per denoising step in the backward)" if args.unet_recompute else
                     "activations of all denoising steps kept in HBM, attention probabilities recomputed)") if native else
                  "the PyTorch library UNet (unet_torch.py: cuDNN / cuBLAS / SDPA, bf16 autocast, torch.utils.checkpoint)")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
     print(json.dumps({"mode": "diffusion", "unet": args.unet, "metric": "image-PGD-iters/sec",
-                      "value": B * args.steps / (ms / 1e3),
+                      "value": world * B * args.steps / (ms / 1e3), "n_gpus": world, "scaling": "weak",
+                      "per_gpu_batch": B,
                       "ms_per_step": ms / args.steps, "steps": args.steps, "loss": float(loss),
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                       "gpu_launches": (c1[0] - c0[0]) + (c1[1] - c0[1]), **extra,

@@ -249,18 +249,19 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap mapV,
                                                                     const FaParams p) {
     constexpr int NC = DP / 64;
+    constexpr int KS = DP == 64 ? 3 : 2;        // K / V ring depth: the TMA round trip is longer than one 64-key tile
     constexpr int kBig = 128 * 128, kSmall = 64 * 128;
     constexpr int kQBytes = NC * kBig, kKBytes = NC * kSmall;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kQBytes;
-    uint8_t* sV = sK + 2 * kKBytes;
-    uint8_t* sP = sV + 2 * kKBytes;
+    uint8_t* sV = sK + KS * kKBytes;
+    uint8_t* sP = sV + KS * kKBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kBig);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = bars + 3;
+    uint64_t* kv_full = bars + 16;              // [KS]
+    uint64_t* kv_empty = bars + 20;             // [KS]
     uint64_t* s_full = bars + 5;
     uint64_t* s_empty = bars + 7;
     uint64_t* p_full = bars + 9;
@@ -272,9 +273,8 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
     const int ntiles = p.tkv / 64;
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
+        for (int i = 0; i < KS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 128);
             mbar_init(&p_full[i], 128);
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
             mbar_arrive_expect_tx(q_full, kQBytes);
             for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * kBig, &mapQ, q_full, c * 64, q0, batch);
             for (int j = 0; j < ntiles; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
+                const int s = j % KS;
+                mbar_wait(&kv_empty[s], (((j / KS) & 1) ^ 1));
                 mbar_arrive_expect_tx(&kv_full[s], 2 * kKBytes);
                 for (int c = 0; c < NC; ++c) {
                     tma_load_3d(sK + s * kKBytes + c * kSmall, &mapK, &kv_full[s], c * 64, j * 64, batch);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
         mbar_wait(q_full, 0);
         tc_fence_after();
         auto issue_pv = [&](int j) {
-            const int s = j & 1, b = j & 1;
+            const int s = j % KS, b = j & 1;
             mbar_wait(&p_full[b], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t pa = smem_u32(sP + b * kBig), va = smem_u32(sV + s * kKBytes);
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
             __syncwarp();
         };
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j & 1;
-            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            const int s = j % KS;
+            mbar_wait(&kv_full[s], (j / KS) & 1);
             mbar_wait(&s_empty[0], ((j & 1) ^ 1));
             tc_fence_after();
             const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + s * kKBytes);
@@ -457,7 +457,8 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
         if ((rc = encode_map_bf16_sw128(&mv, V, 3, dims, str, box64, "attn.fused.V"))) return rc;
     }
     constexpr int kBig = 128 * 128, kSmall = 64 * 128;
-    constexpr size_t smem = size_t(DP / 64) * (kBig + 4 * kSmall) + 2 * kBig + 256 + 1024;
+    constexpr int KS = DP == 64 ? 3 : 2;   // (both forward kernels are given the online kernel's deeper K / V ring)
+    constexpr size_t smem = size_t(DP / 64) * (kBig + 2 * KS * kSmall) + 2 * kBig + 256 + 1024;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -536,19 +537,20 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
                                                                    const __grid_constant__ CUtensorMap mapV,
                                                                    const FbParams p) {
     constexpr int NC = DP / 64;
+    constexpr int KS = DP == 64 ? 3 : 2;        // K / V ring depth: the TMA round trip is longer than one 64-key tile
     constexpr int kBig = 128 * 128, kSmall = 64 * 128;    // [128 rows][128 B], [64 rows][128 B]
     constexpr int kQBytes = NC * kBig, kKBytes = NC * kSmall;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sDO = sQ + kQBytes;
     uint8_t* sK = sDO + kQBytes;                // 2 stages
-    uint8_t* sV = sK + 2 * kKBytes;             // 2 stages
-    uint8_t* sDS = sV + 2 * kKBytes;            // 2 buffers of [128 rows][64 keys]
+    uint8_t* sV = sK + KS * kKBytes;             // 2 stages
+    uint8_t* sDS = sV + KS * kKBytes;           // 2 buffers of [128 rows][64 keys]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBig);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = bars + 3;
+    uint64_t* kv_full = bars + 16;              // [KS]
+    uint64_t* kv_empty = bars + 20;             // [KS]
     uint64_t* sd_full = bars + 5;
     uint64_t* sd_empty = bars + 7;
     uint64_t* ds_full = bars + 9;
@@ -560,8 +562,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
     const int ntiles = p.tkv / 64;
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
+        for (int i = 0; i < KS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
             mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], kSmThreads);
             mbar_init(&ds_full[i], kSmThreads); mbar_init(&ds_empty[i], 1);
         }
@@ -571,6 +573,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
     // 256 TMEM columns (S | dP' single-buffered: the softmax warps free them as soon as they are in registers, + dQ) and
     // ~100 KB of shared memory: two CTAs share an SM and fill each other's pipeline bubbles
     if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (DP == 64 && smem != smem_raw) __trap();   // the launch requests no alignment slack at DP = 64 (112 KB + barriers)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -584,8 +587,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
                 tma_load_3d(sDO + c * kBig, &mapDO, q_full, c * 64, q0, batch);
             }
             for (int j = 0; j < ntiles; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], (((j >> 1) & 1) ^ 1));
+                const int s = j % KS;
+                mbar_wait(&kv_empty[s], (((j / KS) & 1) ^ 1));
                 mbar_arrive_expect_tx(&kv_full[s], 2 * kKBytes);
                 for (int c = 0; c < NC; ++c) {
                     tma_load_3d(sK + s * kKBytes + c * kSmall, &mapK, &kv_full[s], c * 64, j * 64, batch);
@@ -599,7 +602,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
         mbar_wait(q_full, 0);
         tc_fence_after();
         auto issue_acc = [&](int j) {
-            const int s = j & 1, b = j & 1;
+            const int s = j % KS, b = j & 1;
             mbar_wait(&ds_full[b], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t da = smem_u32(sDS + b * kBig), ka = smem_u32(sK + s * kKBytes);
@@ -614,8 +617,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
             __syncwarp();
         };
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j & 1;
-            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            const int s = j % KS;
+            mbar_wait(&kv_full[s], (j / KS) & 1);
             mbar_wait(&sd_empty[0], ((j & 1) ^ 1));
             tc_fence_after();
             const uint32_t qa = smem_u32(sQ), oa = smem_u32(sDO), ka = smem_u32(sK + s * kKBytes), va = smem_u32(sV + s * kKBytes);
@@ -701,21 +704,22 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
                                                                     const __grid_constant__ CUtensorMap mapDO,
                                                                     const FbParams p) {
     constexpr int NC = DP / 64;
+    constexpr int QS = DP == 64 ? 3 : 2;        // Q / dO' ring depth (the TMA round trip is longer than one 64-query tile)
     constexpr int kBig = 128 * 128, kSmall = 64 * 128;
     constexpr int kKBytes = NC * kBig, kQBytes = NC * kSmall;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
     uint8_t* sV = sK + kKBytes;
     uint8_t* sQ = sV + kKBytes;                 // 2 stages of [64 queries][DP]
-    uint8_t* sDO = sQ + 2 * kQBytes;            // 2 stages
-    uint8_t* sPT = sDO + 2 * kQBytes;           // [128 keys][64 queries]
+    uint8_t* sDO = sQ + QS * kQBytes;
+    uint8_t* sPT = sDO + QS * kQBytes;          // [128 keys][64 queries]
     uint8_t* sDST = sPT + kBig;
-    float2* cvec = reinterpret_cast<float2*>(sDST + kBig);   // [2][64] (-m*c, D') of the tile's queries
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + 128);
+    float2* cvec = reinterpret_cast<float2*>(sDST + kBig);   // [64] (-m*c, -D'*scale) of the tile's queries
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + 64);
     uint64_t* kv_full = bars;
-    uint64_t* qd_full = bars + 1;
-    uint64_t* qd_empty = bars + 3;
+    uint64_t* qd_full = bars + 16;              // [QS]
+    uint64_t* qd_empty = bars + 20;             // [QS]
     uint64_t* sd_full = bars + 5;
     uint64_t* sd_empty = bars + 7;
     uint64_t* pd_full = bars + 9;
@@ -727,8 +731,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
     const int ntiles = p.tq / 64;
     if (threadIdx.x == 0) {
         mbar_init(kv_full, 1);
+        for (int i = 0; i < QS; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
             mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], kSmThreads);
             mbar_init(&pd_full[i], kSmThreads); mbar_init(&pd_empty[i], 1);
         }
@@ -738,6 +742,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
     // DP = 64: 256 TMEM columns (S^T | dP'^T single-buffered + dV + dK) and 96 KB of shared memory -> two CTAs per SM
     constexpr uint32_t kTmemCols = DP == 64 ? 256 : 512;
     if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    if (DP == 64 && smem != smem_raw) __trap();   // the launch requests no alignment slack at DP = 64 (112 KB + constants + barriers)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -751,8 +756,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
                 tma_load_3d(sV + c * kBig, &mapV, kv_full, c * 64, k0, batch);
             }
             for (int i = 0; i < ntiles; ++i) {
-                const int s = i & 1;
-                mbar_wait(&qd_empty[s], (((i >> 1) & 1) ^ 1));
+                const int s = i % QS;
+                mbar_wait(&qd_empty[s], (((i / QS) & 1) ^ 1));
                 mbar_arrive_expect_tx(&qd_full[s], 2 * kQBytes);
                 for (int c = 0; c < NC; ++c) {
                     tma_load_3d(sQ + s * kQBytes + c * kSmall, &mapQ, &qd_full[s], c * 64, i * 64, batch);
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
         mbar_wait(kv_full, 0);
         tc_fence_after();
         auto issue_acc = [&](int i) {
-            const int s = i & 1;
+            const int s = i % QS;
             mbar_wait(&pd_full[0], i & 1);
             tc_fence_after();
             const uint32_t pa = smem_u32(sPT), da = smem_u32(sDST);
@@ -785,8 +790,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
             __syncwarp();
         };
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i & 1;
-            mbar_wait(&qd_full[s], (i >> 1) & 1);
+            const int s = i % QS;
+            mbar_wait(&qd_full[s], (i / QS) & 1);
             mbar_wait(&sd_empty[0], ((i & 1) ^ 1));
             tc_fence_after();
             const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQ + s * kQBytes), oa = smem_u32(sDO + s * kQBytes);
@@ -817,17 +822,17 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
         const float c = p.exp_scale, sc = p.scale;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
         for (int i = 0; i < ntiles; ++i) {
-            const int b = i & 1;
-            if (st < 64) {   // this tile's per-query constants (buffer b was last read two tiles ago, before a barrier)
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has finished reading the previous tile's constants
+            if (st < 64) {   // this tile's per-query constants
                 const long long gq = (long long)batch * p.tq + i * 64 + st;
-                cvec[b * 64 + st] = make_float2(-__ldg(p.rmax + gq) * c, -__ldg(p.Dp + gq) * sc);
+                cvec[st] = make_float2(-__ldg(p.rmax + gq) * c, -__ldg(p.Dp + gq) * sc);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&sd_full[0], i & 1);
             tc_fence_after();
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
-            const float2* cv = cvec + b * 64 + half * 32;
+            const float2* cv = cvec + half * 32;
             uint32_t vs[32], vd[32];
             tmem_ld32(t_row + uint32_t(half * 32), vs);
             tmem_ld32(t_row + uint32_t(64 + half * 32), vd);
@@ -898,8 +903,9 @@ int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     if ((rc = encode_map_bf16_sw128(&mk64, K, 3, dk, sk, box64, "attn.bwd.K64"))) return rc;
     if ((rc = encode_map_bf16_sw128(&mv64, V, 3, dk, sk, box64, "attn.bwd.V64"))) return rc;
     constexpr int NC = DP / 64, kBig = 128 * 128, kSmall = 64 * 128;
-    constexpr size_t smem_dq = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 256 + 1024;
-    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 1024 + 256 + 1024;
+    constexpr int KS = DP == 64 ? 3 : 2;
+    constexpr size_t smem_dq = size_t(2 * NC) * kBig + size_t(2 * KS * NC) * kSmall + 2 * kBig + 256 + (DP == 64 ? 0 : 1024);
+    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(2 * KS * NC) * kSmall + 2 * kBig + 512 + 256 + (DP == 64 ? 0 : 1024);
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
