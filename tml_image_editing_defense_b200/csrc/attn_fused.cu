@@ -495,6 +495,7 @@ int launch_fa(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
 struct FbParams {
     const float* rmax;    // [nb][tq]
     const float* Dp;      // [nb][tq]  D' = (dO . O) / l
+    const float2* cq;     // [nb][tq]  (-rmax * scale * log2 e, -D' * scale): the dK/dV kernel's per-query constants
     __nv_bfloat16* dQ;    // [nb][tq][DP]            (dq kernel)
     __nv_bfloat16* dK;    // [nb][tkv][DP]           (dkv kernel)
     __nv_bfloat16* dV;
@@ -505,8 +506,10 @@ struct FbParams {
 // one warp per row: D'[row] = il * sum_c dO[row][c] * O[row][c];  dOs[row][c] = dO[row][c] * il
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO,
                                                             const __nv_bfloat16* __restrict__ O,
-                                                            const float* __restrict__ inv_l, __nv_bfloat16* __restrict__ dOs,
-                                                            float* __restrict__ Dp, long long rows, int DP) {
+                                                            const float* __restrict__ inv_l, const float* __restrict__ rmax,
+                                                            __nv_bfloat16* __restrict__ dOs, float* __restrict__ Dp,
+                                                            float2* __restrict__ cq, float exp_scale, float scale,
+                                                            long long rows, int DP) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -527,7 +530,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) Dp[row] = acc * il;
+    if (lane == 0) {
+        Dp[row] = acc * il;
+        cq[row] = make_float2(-__ldg(rmax + row) * exp_scale, -acc * il * scale);
+    }
 }
 
 template <int DP>
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
                                                                     const __grid_constant__ CUtensorMap mapDO,
                                                                     const FbParams p) {
     constexpr int NC = DP / 64;
-    constexpr int QS = DP == 64 ? 3 : 2;        // Q / dO' ring depth (the TMA round trip is longer than one 64-query tile)
+    constexpr int QS = 2;                       // Q / dO' / constants ring (a third stage measured no gain here)
     constexpr int kBig = 128 * 128, kSmall = 64 * 128;
     constexpr int kKBytes = NC * kBig, kQBytes = NC * kSmall;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -715,8 +721,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
     uint8_t* sDO = sQ + QS * kQBytes;
     uint8_t* sPT = sDO + QS * kQBytes;          // [128 keys][64 queries]
     uint8_t* sDST = sPT + kBig;
-    float2* cvec = reinterpret_cast<float2*>(sDST + kBig);   // [64] (-m*c, -D'*scale) of the tile's queries
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + 64);
+    float2* cvec = reinterpret_cast<float2*>(sDST + kBig);   // [QS][64] (-m*c, -D'*scale) of a tile's queries, part of the ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cvec + QS * 64);
     uint64_t* kv_full = bars;
     uint64_t* qd_full = bars + 16;              // [QS]
     uint64_t* qd_empty = bars + 20;             // [QS]
@@ -758,7 +764,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % QS;
                 mbar_wait(&qd_empty[s], (((i / QS) & 1) ^ 1));
-                mbar_arrive_expect_tx(&qd_full[s], 2 * kQBytes);
+                mbar_arrive_expect_tx(&qd_full[s], 2 * kQBytes + 512);
+                bulk_load_1d(cvec + s * 64, p.cq + (long long)batch * p.tq + i * 64, 512, &qd_full[s]);
                 for (int c = 0; c < NC; ++c) {
                     tma_load_3d(sQ + s * kQBytes + c * kSmall, &mapQ, &qd_full[s], c * 64, i * 64, batch);
                     tma_load_3d(sDO + s * kQBytes + c * kSmall, &mapDO, &qd_full[s], c * 64, i * 64, batch);
@@ -817,22 +824,16 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
     } else {
         const int quad = warp & 3, half = (warp - 2) >> 2;   // thread = (key row, 32-query half of the tile)
         const int row = quad * 32 + lane;
-        const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
         const long long gkey = (long long)batch * p.tkv + k0 + row;
         const float c = p.exp_scale, sc = p.scale;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16);
         for (int i = 0; i < ntiles; ++i) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has finished reading the previous tile's constants
-            if (st < 64) {   // this tile's per-query constants
-                const long long gq = (long long)batch * p.tq + i * 64 + st;
-                cvec[st] = make_float2(-__ldg(p.rmax + gq) * c, -__ldg(p.Dp + gq) * sc);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&qd_full[i % QS], (i / QS) & 1);   // (long complete: the logits below were issued after it) the constants landed
             mbar_wait(&sd_full[0], i & 1);
             tc_fence_after();
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
-            const float2* cv = cvec + half * 32;
+            const float2* cv = cvec + (i % QS) * 64 + half * 32;
             uint32_t vs[32], vd[32];
             tmem_ld32(t_row + uint32_t(half * 32), vs);
             tmem_ld32(t_row + uint32_t(64 + half * 32), vd);
@@ -887,7 +888,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
 
 template <int DP>
 int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, const __nv_bfloat16* dOs,
-              const float* rmax, const float* Dp, __nv_bfloat16* dQ, __nv_bfloat16* dK, __nv_bfloat16* dV, int nb, int tq,
+              const float* rmax, const float* Dp, const float2* cq, __nv_bfloat16* dQ, __nv_bfloat16* dK, __nv_bfloat16* dV, int nb, int tq,
               int tkv, float scale, cudaStream_t st) {
     CUtensorMap mq128, mo128, mk64, mv64, mk128, mv128, mq64, mo64;
     int rc;
@@ -905,7 +906,7 @@ int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
     constexpr int NC = DP / 64, kBig = 128 * 128, kSmall = 64 * 128;
     constexpr int KS = DP == 64 ? 3 : 2;
     constexpr size_t smem_dq = size_t(2 * NC) * kBig + size_t(2 * KS * NC) * kSmall + 2 * kBig + 256 + (DP == 64 ? 0 : 1024);
-    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(2 * KS * NC) * kSmall + 2 * kBig + 512 + 256 + (DP == 64 ? 0 : 1024);
+    constexpr size_t smem_dkv = size_t(2 * NC) * kBig + size_t(4 * NC) * kSmall + 2 * kBig + 1024 + 256 + 1024;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -917,7 +918,7 @@ int launch_fb(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat1
         attr_set[dev & 63] = true;
     }
     FbParams p;
-    p.rmax = rmax; p.Dp = Dp; p.dQ = dQ; p.dK = dK; p.dV = dV; p.tq = tq; p.tkv = tkv;
+    p.rmax = rmax; p.Dp = Dp; p.cq = cq; p.dQ = dQ; p.dK = dK; p.dV = dV; p.tq = tq; p.tkv = tkv;
     p.scale = scale; p.exp_scale = scale * 1.4426950408889634f;
     attn_bwd_dq_kernel<DP><<<dim3(tq / 128, nb), kFaThreads, smem_dq, st>>>(mq128, mo128, mk64, mv64, p);
     if (dK != nullptr && dV != nullptr)   // (cross attention: keys / values are constants of the attack)
@@ -953,17 +954,20 @@ int launch_attn_fused_fwd(const bf16* Q, const bf16* K, const bf16* V, const flo
 }
 
 // Fused backward of the same attention: dO [nb][tq][dp], O, inv_l, rmax from the forward; dOs (bf16 [nb][tq][dp]) and
-// Dp (fp32 [nb][tq]) are scratch.  Writes dQ [nb][tq][dp], dK and dV [nb][tkv][dp] (both null: dQ only).
+// Dp (fp32, 3 * nb * tq + 4 floats: D' then the dK/dV kernel's per-query constants) are scratch.  Writes dQ [nb][tq][dp], dK and dV [nb][tkv][dp] (both null: dQ only).
 int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf16* O, const bf16* dO, const float* rmax,
                           const float* inv_l, bf16* dOs, float* Dp, bf16* dQ, bf16* dK, bf16* dV, int nb, int tq, int tkv,
                           int dp, float scale, cudaStream_t st) {
     if (g_dry_run) return 0;
     if (!attn_fused_supported(tq, tkv, dp)) { set_error("attn.bwd: unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
     const long long rows = (long long)nb * tq;
-    attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dO, O, inv_l, dOs, Dp, rows, dp);
+    // Dp scratch: [rows] D' followed by [rows] float2 per-query constants of the dK/dV kernel (3 floats per row)
+    float2* cq = reinterpret_cast<float2*>(Dp + ((rows + 3) & ~3LL));
+    attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dO, O, inv_l, rmax, dOs, Dp, cq, scale * 1.4426950408889634f,
+                                                                    scale, rows, dp);
     count_launch();
-    if (dp == 64) return launch_fb<64>(Q, K, V, dOs, rmax, Dp, dQ, dK, dV, nb, tq, tkv, scale, st);
-    return launch_fb<128>(Q, K, V, dOs, rmax, Dp, dQ, dK, dV, nb, tq, tkv, scale, st);
+    if (dp == 64) return launch_fb<64>(Q, K, V, dOs, rmax, Dp, cq, dQ, dK, dV, nb, tq, tkv, scale, st);
+    return launch_fb<128>(Q, K, V, dOs, rmax, Dp, cq, dQ, dK, dV, nb, tq, tkv, scale, st);
 }
 
 }  // namespace tml

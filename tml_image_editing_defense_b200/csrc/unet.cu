@@ -387,7 +387,7 @@ int mh_attention_backward(URun& r, const bf16* Q, const bf16* K, const bf16* V, 
     if (P == nullptr && !no_fused_bwd && attn_fused_supported(tq, tkv, dp)) {
         // fused (attn_fused.cu): S and dP are recomputed on the tensor cores inside the two backward kernels
         bf16* dOs = r.Walloc<bf16>((size_t)rows * dp * sizeof(bf16));
-        float* Dp = r.Walloc<float>((size_t)rows * sizeof(float));
+        float* Dp = r.Walloc<float>(((size_t)rows * 3 + 8) * sizeof(float));   // D' + per-query constants
         RC(launch_attn_fused_bwd(Q, K, V, O, dO, rmax, inv_l, dOs, Dp, dQ, dK, dV, nb, tq, tkv, dp, scale, r.st));
         r.wsa.reset(m);
         return 0;
