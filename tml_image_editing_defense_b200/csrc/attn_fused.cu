@@ -59,6 +59,16 @@ __device__ __forceinline__ uint32_t fa_pack(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// explicit shared-space accesses (the tile pointers are derived from a rounded-up integer address, so the compiler would
+// otherwise emit generic ST.E / LD.E for them)
+__device__ __forceinline__ void fa_sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 fa_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float fa_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float fa_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) mh_attn_fwd_kernel(const __grid
                 const uint4 o = make_uint4(fa_pack(f[8 * u], f[8 * u + 1]), fa_pack(f[8 * u + 2], f[8 * u + 3]),
                                            fa_pack(f[8 * u + 4], f[8 * u + 5]), fa_pack(f[8 * u + 6], f[8 * u + 7]));
                 const int unit = half * 4 + u;
-                *reinterpret_cast<uint4*>(dst + ((unit ^ (row & 7)) << 4)) = o;
+                fa_sts128(smem_u32(dst) + ((unit ^ (row & 7)) << 4), o);
             }
             fence_proxy_async();
             mbar_arrive(&p_full[b]);
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(192, 2) mh_attn_fwd_online_kernel(const __grid
                     fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 2]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 3]), c, ra))),
                     fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 4]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 5]), c, ra))),
                     fa_pack(fa_ex2(fmaf(__uint_as_float(vv[k + 6]), c, ra)), fa_ex2(fmaf(__uint_as_float(vv[k + 7]), c, ra))));
-                *reinterpret_cast<uint4*>(dst + ((u ^ (row & 7)) << 4)) = o;
+                fa_sts128(smem_u32(dst) + ((u ^ (row & 7)) << 4), o);
             }
             fence_proxy_async();
             mbar_arrive(&p_full[b]);
@@ -503,34 +513,36 @@ struct FbParams {
     float exp_scale, scale;
 };
 
-// one warp per row: D'[row] = il * sum_c dO[row][c] * O[row][c];  dOs[row][c] = dO[row][c] * il
+// eight lanes per row (DP / 8 = 8 or 16 octets): D'[row] = il * sum_c dO[row][c] * O[row][c];  dOs[row][c] = dO[row][c] * il;
+// cq[row] = (-rmax * scale * log2 e, -D' * scale)
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO,
                                                             const __nv_bfloat16* __restrict__ O,
                                                             const float* __restrict__ inv_l, const float* __restrict__ rmax,
                                                             __nv_bfloat16* __restrict__ dOs, float* __restrict__ Dp,
                                                             float2* __restrict__ cq, float exp_scale, float scale,
                                                             long long rows, int DP) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float il = __ldg(inv_l + row);
+    const int sub = threadIdx.x & 7;
+    const long long row = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const bool live = row < rows;
+    const float il = live ? __ldg(inv_l + row) : 0.f;
     float acc = 0.f;
-    for (int o = lane; o < (DP >> 3); o += 32) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + row * DP) + o);
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(O + row * DP) + o);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-        uint32_t ow[4];
+    if (live)
+        for (int o = sub; o < (DP >> 3); o += 8) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + row * DP) + o);
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(O + row * DP) + o);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+            uint32_t ow[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            acc = fmaf(fa_lo(aw[k]), fa_lo(bw[k]), acc);
-            acc = fmaf(fa_hi(aw[k]), fa_hi(bw[k]), acc);
-            ow[k] = fa_pack(fa_lo(aw[k]) * il, fa_hi(aw[k]) * il);
+            for (int k = 0; k < 4; ++k) {
+                acc = fmaf(fa_lo(aw[k]), fa_lo(bw[k]), acc);
+                acc = fmaf(fa_hi(aw[k]), fa_hi(bw[k]), acc);
+                ow[k] = fa_pack(fa_lo(aw[k]) * il, fa_hi(aw[k]) * il);
+            }
+            reinterpret_cast<uint4*>(dOs + row * DP)[o] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
-        reinterpret_cast<uint4*>(dOs + row * DP)[o] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) {
         Dp[row] = acc * il;
         cq[row] = make_float2(-__ldg(rmax + row) * exp_scale, -acc * il * scale);
     }
@@ -676,7 +688,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dq_kernel(const __grid
                                    fa_ex2(fmaf(__uint_as_float(vs[i + 1]), c, ra)) * fmaf(__uint_as_float(vd[i + 1]), sc, dpr));
                 }
                 const int unit = half * 4 + u;
-                *reinterpret_cast<uint4*>(drow + ((unit ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                fa_sts128(smem_u32(drow) + ((unit ^ (row & 7)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
             }
             fence_proxy_async();
             mbar_arrive(&ds_full[b]);
@@ -833,7 +845,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
             tc_fence_after();
             uint8_t* prow = sPT + row * 128;
             uint8_t* drow = sDST + row * 128;
-            const float2* cv = cvec + (i % QS) * 64 + half * 32;
+            const uint32_t cv_addr = smem_u32(cvec + (i % QS) * 64 + half * 32);
             uint32_t vs[32], vd[32];
             tmem_ld32(t_row + uint32_t(half * 32), vs);
             tmem_ld32(t_row + uint32_t(64 + half * 32), vd);
@@ -847,7 +859,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int i2 = 8 * u + 2 * k;
-                    const float2 c0 = cv[i2], c1 = cv[i2 + 1];
+                    const float4 cc = fa_lds128(cv_addr + uint32_t(i2) * 8u);   // two queries' (-m*c, -D'*scale)
+                    const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
                     const float p0 = fa_ex2(fmaf(__uint_as_float(vs[i2]), c, c0.x));
                     const float p1 = fa_ex2(fmaf(__uint_as_float(vs[i2 + 1]), c, c1.x));
                     wp[k] = fa_pack(p0, p1);
@@ -855,8 +868,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_bwd_dkv_kernel(const __gri
                 }
                 const int unit = half * 4 + u;
                 const int off = (unit ^ (row & 7)) << 4;
-                *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-                *reinterpret_cast<uint4*>(drow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                fa_sts128(smem_u32(prow) + off, make_uint4(wp[0], wp[1], wp[2], wp[3]));
+                fa_sts128(smem_u32(drow) + off, make_uint4(wd[0], wd[1], wd[2], wd[3]));
             }
             fence_proxy_async();
             mbar_arrive(&pd_full[0]);
@@ -963,7 +976,7 @@ int launch_attn_fused_bwd(const bf16* Q, const bf16* K, const bf16* V, const bf1
     const long long rows = (long long)nb * tq;
     // Dp scratch: [rows] D' followed by [rows] float2 per-query constants of the dK/dV kernel (3 floats per row)
     float2* cq = reinterpret_cast<float2*>(Dp + ((rows + 3) & ~3LL));
-    attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dO, O, inv_l, rmax, dOs, Dp, cq, scale * 1.4426950408889634f,
+    attn_bwd_prep_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(dO, O, inv_l, rmax, dOs, Dp, cq, scale * 1.4426950408889634f,
                                                                     scale, rows, dp);
     count_launch();
     if (dp == 64) return launch_fb<64>(Q, K, V, dOs, rmax, Dp, cq, dQ, dK, dV, nb, tq, tkv, scale, st);

@@ -689,7 +689,7 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                         if (has_bias) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+                                const float4 b4 = lds_f4(smem_u32(bias_s + c + 4 * j));
                                 f[4 * j] = fmaf(__uint_as_float(v[4 * j]), al, b4.x);
                                 f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), al, b4.y);
                                 f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), al, b4.z);
@@ -737,16 +737,16 @@ __device__ __forceinline__ void lean_epilogue(const TcParams& p, const CUtensorM
                         // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) =
-                                make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+                            sts_u4(smem_u32(rowp) + ((j ^ (lane & 7)) << 4),
+                                   make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                              __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
                     } else {
                         // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint4 o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                                        pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+                            sts_u4(smem_u32(rowp) + ((j ^ ((lane >> 1) & 3)) << 4), o);
                             if (mode == 2)   // the softmax denominator sums the probabilities as stored (bf16), in a fixed order
                                 red += ((bf16_lo(o.x) + bf16_hi(o.x)) + (bf16_lo(o.y) + bf16_hi(o.y))) +
                                        ((bf16_lo(o.z) + bf16_hi(o.z)) + (bf16_lo(o.w) + bf16_hi(o.w)));
