@@ -259,7 +259,11 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
         const long cta_m_tiles = (long)op.A_B * t->tiles_h;
         static const bool no_pair66 = getenv("TML_PAIR") && getenv("TML_PAIR")[0] == '0';   // tuning switch
         // (a pair = the same tile of two consecutive images, see decode_sub: needs an even number of images)
-        t->pair = (!no_pair66 && BN == 256 && op.A_B % 2 == 0 && cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
+        // (narrower column tiles, e.g. 160 of the UNet's 320-channel layers, pair up as well: each CTA stages half of the
+        // weight tile, which is what bounds these layers -- 80 B/clk/SM from L2 on single CTAs)
+        static const int pair66_min_bn = getenv("TML_H66_PAIR_MIN_BN") ? atoi(getenv("TML_H66_PAIR_MIN_BN")) : 256;   // experiment switch
+        t->pair = (!no_pair66 && (BN == 256 || (BN >= pair66_min_bn && BN % 32 == 0)) && op.A_B % 2 == 0 &&
+                   cta_m_tiles * t->n_tiles >= 4) ? 1 : 0;
         t->stage_bytes = (t->pair ? BN / 2 : BN) * 128;
         int stages = (kMaxSmem - 1024 - kBarrierBytes - kGnSmemBytes - 2 * t->halo_bytes) / t->stage_bytes;
         if (stages > 8) stages = 8;
