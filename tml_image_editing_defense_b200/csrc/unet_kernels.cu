@@ -283,8 +283,9 @@ void launch_gng_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const
 // One warp per row; a lane keeps its octets (C/8 of them over 32 lanes, at most 8 each: C <= 2048) in registers,
 // mean and variance are two passes over the registers.  stats[row] = (mean, rstd) for the backward.
 // ================================================================================================
-constexpr int kLnMaxOct = 8;
+constexpr int kLnMaxOct = 8;   // widest instantiation: C <= 2048 (the register arrays are sized per instantiation)
 
+template <int MAXO>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
                                                      float2* __restrict__ stats, long long rows, int C, float eps) {
@@ -292,10 +293,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int C8 = C >> 3;
-    uint4 v[kLnMaxOct];
+    uint4 v[MAXO];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxOct; ++i) {
+    for (int i = 0; i < MAXO; ++i) {
         const int o = lane + 32 * i;
         if (o < C8) {
             v[i] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + (size_t)o * 8));
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     const float mean = u_warp_sum(s) / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxOct; ++i) {
+    for (int i = 0; i < MAXO; ++i) {
         const int o = lane + 32 * i;
         if (o < C8) {
             float f[8];
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     const float rstd = rsqrtf(u_warp_sum(q) / (float)C + eps);
     if (lane == 0) stats[row] = make_float2(mean, rstd);
 #pragma unroll
-    for (int i = 0; i < kLnMaxOct; ++i) {
+    for (int i = 0; i < MAXO; ++i) {
         const int o = lane + 32 * i;
         if (o < C8) {
             float f[8];
@@ -339,11 +340,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 void launch_ln_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, long long rows, int C,
                    float eps, cudaStream_t s) {
     if (g_dry_run) return;
-    ln_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, gamma, beta, y, stats, rows, C, eps);
+    const int per_lane = ((C >> 3) + 31) / 32;   // octets per lane
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (per_lane <= 2) ln_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, C, eps);
+    else if (per_lane <= 3) ln_fwd_kernel<3><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, C, eps);
+    else if (per_lane <= 5) ln_fwd_kernel<5><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, C, eps);
+    else ln_fwd_kernel<kLnMaxOct><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, C, eps);
     COUNT_LAUNCH();
 }
 
 // dx = rstd * (g - mean(g) - xh * mean(g * xh)) [+ resid],  g = dy * gamma,  xh = (x - mean) * rstd
+template <int MAXO>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                      const float* __restrict__ gamma, const float2* __restrict__ stats,
                                                      const bf16* __restrict__ resid, bf16* __restrict__ dx,
@@ -354,10 +361,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
     const int C8 = C >> 3;
     const float2 st = stats[row];
     // x and dy stay packed in registers between the two passes (gamma is re-read as two float4 per octet: L1 hits)
-    uint4 vx[kLnMaxOct], vd[kLnMaxOct];
+    uint4 vx[MAXO], vd[MAXO];
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxOct; ++i) {
+    for (int i = 0; i < MAXO; ++i) {
         const int o = lane + 32 * i;
         if (o < C8) {
             vx[i] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + (size_t)o * 8));
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
     }
     const float m1 = u_warp_sum(a) / (float)C, m2 = u_warp_sum(b) / (float)C;
 #pragma unroll
-    for (int i = 0; i < kLnMaxOct; ++i) {
+    for (int i = 0; i < MAXO; ++i) {
         const int o = lane + 32 * i;
         if (o < C8) {
             float fx[8], fd[8], fr[8], out[8];
@@ -404,7 +411,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
 void launch_ln_bwd(const bf16* x, const bf16* dy, const float* gamma, const float2* stats, const bf16* resid, bf16* dx,
                    long long rows, int C, cudaStream_t s) {
     if (g_dry_run) return;
-    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, dy, gamma, stats, resid, dx, rows, C);
+    const int per_lane = ((C >> 3) + 31) / 32;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (per_lane <= 2) ln_bwd_kernel<2><<<grid, 256, 0, s>>>(x, dy, gamma, stats, resid, dx, rows, C);
+    else if (per_lane <= 3) ln_bwd_kernel<3><<<grid, 256, 0, s>>>(x, dy, gamma, stats, resid, dx, rows, C);
+    else if (per_lane <= 5) ln_bwd_kernel<5><<<grid, 256, 0, s>>>(x, dy, gamma, stats, resid, dx, rows, C);
+    else ln_bwd_kernel<kLnMaxOct><<<grid, 256, 0, s>>>(x, dy, gamma, stats, resid, dx, rows, C);
     COUNT_LAUNCH();
 }
 
