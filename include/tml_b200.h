@@ -153,6 +153,13 @@ int tml_debug_unet_saved_tensor(TmlUnet* unet, const char* name, int index, size
 /* Tests on a machine without a GPU: while on, tml_unet_create skips the device checks and finalize uploads nothing, so
  * tml_unet_query still replays both walks as a dry run (layout, scratch size, shape validation of every GEMM). */
 void tml_debug_set_host_only(int on);
+/* The fused attention kernels on their own (kernel unit tests): Q [nb][tq][dp], K / V [nb][tkv][dp] dense bf16, dp = 64 or
+ * 128, tq and tkv multiples of 128; channel `lcol` of V must be 1.0 on every key row (the softmax denominator column).
+ * Forward (online softmax): O [nb][tq][dp] bf16, rmax / inv_l [nb][tq] fp32.  With dO (bf16, same shape as O): dQ, and dK / dV
+ * unless both are NULL; ws >= nb*tq*(2*dp + 12) + 512 bytes. */
+int tml_debug_attention(const void* Q, const void* K, const void* V, int nb, int tq, int tkv, int dp, int lcol, float scale,
+                        void* O, float* rmax, float* inv_l, const void* dO, void* dQ, void* dK, void* dV, void* ws,
+                        size_t ws_bytes, void* stream);
 
 /* ---- introspection / test hooks ---- */
 /* number of kernels launched by this library since load: [0] tcgen05 GEMMs, [1] all other kernels */

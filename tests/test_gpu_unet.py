@@ -161,3 +161,75 @@ def test_transposed_a_operand_gemm(dev):
         torch.cuda.synchronize()
         ref = torch.einsum("bkm,bnk->bmn", A.float(), Bt.float())
         assert rel_err(D.float(), ref) < 1e-2, (nb, tq, tk, dp, rel_err(D.float(), ref))
+
+
+def _fused_attention(dev, q, k, v, dout, d, scale, cross=False):
+    """q [nb,tq,dp], k / v [nb,tkv,dp] bf16 with channels >= d zero (v[:, :, d] = 1): runs the fused kernels through
+    tml_debug_attention and returns (O, dQ, dK, dV) as fp32 restricted to the d real channels."""
+    import ctypes as C
+    from tml_image_editing_defense_b200 import _lib
+    lib = _lib.load()
+    nb, tq, dp = q.shape
+    tkv = k.shape[1]
+    O = torch.zeros_like(q)
+    rmax = torch.zeros((nb, tq), device=dev)
+    inv_l = torch.zeros((nb, tq), device=dev)
+    dQ, dK, dV = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    ws = torch.zeros(nb * tq * (2 * dp + 12) + 1024, dtype=torch.uint8, device=dev)
+    _lib.check(lib.tml_debug_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), nb, tq, tkv, dp, d, scale, O.data_ptr(),
+                                       rmax.data_ptr(), inv_l.data_ptr(), dout.data_ptr(), dQ.data_ptr(),
+                                       None if cross else dK.data_ptr(), None if cross else dV.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    return O.float()[..., :d], dQ.float()[..., :d], dK.float()[..., :d], dV.float()[..., :d]
+
+
+@pytest.mark.parametrize("case", ["random", "rising_maxima", "masked_keys"])
+def test_fused_attention_kernels_vs_fp32(dev, case):
+    """mh_attn_fwd_online_kernel / attn_bwd_dq_kernel / attn_bwd_dkv_kernel on their own against fp32 softmax attention and
+    its autograd: random logits; logits that keep growing along the keys (the online softmax has to rescale its TMEM
+    accumulator again and again); and the cross-attention layout (77 real keys in 128 slots, masked through the spare
+    channel, no dK / dV).  Tolerances: bf16 operands and probabilities, fp32 accumulation."""
+    g = torch.Generator().manual_seed(11)
+    nb, tq, d, dp = 6, 256, 40, 64
+    tkv = 128 if case == "masked_keys" else 512
+    scale = d ** -0.5
+    q = torch.zeros((nb, tq, dp))
+    k = torch.zeros((nb, tkv, dp))
+    v = torch.zeros((nb, tkv, dp))
+    q[..., :d] = torch.randn((nb, tq, d), generator=g) * 1.5
+    k[..., :d] = torch.randn((nb, tkv, d), generator=g) * 1.5
+    v[..., :d] = torch.randn((nb, tkv, d), generator=g)
+    if case == "rising_maxima":
+        # logits grow by ~0.1 per key along a common direction (+9 in log2 units per 64-key tile: the exponent reference
+        # moves on every tile); steeper ramps make the rows near one-hot, where the cancellation dP - D limits ANY bf16
+        # backward (0.4 per key: forward still within 2e-2, dQ off by 30 %)
+        u = torch.randn((d,), generator=g)
+        u = u / u.norm()
+        q[..., :d] = q[..., :d] * 0.3 + 4.0 * u
+        k[..., :d] = k[..., :d] * 0.3 + (torch.arange(tkv).float()[None, :, None] * (0.1 / (4.0 * scale))) * u
+    valid = tkv
+    if case == "masked_keys":
+        valid = 77
+        k[:, valid:, :] = 0
+        v[:, valid:, :] = 0
+        q[..., d] = 1.0
+        k[:, valid:, d] = -29952.0
+    v[..., d] = 1.0
+    dout = torch.zeros((nb, tq, dp))
+    dout[..., :d] = torch.randn((nb, tq, d), generator=g)
+    qb, kb, vb, db = (t.to(dev).bfloat16() for t in (q, k, v, dout))
+    O, dQ, dK, dV = _fused_attention(dev, qb, kb, vb, db, d, scale, cross=case == "masked_keys")
+    qr = qb.float()[..., :d].clone().requires_grad_(True)
+    kr = kb.float()[:, :valid, :d].clone().requires_grad_(True)
+    vr = vb.float()[:, :valid, :d].clone().requires_grad_(True)
+    P = torch.softmax(torch.einsum("bqd,bkd->bqk", qr, kr) * scale, dim=-1)
+    Oref = torch.einsum("bqk,bkd->bqd", P, vr)
+    gq, gk, gv = torch.autograd.grad((Oref * db.float()[..., :d]).sum(), [qr, kr, vr])
+    assert not torch.isnan(O).any()
+    assert rel_err(O, Oref.detach()) < 2e-2, rel_err(O, Oref.detach())
+    tol = 1e-1 if case == "rising_maxima" else 4e-2
+    assert rel_err(dQ, gq) < tol, rel_err(dQ, gq)
+    if case != "masked_keys":
+        assert rel_err(dK, gk) < tol, rel_err(dK, gk)
+        assert rel_err(dV, gv) < tol, rel_err(dV, gv)

@@ -108,6 +108,9 @@ SIGNATURES = {
     "tml_debug_unet_saved_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t),
                                               C.POINTER(C.c_int)]),
     "tml_debug_set_host_only": (None, [C.c_int]),
+    "tml_debug_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tml_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "tml_gemm_timing_enable": (None, [C.c_int]),
     "tml_gemm_timing_collect": (None, [C.POINTER(C.c_double)]),

@@ -1112,6 +1112,29 @@ int tml_unet_backward(TmlUnet* u, const float* dout, int B, int h, int w, int ct
 
 void tml_debug_set_host_only(int on) { g_host_only = on != 0; }
 
+int tml_debug_attention(const void* Q, const void* K, const void* V, int nb, int tq, int tkv, int dp, int lcol, float scale,
+                        void* O, float* rmax, float* inv_l, const void* dO, void* dQ, void* dK, void* dV, void* ws,
+                        size_t ws_bytes, void* stream) {
+    if (!Q || !K || !V || !O || !rmax || !inv_l) { set_error("null buffer"); return -1; }
+    if (!attn_fused_supported(tq, tkv, dp)) { set_error("unsupported shape tq=%d tkv=%d dp=%d", tq, tkv, dp); return -1; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RC(launch_attn_fused_fwd(reinterpret_cast<const bf16*>(Q), reinterpret_cast<const bf16*>(K), reinterpret_cast<const bf16*>(V),
+                             nullptr, rmax, inv_l, reinterpret_cast<bf16*>(O), nb, tq, tkv, dp, lcol, scale, st));
+    if (dO != nullptr) {
+        const size_t rows = (size_t)nb * tq;
+        const size_t need = rows * dp * sizeof(bf16) + 256 + (rows * 3 + 8) * sizeof(float);
+        if (!ws || ws_bytes < need || !dQ) { set_error("attention backward needs %zu bytes of scratch", need); return -1; }
+        bf16* dOs = reinterpret_cast<bf16*>(ws);
+        float* Dp = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((rows * dp * sizeof(bf16) + 255) & ~size_t(255)));
+        RC(launch_attn_fused_bwd(reinterpret_cast<const bf16*>(Q), reinterpret_cast<const bf16*>(K), reinterpret_cast<const bf16*>(V),
+                                 reinterpret_cast<const bf16*>(O), reinterpret_cast<const bf16*>(dO), rmax, inv_l, dOs, Dp,
+                                 reinterpret_cast<bf16*>(dQ), reinterpret_cast<bf16*>(dK), reinterpret_cast<bf16*>(dV), nb, tq, tkv,
+                                 dp, scale, st));
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int tml_debug_unet_saved_tensor(TmlUnet* u, const char* name, int index, size_t* offset, int dims[4]) {
     if (!u || !name || !offset || !dims) { set_error("null argument"); return -1; }
     const Tape& tp = u->tape;
