@@ -233,3 +233,44 @@ def test_fused_attention_kernels_vs_fp32(dev, case):
     if case != "masked_keys":
         assert rel_err(dK, gk) < tol, rel_err(dK, gk)
         assert rel_err(dV, gv) < tol, rel_err(dV, gv)
+
+
+def test_diffusion_attack_pgd_loop_native(dev):
+    """DiffusionAttack.run = the reference's PGD loop (main.py:79-135) around the full attack on native kernels: the
+    iterate stays in the eps-ball and the image range, the loss history is finite, and the first update is the fused
+    linf step of the first gradient."""
+    from oracle.decoder_oracle import make_vae_oracle
+    from tests.gpu_check_unet import make_oracle
+    from tml_image_editing_defense_b200 import ops
+    from tml_image_editing_defense_b200.configs import TrainConfig
+    from tml_image_editing_defense_b200.diffusion import DiffusionAttack
+    from tml_image_editing_defense_b200.schedulers import DDIMScheduler
+    from tml_image_editing_defense_b200.unet import UNet2DConditionModel as NativeUNet
+    from tml_image_editing_defense_b200.unet_torch import UNetConfig
+    from tml_image_editing_defense_b200.vae import AutoencoderKL
+    ucfg = UNetConfig(block_out_channels=(64, 128), cross_attention_dim=64, attention_head_dim=8, norm_num_groups=32,
+                      down_has_attn=(True, False), up_has_attn=(False, True))
+    native = NativeUNet(ucfg, device=str(dev)).load_state_dict(make_oracle(ucfg, 21, 2.0).state_dict())
+    vae = AutoencoderKL(device=str(dev)).load_state_dict(make_vae_oracle(0).state_dict())
+    eps, step = 8 / 255, 2 / 255
+    cfg = TrainConfig(norm_type="linf", eps=eps, step_size=step, grad_reps=1, override_from_norm_type=False,
+                      n_optimization_steps=3, device=str(dev), apply_loss_on_images=True, apply_loss_on_latents=False,
+                      perturbation_loss_lambda=1.0, n_denoising_steps_per_iteration=2, n_noise=1)
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(2, 3, 128, 128, generator=g) * 1.6 - 0.8).to(dev)
+    tgt = (torch.rand(1, 3, 128, 128, generator=g) * 2 - 1).to(dev)
+    pe = torch.randn(2, 7, 64, generator=g).to(dev)
+    nz = [torch.randn(2, 4, 16, 16, generator=g).to(dev)]
+    da = DiffusionAttack(cfg, vae, native, DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+    x_adv = da.run(x, tgt, pe, noises=nz)
+    assert len(da.loss_history) == 3 and all(l == l and abs(l) < 1e6 for l in da.loss_history)
+    assert float((x_adv - x).abs().max()) <= eps + 1e-6
+    assert float(x_adv.min()) >= -1.0 and float(x_adv.max()) <= 1.0
+    assert float((x_adv - x).abs().max()) > 0.5 * step
+    g0, _, _, _ = da.compute_grad(x.clone(), pe, x, tgt.expand(2, -1, -1, -1).contiguous(), None, nz)
+    first = ops.pgd_step_linf_(x.clone(), g0.contiguous(), x, eps, step, -1.0, 1.0)
+    import copy
+    cfg1 = copy.copy(cfg)
+    cfg1.n_optimization_steps = 1
+    da1 = DiffusionAttack(cfg1, vae, native, DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+    assert torch.equal(da1.run(x, tgt, pe, noises=nz), first)

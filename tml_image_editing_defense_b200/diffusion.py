@@ -93,3 +93,42 @@ class DiffusionAttack:
             (grad,) = torch.autograd.grad(loss.sum(), [cur])                      # :176
         return grad, loss.detach().mean(), output_image.detach(), {"rec_loss": rec.detach().mean(),
                                                                     "pert_loss": pert.detach().mean()}
+
+    # ------------------------------------------------------------------ main.py:47-142
+    def run(self, source_image: torch.Tensor, target_image: torch.Tensor, prompt_embeds: torch.Tensor,
+            noises: Optional[List[torch.Tensor]] = None, source_mask: Optional[torch.Tensor] = None,
+            vae_noise: Optional[torch.Tensor] = None, callback=None) -> torch.Tensor:
+        """The reference's PGD loop around the diffusion attack (main.py:79-135): per iteration ``grad_reps`` gradient
+        evaluations through the denoising loop, their mean, one ``perturbation_step`` (the fused sm_100a update).
+        ``noises``: the fixed training noises of main.py:60-66 (``n_noise`` seeded N(0,1) latents when omitted)."""
+        from . import ops
+        c = self.cfg
+        x = source_image.to(self.device, torch.float32).contiguous()
+        tgt = target_image.to(self.device, torch.float32).contiguous()
+        if tgt.shape[0] == 1 and x.shape[0] > 1:
+            tgt = tgt.expand(x.shape[0], -1, -1, -1).contiguous()
+        lat_shape = (x.shape[0], 4, x.shape[2] // 8, x.shape[3] // 8)
+        if noises is None:
+            g = torch.Generator(device=self.device).manual_seed(c.seed)
+            noises = [torch.randn(lat_shape, generator=g, device=self.device) for _ in range(max(1, c.n_noise))]
+        self.noises = noises
+        x_adv = x.clone()
+        self.loss_history = []
+        for it in range(c.n_optimization_steps):
+            grads, losses = [], []
+            for _ in range(c.grad_reps):                                        # :88-99
+                g_, loss, _, _ = self.compute_grad(x_adv, prompt_embeds, x, tgt, None, noises, vae_noise)
+                grads.append(g_)
+                losses.append(loss)
+            grad = grads[0] if len(grads) == 1 else torch.stack(grads).mean(dim=0)   # :102
+            mask = source_mask if c.use_segmentation_mask else None
+            if c.norm_type == "linf":                                           # :248-276
+                ops.pgd_step_linf_(x_adv, grad.contiguous(), x, float(c.eps), float(c.step_size), float(c.min_value),
+                                   float(c.max_value))
+            else:
+                ops.pgd_step_l2_(x_adv, grad.contiguous(), x, mask, float(c.eps), float(c.step_size), float(c.min_value),
+                                 float(c.max_value))
+            self.loss_history.append(float(torch.stack(losses).mean()))
+            if callback is not None:
+                callback(it, self.loss_history[-1])
+        return x_adv

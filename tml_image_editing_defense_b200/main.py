@@ -4,6 +4,7 @@ and the image loop of run_all.py:23-93, for the VAE-encoder attack).
     python -m tml_image_editing_defense_b200.main --num_images 64 --max_train_steps 200
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m tml_image_editing_defense_b200.main --num_images 512
     torchrun ... -m tml_image_editing_defense_b200.main --universal        # shared perturbation (old/train_noise.py)
+    python -m tml_image_editing_defense_b200.main --diffusion --num_images 8 --images_per_pass 8 --max_train_steps 50
 
 One process per GPU; rank r immunizes images r::world (no communication; run_all.py:14-21 split the list by
 hand over two GPUs).  Results: `<output_dir>/adversarial_rank{r}.pt` (+ PNGs when torchvision is present, as
@@ -45,7 +46,7 @@ def main(argv=None) -> int:
 
     cfg_vae = SDXL_VAE if args.sdxl else SD15_VAE
     sd = load_checkpoint(args.pretrained_vae_model_name_or_path) if args.pretrained_vae_model_name_or_path \
-        else random_init_state_dict(cfg_vae, seed=args.seed)
+        else random_init_state_dict(cfg_vae, seed=args.seed, include_decoder=args.diffusion)
     vae = AutoencoderKL(cfg_vae, device=dev).load_state_dict(sd)
 
     if args.train_data_dir:
@@ -62,7 +63,45 @@ def main(argv=None) -> int:
     target = torch.randn(lat, generator=g).to(dev)
 
     t0 = time.perf_counter()
-    if args.universal:
+    if args.diffusion:
+        # the reference's default mode (main.py:144-246) with every network on this repo's kernels
+        from .diffusion import DiffusionAttack
+        from .schedulers import DDIMScheduler
+        from .unet import UNet2DConditionModel
+        from .unet_torch import UNet2DConditionModel as TorchUNet
+        if not vae.has_decoder:
+            raise SystemExit("--diffusion needs the VAE decoder weights (decoder.*, post_quant_conv.*)")
+        if args.pretrained_unet_model_name_or_path:
+            usd = load_checkpoint(args.pretrained_unet_model_name_or_path)
+        else:   # random init of the SD-1.5 topology (no network for checkpoints)
+            with torch.device(dev):
+                torch.manual_seed(args.seed)
+                usd = TorchUNet().requires_grad_(False).state_dict()
+        unet = UNet2DConditionModel(device=dev, keep_activations=not args.gradient_checkpointing).load_state_dict(usd)
+        del usd
+        cfg = TrainConfig(norm_type=args.norm_type, eps=args.eps, step_size=args.step_size, grad_reps=args.grad_reps,
+                          min_value=args.min_value, max_value=args.max_value, override_from_norm_type=False,
+                          n_optimization_steps=args.max_train_steps, seed=args.seed, device=dev,
+                          resolution=args.resolution, output_path=out_dir,
+                          n_denoising_steps_per_iteration=args.n_denoising_steps_per_iteration,
+                          guidance_scale=args.guidance_scale)
+        da = DiffusionAttack(cfg, vae, unet, DDIMScheduler(), use_checkpointing=False, unet_dtype=torch.float32)
+        ge = torch.Generator().manual_seed(args.seed + 29)
+        prompt_embeds = torch.randn((2, 77, unet.config.cross_attention_dim), generator=ge).to(dev)   # no CLIP offline
+        target_image = (torch.rand((1, 3, args.resolution, args.resolution), generator=ge) * 2 - 1).to(dev)
+        loader = ShardedImageLoader(ds, max(1, args.images_per_pass), rank, world, dev, fetch=fetch)
+        outs, hist = [], []
+        for _, images, _ in loader:
+            outs.append(da.run(images, target_image, prompt_embeds).cpu())
+            hist = hist or list(da.loss_history)
+        x_adv = torch.cat(outs) if outs else torch.empty((0, 3, args.resolution, args.resolution))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        torch.save({"indices": idx, "x_adv": x_adv}, out_dir / f"adversarial_rank{rank}.pt")
+        print(json.dumps({"rank": rank, "mode": "diffusion", "steps": args.max_train_steps, "images": len(idx),
+                          "seconds": dt, "image_pgd_iters_per_s": len(idx) * args.max_train_steps / dt,
+                          "loss_first": hist[0] if hist else None, "loss_last": hist[-1] if hist else None}), flush=True)
+    elif args.universal:
         images = torch.cat([im for _, im, _ in ShardedImageLoader(ds, max(1, args.train_batch_size), rank, world, dev, fetch=fetch)]) \
             if idx else torch.empty((0, 3, args.resolution, args.resolution), device=dev)
         ucfg = UniversalConfig(grad_reps=args.grad_reps, eps=args.eps, step_size=args.step_size,

@@ -39,6 +39,13 @@ def parse_args(input_args=None):
     p.add_argument("--grad_reps", type=int, default=1)
     p.add_argument("--latent_loss", type=str, default="l2norm", choices=["l2norm", "mse"])
     p.add_argument("--universal", action="store_true", help="Shared-perturbation mode (old/train_noise.py).")
+    p.add_argument("--diffusion", action="store_true",
+                   help="The reference's full attack (main.py:144-246): encode, add_noise, UNet denoising steps with "
+                        "classifier-free guidance, decode, image-space losses -- every network on the sm_100a kernels.")
+    p.add_argument("--pretrained_unet_model_name_or_path", type=str, default=None,
+                   help="--diffusion: torch state dict with diffusers UNet2DConditionModel keys; random init if omitted.")
+    p.add_argument("--n_denoising_steps_per_iteration", type=int, default=4)
+    p.add_argument("--guidance_scale", type=float, default=3.0)   # configs.py default
     p.add_argument("--sdxl", action="store_true", help="SDXL VAE scaling factor (architecture is identical).")
     args = p.parse_args(input_args)
     env_local_rank = int(os.environ.get("LOCAL_RANK", -1))
