@@ -187,7 +187,9 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
     // Small problems (a few tile waves): a narrower column tile can fill the last wave better than the widest one, e.g.
     // 4096 x 1280 (the UNet's 16 x 16 level) is 80 CTA-pair tiles of 256 columns = 2 waves of 74 pairs, but 256 tiles of
     // 160 columns = 2 waves of 148 CTAs at 0.62 of the work per tile.  Cost model: waves x (columns + fixed per-tile cost).
-    static const bool no_bn_heur = getenv("TML_NO_BN_HEUR") && getenv("TML_NO_BN_HEUR")[0] == '1';   // A/B switch
+    // (measured: neutral in situ, 758 vs 805 TFLOP/s in isolation at 4096 x 1280 x 11520 because the narrower tiles lose the
+    // CTA pairs' halved weight traffic -- off unless TML_BN_HEUR=1)
+    static const bool no_bn_heur = !(getenv("TML_BN_HEUR") && getenv("TML_BN_HEUR")[0] == '1');   // experiment switch
     if (!no_bn_heur && op.N > 256 && op.epi_mode == 0 && op.gn_mode == 0 && !op.a_trans && TW * TH > 0 &&
         !(op.stride == 1 && op.ntaps == 9 && (op.OW % 128 == 0 || op.OW == 64))) {   // (halo modes keep their geometry)
         const long sub = (long)op.A_B * (op.OH / TH) * (op.OW / TW);
@@ -356,6 +358,8 @@ int gemm_plan(const GemmOp& op, GemmTiling* t) {
 struct TcParams {
     int mode;  // 0: stride 1 (4-D map c,w,h,b)   1: stride 2 (5-D map c,wpar,w/2,h,b)
     int a_trans;   // A stored [batch][k][m] (3-D map m,k,b; boxes of 64 m x 64 k): MN-major UMMA operand
+    int b_prefetch;   // > 0: L2 prefetch of the weight tile this many k-blocks ahead (weight-streaming layers: few output
+                      // rows, tens of MB of weights coming from HBM once -- the ring alone keeps too few bytes in flight)
     int TW, TH, rows_valid;
     int tiles_w, tiles_h, nimg;
     int n_tiles, BN;
@@ -919,6 +923,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                     tma_load_5d_2sm(sA + size_t(i) * p.TW * 128, &mapA, &full_bar[stage], c0, dw & 1,
                                                     sb[0].ow0 + (dw >> 1), 2 * (sb[0].oh0 + i) + dh, sb[0].img);
                             }
+                            if (p.b_prefetch > 0 && kb + p.b_prefetch < kblocks)
+                                tma_prefetch_l2_3d(&mapB, (kb + p.b_prefetch) * kBlockK, nt * p.BN + int(crank) * (p.BN / 2), 0);
                             tma_load_3d_2sm(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN + int(crank) * (p.BN / 2),
                                             p.b_batched ? sb[0].img : 0);
                         }
@@ -944,6 +950,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                                             sb[sub].ow0 + (dw >> 1), 2 * (sb[sub].oh0 + i) + dh, sb[sub].img);
                         }
                     }
+                    if (p.b_prefetch > 0 && kb + p.b_prefetch < kblocks)
+                        tma_prefetch_l2_3d(&mapB, (kb + p.b_prefetch) * kBlockK, nt * p.BN, 0);
                     tma_load_3d(sB, &mapB, &full_bar[stage], kb * kBlockK, nt * p.BN, p.b_batched ? sb[0].img : 0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -2056,6 +2064,14 @@ int gemm_launch_tc(const GemmOp& op, int num_sms, cudaStream_t stream) {
     p.out_bytes = t.out_bytes;
     p.mode = op.stride == 2 ? 1 : 0;
     p.a_trans = op.a_trans;
+    {   // weight-streaming layers: shared weights of >= 8 MB for at most 8192 output rows (the UNet's 16 x 16 and 8 x 8 levels)
+        // (measured, tools/gpu_r2_pf.sh: no effect at 8 / 24 / 48 k-blocks -- these layers sit on the ~8 TB/s the L2 can hand to
+        // the SMs, 33 B/clk/SM with every weight tile re-read by 16 row tiles, not on HBM latency: off by default)
+        static const int pf = getenv("TML_B_PREFETCH") ? atoi(getenv("TML_B_PREFETCH")) : 0;   // experiment switch
+        const double wbytes = 2.0 * op.N * op.ntaps * op.A_C;
+        const long rows = (long)op.A_B * op.OH * op.OW;
+        p.b_prefetch = (op.B_sBatch == 0 && !t.halo && wbytes >= 8e6 && rows <= 8192) ? pf : 0;
+    }
     p.TW = t.TW; p.TH = t.TH; p.rows_valid = t.rows_valid;
     p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.nimg = op.A_B;
     p.n_tiles = t.n_tiles; p.BN = t.BN; p.mt = t.mt;

@@ -187,6 +187,11 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0,
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // cta_group::2 loads: data lands in the executing CTA's shared memory, the transaction bytes are
 // counted on the LEADER CTA's mbarrier (same offset).
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
