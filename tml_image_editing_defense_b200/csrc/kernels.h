@@ -85,6 +85,7 @@ void launch_posterior_sample_bwd(const float* moments, const float* noise, const
 
 // ---- UNet helpers (unet_kernels.cu; diffusion attack, main.py:229-243) ----
 // GroupNorm(32 groups) for any channel count with C % 32 == 0 and C % 8 == 0 (partials / finalize as above)
+int gng_num_chunks(int HW, int C);   // partial entries per image of the gng_* kernels (a function of HW and C only)
 void launch_gng_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s);
 void launch_gng_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s);
 void launch_gng_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, const float2* mr, const float* gamma,

@@ -215,14 +215,14 @@ GemmOp lin_op(const char* name, const bf16* A, int B, int h, int w, int K, const
     return dense_lin_op(name, A, B, h, w, K, Wm, N, bias, resid, D);
 }
 
-size_t gn_part_bytes(int B, int hw, int C) { return (size_t)B * gn_num_chunks(hw, C) * 32 * 2 * sizeof(float); }
+size_t gn_part_bytes(int B, int hw, int C) { return (size_t)B * gng_num_chunks(hw, C) * 32 * 2 * sizeof(float); }
 
 int ugn_forward(URun& r, const bf16* x, const Norm& n, const GnSaved& g, bf16* y, int hw, int silu, float eps) {
     const size_t m = r.wsa.mark();
     float* part = r.Walloc<float>(gn_part_bytes(r.B, hw, n.C));
     launch_gng_stats(x, part, r.B, hw, n.C, r.st);
     launch_gn_finalize(part, n.gamma, n.beta, r.S<float2>(g.ss), r.S<float2>(g.mr), r.B, hw, n.C, eps,
-                       gn_num_chunks(hw, n.C), r.st);
+                       gng_num_chunks(hw, n.C), r.st);
     launch_gng_apply(x, r.S<float2>(g.ss), y, r.B, hw, n.C, silu, r.st);
     r.wsa.reset(m);
     return 0;
@@ -233,7 +233,7 @@ int ugn_backward(URun& r, const bf16* x, const bf16* dy, const Norm& n, const Gn
     float* part = r.Walloc<float>(gn_part_bytes(r.B, hw, n.C));
     launch_gng_bwd_partial(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), n.gamma, part, r.B, hw, n.C, silu, r.st);
     float2* mm = r.Walloc<float2>((size_t)r.B * 32 * sizeof(float2));
-    launch_gn_bwd_finalize(part, mm, r.B, hw, n.C, gn_num_chunks(hw, n.C), r.st);
+    launch_gn_bwd_finalize(part, mm, r.B, hw, n.C, gng_num_chunks(hw, n.C), r.st);
     launch_gng_bwd_apply(x, dy, r.S<float2>(g.ss), r.S<float2>(g.mr), mm, resid, dx, r.B, hw, n.C, silu, r.st);
     r.wsa.reset(m);
     return 0;

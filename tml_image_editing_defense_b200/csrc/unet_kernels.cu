@@ -53,11 +53,29 @@ __device__ __forceinline__ float u_dsilu(float u) {
 // (C/8 > 256) walk the octets in steps of 256.  Per-channel sums go through shared memory and thread g < 32 adds
 // the channels of its group in a fixed order, so a group may start anywhere inside an octet.
 // ================================================================================================
-int gng_num_chunks(int HW, int C) { return gn_num_chunks(HW, C); }
-static int gng_ppc(int C) { return 32768 / C > 0 ? 32768 / C : 1; }
-static size_t gng_smem(int C) {
-    const int C8 = C >> 3, span = C8 < 256 ? C8 : 256, PL = 256 / span;
-    return (size_t)PL * C * 2 * sizeof(float);
+// Pixels per block.  The UNet's GroupNorms run on small tensors (8 x 8 ... 64 x 64 latents at 320 ... 2560 channels), so
+// what matters is how many blocks and how many loads are in flight, not the streaming rate of one block: a thread owns
+// 4 ... 16 pixels of its channel octet (at least ~64 blocks per image), and the loops below issue kU independent
+// 16-byte loads per tensor before they touch the data (a plain `#pragma unroll` over the guarded pixel loop keeps ONE
+// load in flight per thread: measured 0.2 - 2 TB/s).  The chunking depends on (HW, C) only -- never on the batch --
+// so an image's statistics are bit-identical whatever batch it shares.
+static int gng_pl(int C) { const int C8 = C >> 3, span = C8 < 256 ? C8 : 256; return 256 / span; }
+static int gng_ppc(int HW, int C) {
+    const int PL = gng_pl(C);
+    int per_thread = HW / (PL * 64);
+    per_thread = per_thread < 4 ? 4 : (per_thread > 16 ? 16 : per_thread);
+    return PL * per_thread;
+}
+int gng_num_chunks(int HW, int C) { const int p = gng_ppc(HW, C); return (HW + p - 1) / p; }
+static size_t gng_smem(int C) { return (size_t)gng_pl(C) * C * 2 * sizeof(float); }
+constexpr int kU = 4;   // independent 16-byte loads in flight per thread and tensor
+
+// Sum of the 8 lanes that share a group (lanes 8k .. 8k+7), fixed tree.
+__device__ __forceinline__ float u_sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
 __global__ void __launch_bounds__(256) gng_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW,
@@ -73,13 +91,19 @@ __global__ void __launch_bounds__(256) gng_stats_kernel(const bf16* __restrict__
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
             const bf16* base = x + (size_t)b * HW * C + (size_t)o * 8;
-#pragma unroll 4
-            for (int p = p0 + l; p < p1; p += PL) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
-                float f[8];
-                u_unpack8(u, f);
+            for (int p = p0 + l; p < p1; p += PL * kU) {
+                uint4 u[kU];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+                for (int k = 0; k < kU; ++k)
+                    if (p + k * PL < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + k * PL) * C));
+#pragma unroll
+                for (int k = 0; k < kU; ++k) {
+                    if (p + k * PL >= p1) break;
+                    float f[8];
+                    u_unpack8(u[k], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -89,24 +113,28 @@ __global__ void __launch_bounds__(256) gng_stats_kernel(const bf16* __restrict__
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int g = threadIdx.x, cpg = C / 32;
+    {   // eight threads per group: thread (g, sub) adds channels g*cpg + sub, + 8, ... in order, then a fixed tree
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7, cpg = C / 32;
         float s = 0.f, q = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8)
             for (int ll = 0; ll < PL; ++ll) {
                 s += sm[((size_t)ll * C + c) * 2];
                 q += sm[((size_t)ll * C + c) * 2 + 1];
             }
-        float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
-        out[0] = s;
-        out[1] = q;
+        s = u_sum8(s);
+        q = u_sum8(q);
+        if (sub == 0) {
+            float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+            out[0] = s;
+            out[1] = q;
+        }
     }
 }
 
 void launch_gng_stats(const bf16* x, float* partial, int B, int HW, int C, cudaStream_t s) {
     if (g_dry_run) return;
     dim3 grid(gng_num_chunks(HW, C), B);
-    gng_stats_kernel<<<grid, 256, gng_smem(C), s>>>(x, partial, HW, C, gng_ppc(C));
+    gng_stats_kernel<<<grid, 256, gng_smem(C), s>>>(x, partial, HW, C, gng_ppc(HW, C));
     COUNT_LAUNCH();
 }
 
@@ -119,23 +147,32 @@ __global__ void __launch_bounds__(256) gng_apply_kernel(const bf16* __restrict__
     if (l >= PL) return;
     for (int o = o0; o < C8; o += span) {
         float sc[8], sh[8];
+        {
+            const float4* sp = reinterpret_cast<const float4*>(ss + (size_t)b * C + o * 8);   // 8 (scale, shift) pairs
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float2 v = __ldg(&ss[(size_t)b * C + o * 8 + j]);
-            sc[j] = v.x; sh[j] = v.y;
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = __ldg(sp + j);
+                sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+            }
         }
         const size_t base = (size_t)b * HW * C + (size_t)o * 8;
-#pragma unroll 4
-        for (int p = p0 + l; p < p1; p += PL) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-            float f[8];
-            u_unpack8(u, f);
+        for (int p = p0 + l; p < p1; p += PL * kU) {
+            uint4 u[kU];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float v = fmaf(f[j], sc[j], sh[j]);
-                f[j] = silu ? u_silu(v) : v;
+            for (int k = 0; k < kU; ++k)
+                if (p + k * PL < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + k * PL) * C));
+#pragma unroll
+            for (int k = 0; k < kU; ++k) {
+                if (p + k * PL >= p1) break;
+                float f[8];
+                u_unpack8(u[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = fmaf(f[j], sc[j], sh[j]);
+                    f[j] = silu ? u_silu(v) : v;
+                }
+                *reinterpret_cast<uint4*>(y + base + (size_t)(p + k * PL) * C) = u_pack8(f);
             }
-            *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = u_pack8(f);
         }
     }
 }
@@ -143,7 +180,7 @@ __global__ void __launch_bounds__(256) gng_apply_kernel(const bf16* __restrict__
 void launch_gng_apply(const bf16* x, const float2* ss, bf16* y, int B, int HW, int C, int silu, cudaStream_t s) {
     if (g_dry_run) return;
     dim3 grid(gng_num_chunks(HW, C), B);
-    gng_apply_kernel<<<grid, 256, 0, s>>>(x, ss, y, HW, C, gng_ppc(C), silu);
+    gng_apply_kernel<<<grid, 256, 0, s>>>(x, ss, y, HW, C, gng_ppc(HW, C), silu);
     COUNT_LAUNCH();
 }
 
@@ -163,25 +200,38 @@ __global__ void __launch_bounds__(256) gng_bwd_partial_kernel(const bf16* __rest
     if (l < PL) {
         for (int o = o0; o < C8; o += span) {
             float sc[8], sh[8], s1[8], s2[8];
+            {
+                const float4* sp = reinterpret_cast<const float4*>(ss + (size_t)b * C + o * 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float2 v = __ldg(&ss[(size_t)b * C + o * 8 + j]);
-                sc[j] = v.x; sh[j] = v.y; s1[j] = 0.f; s2[j] = 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = __ldg(sp + j);
+                    sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+                }
             }
-            const size_t base = (size_t)b * HW * C + (size_t)o * 8;
-#pragma unroll 2
-            for (int p = p0 + l; p < p1; p += PL) {
-                const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-                const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
-                float fx[8], fd[8];
-                u_unpack8(ux, fx);
-                u_unpack8(ud, fd);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float u = fmaf(fx[j], sc[j], sh[j]);
-                    const float d = silu ? fd[j] * u_dsilu(u) : fd[j];
-                    s1[j] += d;
-                    s2[j] = fmaf(d, fx[j], s2[j]);
+            for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            const size_t base = (size_t)b * HW * C + (size_t)o * 8;
+            for (int p = p0 + l; p < p1; p += PL * kU) {
+                uint4 ux[kU], ud[kU];
+#pragma unroll
+                for (int k = 0; k < kU; ++k)
+                    if (p + k * PL < p1) {
+                        ux[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + k * PL) * C));
+                        ud[k] = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)(p + k * PL) * C));
+                    }
+#pragma unroll
+                for (int k = 0; k < kU; ++k) {
+                    if (p + k * PL >= p1) break;
+                    float fx[8], fd[8];
+                    u_unpack8(ux[k], fx);
+                    u_unpack8(ud[k], fd);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float u = fmaf(fx[j], sc[j], sh[j]);
+                        const float d = silu ? fd[j] * u_dsilu(u) : fd[j];
+                        s1[j] += d;
+                        s2[j] = fmaf(d, fx[j], s2[j]);
+                    }
                 }
             }
 #pragma unroll
@@ -192,11 +242,11 @@ __global__ void __launch_bounds__(256) gng_bwd_partial_kernel(const bf16* __rest
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int g = threadIdx.x, cpg = C / 32;
+    {   // eight threads per group (see gng_stats_kernel)
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7, cpg = C / 32;
         const float2 m = __ldg(&mr[(size_t)b * 32 + g]);
         float a = 0.f, q = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
             float s1 = 0.f, s2 = 0.f;
             for (int ll = 0; ll < PL; ++ll) {
                 s1 += sm[((size_t)ll * C + c) * 2];
@@ -206,9 +256,13 @@ __global__ void __launch_bounds__(256) gng_bwd_partial_kernel(const bf16* __rest
             a = fmaf(gm, s1, a);
             q = fmaf(gm * m.y, s2 - m.x * s1, q);
         }
-        float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
-        out[0] = a;
-        out[1] = q;
+        a = u_sum8(a);
+        q = u_sum8(q);
+        if (sub == 0) {
+            float* out = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+            out[0] = a;
+            out[1] = q;
+        }
     }
 }
 
@@ -216,7 +270,7 @@ void launch_gng_bwd_partial(const bf16* x, const bf16* dy, const float2* ss, con
                             float* partial, int B, int HW, int C, int silu, cudaStream_t s) {
     if (g_dry_run) return;
     dim3 grid(gng_num_chunks(HW, C), B);
-    gng_bwd_partial_kernel<<<grid, 256, gng_smem(C), s>>>(x, dy, ss, mr, gamma, partial, HW, C, gng_ppc(C), silu);
+    gng_bwd_partial_kernel<<<grid, 256, gng_smem(C), s>>>(x, dy, ss, mr, gamma, partial, HW, C, gng_ppc(HW, C), silu);
     COUNT_LAUNCH();
 }
 
@@ -235,37 +289,50 @@ __global__ void __launch_bounds__(256) gng_bwd_apply_kernel(const bf16* __restri
     if (l >= PL) return;
     for (int o = o0; o < C8; o += span) {
         float sc[8], sh[8], cx[8], c0[8];
+        {
+            const float4* sp = reinterpret_cast<const float4*>(ss + (size_t)b * C + o * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = __ldg(sp + j);
+                sc[2 * j] = v.x; sh[2 * j] = v.y; sc[2 * j + 1] = v.z; sh[2 * j + 1] = v.w;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = o * 8 + j;
-            const float2 v = __ldg(&ss[(size_t)b * C + c]);
             const float2 m = __ldg(&mr[(size_t)b * 32 + c / cpg]);
             const float2 k = __ldg(&mm[(size_t)b * 32 + c / cpg]);
-            sc[j] = v.x; sh[j] = v.y;
             cx[j] = -m.y * m.y * k.y;
             c0[j] = m.y * (m.y * m.x * k.y - k.x);
         }
         const size_t base = (size_t)b * HW * C + (size_t)o * 8;
-#pragma unroll 2
-        for (int p = p0 + l; p < p1; p += PL) {
-            const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-            const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
-            float fx[8], fd[8], fr[8], out[8];
-            u_unpack8(ux, fx);
-            u_unpack8(ud, fd);
-            if (resid != nullptr) {
-                const uint4 ur = __ldg(reinterpret_cast<const uint4*>(resid + base + (size_t)p * C));
-                u_unpack8(ur, fr);
-            }
+        for (int p = p0 + l; p < p1; p += PL * kU) {
+            uint4 ux[kU], ud[kU], ur[kU];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float u = fmaf(fx[j], sc[j], sh[j]);
-                const float d = silu ? fd[j] * u_dsilu(u) : fd[j];
-                float v = fmaf(sc[j], d, fmaf(cx[j], fx[j], c0[j]));
-                if (resid != nullptr) v += fr[j];
-                out[j] = v;
+            for (int k = 0; k < kU; ++k)
+                if (p + k * PL < p1) {
+                    ux[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + k * PL) * C));
+                    ud[k] = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)(p + k * PL) * C));
+                    if (resid != nullptr)
+                        ur[k] = __ldg(reinterpret_cast<const uint4*>(resid + base + (size_t)(p + k * PL) * C));
+                }
+#pragma unroll
+            for (int k = 0; k < kU; ++k) {
+                if (p + k * PL >= p1) break;
+                float fx[8], fd[8], fr[8], out[8];
+                u_unpack8(ux[k], fx);
+                u_unpack8(ud[k], fd);
+                if (resid != nullptr) u_unpack8(ur[k], fr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float u = fmaf(fx[j], sc[j], sh[j]);
+                    const float d = silu ? fd[j] * u_dsilu(u) : fd[j];
+                    float v = fmaf(sc[j], d, fmaf(cx[j], fx[j], c0[j]));
+                    if (resid != nullptr) v += fr[j];
+                    out[j] = v;
+                }
+                *reinterpret_cast<uint4*>(dx + base + (size_t)(p + k * PL) * C) = u_pack8(out);
             }
-            *reinterpret_cast<uint4*>(dx + base + (size_t)p * C) = u_pack8(out);
         }
     }
 }
@@ -274,7 +341,7 @@ void launch_gng_bwd_apply(const bf16* x, const bf16* dy, const float2* ss, const
                           const bf16* resid, bf16* dx, int B, int HW, int C, int silu, cudaStream_t s) {
     if (g_dry_run) return;
     dim3 grid(gng_num_chunks(HW, C), B);
-    gng_bwd_apply_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, mm, resid, dx, HW, C, gng_ppc(C), silu);
+    gng_bwd_apply_kernel<<<grid, 256, 0, s>>>(x, dy, ss, mr, mm, resid, dx, HW, C, gng_ppc(HW, C), silu);
     COUNT_LAUNCH();
 }
 
@@ -493,86 +560,86 @@ void launch_geglu_bwd(const bf16* h, const bf16* dout, bf16* dh, long long rows,
 // -30000 and its softmax numerator underflows to exactly 0; real key rows carry 0 there.
 //   fill: 0 = zeros, 1 = query rows (slot d = 1), 2 = key rows (slot d = -30000 on rows >= tok_valid)
 // ================================================================================================
+// grid = (vectors of one (image, head) / 256, heads, images): no 64-bit division per thread
 __global__ void __launch_bounds__(256) head_split_kernel(const bf16* __restrict__ in, long long ld_in, long long bs_in,
-                                                         int col0, bf16* __restrict__ out, int heads, int tok_src,
-                                                         int tok_valid, int tok_out, int d, int dpad, int fill,
-                                                         long long total) {
-    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (t >= total) return;
-    const int P8 = dpad >> 3;
-    const int oj = (int)(t % P8);
-    long long r = t / P8;
-    const int tk = (int)(r % tok_out);
-    r /= tok_out;
-    const int h = (int)(r % heads);
-    const long long b = r / heads;
+                                                         int col0, bf16* __restrict__ out, int tok_src,
+                                                         int tok_valid, int tok_out, int d, int dpad, int fill) {
+    const unsigned P8 = unsigned(dpad) >> 3;
+    const unsigned t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= unsigned(tok_out) * P8) return;
+    const unsigned tk = t / P8, oj = t - tk * P8;
+    const int h = blockIdx.y, heads = gridDim.y;
+    const size_t b = blockIdx.z;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (oj * 8 < d) {
-        if (tk < tok_valid && tk < tok_src)
-            v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)b * bs_in + (size_t)tk * ld_in + col0 + h * d + oj * 8));
-    } else if (oj * 8 == d) {
+    if (int(oj * 8) < d) {
+        if (int(tk) < tok_valid && int(tk) < tok_src)
+            v = __ldg(reinterpret_cast<const uint4*>(in + b * bs_in + (size_t)tk * ld_in + col0 + h * d + oj * 8));
+    } else if (int(oj * 8) == d) {
         if (fill == 1) v.x = 0x3F80u;                              // bf16 1.0 in the low half
-        else if (fill == 2 && tk >= tok_valid) v.x = 0xC6EAu;      // bf16 -29952
+        else if (fill == 2 && int(tk) >= tok_valid) v.x = 0xC6EAu;  // bf16 -29952
     }
-    *reinterpret_cast<uint4*>(out + (size_t)t * 8) = v;
+    *reinterpret_cast<uint4*>(out + ((b * heads + h) * tok_out) * dpad + (size_t)t * 8) = v;
 }
 
 void launch_head_split(const bf16* in, long long ld_in, long long bs_in, int col0, bf16* out, int B, int heads,
                        int tok_src, int tok_valid, int tok_out, int d, int dpad, int fill, cudaStream_t s) {
     if (g_dry_run) return;
-    const long long total = (long long)B * heads * tok_out * (dpad >> 3);
-    head_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, ld_in, bs_in, col0, out, heads, tok_src,
-                                                                     tok_valid, tok_out, d, dpad, fill, total);
+    const unsigned per = (unsigned)tok_out * (unsigned)(dpad >> 3);
+    head_split_kernel<<<dim3((per + 255) / 256, heads, B), 256, 0, s>>>(in, ld_in, bs_in, col0, out, tok_src, tok_valid,
+                                                                       tok_out, d, dpad, fill);
     COUNT_LAUNCH();
 }
 
-// out[b][t][col0 + h*d + j] = in[(b*heads + h)][t][j], j < d
+// out[b][t][col0 + h*d + j] = in[(b*heads + h)][t][j], j < d.   grid = (vectors of one image / 256, images); the
+// writes of consecutive threads are consecutive (octets of a head, then the next head)
 __global__ void __launch_bounds__(256) head_merge_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
                                                          long long ld_out, long long bs_out, int col0, int heads,
-                                                         int tok, int d, int dpad, long long total) {
-    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (t >= total) return;
-    const int D8 = d >> 3;
-    const int oj = (int)(t % D8);
-    long long r = t / D8;
-    const int h = (int)(r % heads);
-    r /= heads;
-    const int tk = (int)(r % tok);
-    const long long b = r / tok;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * heads + h) * tok + tk) * dpad + oj * 8));
-    *reinterpret_cast<uint4*>(out + (size_t)b * bs_out + (size_t)tk * ld_out + col0 + h * d + oj * 8) = v;
+                                                         int tok, int d, int dpad) {
+    const unsigned D8 = unsigned(d) >> 3;
+    const unsigned t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= unsigned(tok) * unsigned(heads) * D8) return;
+    const unsigned r = t / D8, oj = t - r * D8;
+    const unsigned tk = r / unsigned(heads), h = r - tk * unsigned(heads);
+    const size_t b = blockIdx.y;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((b * heads + h) * tok + tk) * dpad + oj * 8));
+    *reinterpret_cast<uint4*>(out + b * bs_out + (size_t)tk * ld_out + col0 + h * d + oj * 8) = v;
 }
 
 void launch_head_merge(const bf16* in, bf16* out, long long ld_out, long long bs_out, int col0, int B, int heads,
                        int tok, int d, int dpad, cudaStream_t s) {
     if (g_dry_run) return;
-    const long long total = (long long)B * tok * heads * (d >> 3);
-    head_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, ld_out, bs_out, col0, heads, tok, d, dpad,
-                                                                     total);
+    const unsigned per = (unsigned)tok * (unsigned)heads * (unsigned)(d >> 3);
+    head_merge_kernel<<<dim3((per + 255) / 256, B), 256, 0, s>>>(in, out, ld_out, bs_out, col0, heads, tok, d, dpad);
     COUNT_LAUNCH();
 }
 
 // ================================================================================================
 // Column-block copy (skip-connection concatenation and its split in the backward), elementwise add.
 // ================================================================================================
-// out[r][oc0 + j] = in[r][ic0 + j],  j < ncols (ncols, offsets, strides multiples of 8)
+// out[r][oc0 + j] = in[r][ic0 + j],  j < ncols (ncols, offsets, strides multiples of 8).  Index = 32-bit when the
+// vector count allows it (always, at the UNet's sizes): a 64-bit division per 16-byte copy is most of the kernel.
+template <typename I>
 __global__ void __launch_bounds__(256) copy_cols_kernel(const bf16* __restrict__ in, long long ld_in, int ic0,
                                                         bf16* __restrict__ out, long long ld_out, int oc0, int ncols,
                                                         long long total) {
-    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (t >= total) return;
-    const int N8 = ncols >> 3;
-    const long long r = t / N8;
-    const int o = (int)(t - r * N8);
-    *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + oc0 + o * 8) =
-        __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld_in + ic0 + o * 8));
+    const I t = (I)blockIdx.x * 256 + threadIdx.x;
+    if ((long long)t >= total) return;
+    const I N8 = (I)(ncols >> 3);
+    const I r = t / N8;
+    const I o = t - r * N8;
+    *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + oc0 + (size_t)o * 8) =
+        __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld_in + ic0 + (size_t)o * 8));
 }
 
 void launch_copy_cols(const bf16* in, long long ld_in, int ic0, bf16* out, long long ld_out, int oc0, int ncols,
                       long long rows, cudaStream_t s) {
     if (g_dry_run) return;
     const long long total = rows * (ncols >> 3);
-    copy_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, ld_in, ic0, out, ld_out, oc0, ncols, total);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (total < (1ll << 31))
+        copy_cols_kernel<unsigned><<<blocks, 256, 0, s>>>(in, ld_in, ic0, out, ld_out, oc0, ncols, total);
+    else
+        copy_cols_kernel<long long><<<blocks, 256, 0, s>>>(in, ld_in, ic0, out, ld_out, oc0, ncols, total);
     COUNT_LAUNCH();
 }
 
