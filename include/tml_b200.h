@@ -197,6 +197,9 @@ int tml_debug_gemm(const TmlGemmDesc* d, void* stream);
 int tml_debug_gn_tiles_per_image(int OH, int OW);
 /* the same for one specific op (the operand-swapped 3x3 kernel reduces gn_mode 2 per 64-pixel segment) */
 int tml_debug_gn_chunks_per_image(const TmlGemmDesc* d);
+/* partial entries per image of the UNet's general GroupNorm kernels (gng_*): a function of the pixel count and the
+   channel count only -- never of the batch -- so an image's statistics do not depend on the batch it shares */
+int tml_debug_unet_gn_chunks_per_image(int HW, int C);
 /* Offsets (bytes into `saved`) and [B,H,W,C] dims of the bf16 NHWC activations the forward keeps:
  * "conv_in", "resnet_h1"/"resnet_out" (index = resnet in forward order), "down_out", "attn_qkv",
  * "attn_P" ([B,tok,tok,1]), "attn_out". */

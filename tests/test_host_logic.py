@@ -85,6 +85,23 @@ def test_partial_sum_geometry_of_the_fused_reductions():
     assert n(_conv_desc(2, 16, 16, 128, 256, 1, taps=1)) == lib.tml_debug_gn_tiles_per_image(16, 16)  # 1x1: pixel-major
 
 
+def test_unet_groupnorm_chunking_is_batch_independent_and_fine_grained():
+    """The UNet's general GroupNorm kernels (csrc/unet_kernels.cu: gng_*) split an image into pixel chunks that depend on
+    (HW, C) only -- the entry point takes no batch -- with 4 ... 16 pixels per thread: at least 64 blocks per image at the
+    SD-1.5 levels that have that many pixels (a coarser split left the 8x8 / 16x16 levels at 48-176 blocks per launch)."""
+    from tml_image_editing_defense_b200 import _lib
+    lib = _lib.load()
+    n = lib.tml_debug_unet_gn_chunks_per_image
+    for hw, c in [(4096, 320), (4096, 640), (4096, 960), (1024, 640), (1024, 1280), (1024, 1920), (256, 1280), (256, 2560)]:
+        pl = 256 // min(c // 8, 256)                       # pixel lanes of a 256-thread block
+        chunks = n(hw, c)
+        ppc = -(-hw // chunks)                             # ceil: pixels per chunk (the last chunk may be ragged)
+        assert chunks >= 64, (hw, c, chunks)
+        assert 4 * pl <= ppc <= 16 * pl, (hw, c, chunks, ppc, pl)
+    assert n(64, 1280) == 16 and n(64, 2560) == 16         # 8x8 level: 4 pixels per thread
+    assert n(0, 320) == -1 and n(64, 100) == -1            # bad shapes are rejected, not guessed
+
+
 @pytest.mark.parametrize("ci,co", [(8, 16), (16, 8)])
 def test_pack_forward_s1_matches_conv2d(ci, co):
     g = torch.Generator().manual_seed(0)

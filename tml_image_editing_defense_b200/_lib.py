@@ -120,6 +120,7 @@ SIGNATURES = {
     "tml_debug_gemm": (C.c_int, [C.POINTER(TmlGemmDesc), C.c_void_p]),
     "tml_debug_gn_tiles_per_image": (C.c_int, [C.c_int, C.c_int]),
     "tml_debug_gn_chunks_per_image": (C.c_int, [C.c_void_p]),
+    "tml_debug_unet_gn_chunks_per_image": (C.c_int, [C.c_int, C.c_int]),
     "tml_debug_saved_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "tml_debug_set_grad_dump": (None, [C.c_void_p, C.c_size_t, C.c_int]),
     "tml_debug_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),

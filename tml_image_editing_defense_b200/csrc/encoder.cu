@@ -533,6 +533,7 @@ int tml_debug_saved_tensor(TmlEncoder* e, const char* name, int index, size_t* o
 }
 
 int tml_debug_gn_tiles_per_image(int OH, int OW) { return gemm_gn_tiles_per_image(OH, OW); }
+int tml_debug_unet_gn_chunks_per_image(int HW, int C) { return (HW > 0 && C > 0 && C % 32 == 0 && C % 8 == 0) ? gng_num_chunks(HW, C) : -1; }
 
 int tml_debug_pack_conv3x3(const float* w, int Co, int Ci, int mode, uint16_t* out, int* ntaps, int* dh, int* dw) {
     std::vector<uint16_t> h;
